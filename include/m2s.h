@@ -1,0 +1,149 @@
+/* m2s.h — C ABI of libm2s.so, the B200-native (sm_100a) replacement for the hot path of the Rust
+ * crate Azkellas/mesh_to_sdf v0.4.0: nearest-triangle distance + Raycast/Normal sign behind
+ * `generate_grid_sdf` and `generate_sdf`.
+ *
+ * The reference has no FFI of its own: its boundary is the crate's public Rust API
+ * (mesh_to_sdf/src/lib.rs:146-148 re-exports). Each entry point below cites the reference item it
+ * replaces; the Rust facade that binds them is in rust/mesh_to_sdf/ (source) and INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every buffer; nothing is retained after return;
+ *   - vertices / queries are packed xyz float32 (what the facade reads through Point::x()/y()/z(),
+ *     src/point.rs:46-56); triangles are already expanded u32 index triples
+ *     (Topology::get_triangles, src/lib.rs:175-193 — the facade / m2s_expand_topology does that);
+ *   - grid output index = z + y*nz + x*ny*nz (Grid::get_cell_idx, src/grid.rs:122-124);
+ *   - every error is a status code (the reference panics; the facade maps non-OK to panic!);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call returns
+ *     M2S_ENODEV / M2S_ECUDA.
+ */
+#ifndef M2S_H
+#define M2S_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M2S_ABI_VERSION 1
+
+typedef enum m2s_status {
+    M2S_OK = 0,
+    M2S_EINVAL = 1, /* bad argument (null pointer, unknown enum, zero cell count …)              */
+    M2S_EINDEX = 2, /* a triangle index >= nv   (reference: slice index panic)                    */
+    M2S_ENAN = 3,   /* non-finite input / NaN distance (reference: panic "NaN distance" lib.rs:257)*/
+    M2S_ECUDA = 4,  /* CUDA runtime error, see m2s_last_error                                     */
+    M2S_ENCCL = 5,  /* reserved                                                                   */
+    M2S_ENODEV = 6, /* no usable CUDA device                                                      */
+    M2S_EEMPTY = 7  /* Rtree / RtreeBvh on a mesh without triangles (rtree.rs:117 panics;
+                       rtree_bvh.rs:104-106 returns an empty Vec — the facade handles both)       */
+} m2s_status;
+
+/* SignMethod, src/lib.rs:204-216 (declaration order; Raycast is #[default]). */
+typedef enum m2s_sign_method { M2S_SIGN_RAYCAST = 0, M2S_SIGN_NORMAL = 1 } m2s_sign_method;
+
+/* AccelerationMethod, src/lib.rs:224-239. `sign` is only read for NONE and BVH. */
+typedef enum m2s_accel_method {
+    M2S_ACCEL_NONE = 0,
+    M2S_ACCEL_BVH = 1,
+    M2S_ACCEL_RTREE = 2,
+    M2S_ACCEL_RTREE_BVH = 3 /* #[default] */
+} m2s_accel_method;
+
+/* Topology, src/lib.rs:151-167. */
+typedef enum m2s_topology { M2S_TRIANGLE_LIST = 0, M2S_TRIANGLE_STRIP = 1 } m2s_topology;
+
+typedef struct m2s_ctx m2s_ctx; /* opaque: device(s), streams, scratch arenas */
+
+/* Phase timings of the last call, milliseconds, measured with CUDA events on the context's stream
+ * (replaces the reference's log::info! phase timers, src/generate/grid.rs:303-307,342-346,369-373). */
+typedef struct m2s_timings {
+    float h2d_ms;   /* host -> device copies (0 for the *_device entry points)             */
+    float build_ms; /* triangle records, Morton sort, LBVH hierarchy + refit               */
+    float sign_ms;  /* raycast row toggles + scan (grid) / per-query ray walks (points)    */
+    float dist_ms;  /* nearest-triangle kernel (sign applied in its epilogue for grids)    */
+    float d2h_ms;   /* device -> host copy of the result                                   */
+    float total_ms; /* first event to last event                                           */
+} m2s_timings;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+/* Create a context on `n_devices` CUDA devices (`devices == NULL || n_devices == 0` -> device 0).
+ * With more than one device, m2s_generate_grid_sdf shards the grid by slabs along x (the slowest
+ * axis of get_cell_idx) and m2s_generate_sdf shards the queries by contiguous ranges. */
+m2s_status m2s_create(const int* devices, int n_devices, m2s_ctx** out);
+
+/* Same, single device, but all work is enqueued on the caller's `cudaStream_t` (passed as void*;
+ * NULL = the legacy default stream). Lets a host framework time / order the library's work with
+ * its own events. */
+m2s_status m2s_create_on_stream(int device, void* cuda_stream, m2s_ctx** out);
+
+void m2s_destroy(m2s_ctx* ctx);
+
+/* Human-readable description of the last non-OK status on this context ("" if none). */
+const char* m2s_last_error(const m2s_ctx* ctx);
+
+m2s_status m2s_last_timings(const m2s_ctx* ctx, m2s_timings* out);
+
+/* Number of kernels this library launched on behalf of `ctx` since creation (bench.py's gpu_launches). */
+uint64_t m2s_launch_count(const m2s_ctx* ctx);
+
+int m2s_abi_version(void);
+
+/* Number of devices the context drives. */
+int m2s_device_count(const m2s_ctx* ctx);
+
+/* ---- host-buffer entry points: the drop-in boundary ----------------------------------------------- */
+
+/* generate_grid_sdf(vertices, indices, grid, sign_method) -> Vec<f32>
+ *   replaces src/generate/grid.rs:265-378 (generate_preheap :383-457, generate_heap :464-490,
+ *   propagate_heap :495-558, compute_raycasts :568-642).
+ * first_cell / cell_size / cell_count are Grid's three fields (src/grid.rs:30-37).
+ * `out` has nx*ny*nz floats. nt == 0 fills f32::MAX (what the reference's un-seeded grid returns). */
+m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv,
+                                 const uint32_t* tri_idx, uint64_t nt, const float first_cell[3],
+                                 const float cell_size[3], const uint64_t cell_count[3], int sign_method,
+                                 float* out);
+
+/* generate_sdf(vertices, indices, query_points, acceleration_method) -> Vec<f32>
+ *   replaces src/lib.rs:291-311 and the four drivers it dispatches to:
+ *   generic/default.rs:11-74 (NONE), generic/bvh.rs:52-145 + bvh_ext.rs (BVH),
+ *   generic/rtree.rs:87-126 (RTREE), generic/rtree_bvh.rs:79-174 (RTREE_BVH).
+ * `out` has nq floats, in query order. nt == 0: NONE/BVH fill f32::MAX per query; RTREE and
+ * RTREE_BVH return M2S_EEMPTY without touching `out`. */
+m2s_status m2s_generate_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx,
+                            uint64_t nt, const float* queries_xyz, uint64_t nq, int accel_method,
+                            int sign_method, float* out);
+
+/* ---- device-buffer entry points (single-device contexts) --------------------------------------------
+ * Same semantics, but every pointer is a device pointer on the context's device and all work is
+ * only enqueued on the context's stream (no host synchronisation on the success path except one
+ * 64-byte status read-back after the build). The grid variant computes the slab
+ * x in [x_begin, x_end) of the full grid and writes it at out_slab[(x - x_begin)*ny*nz + y*nz + z]:
+ * this is the per-rank call of the multi-GPU path (one process per GPU, slabs along x). */
+m2s_status m2s_generate_grid_sdf_device(m2s_ctx* ctx, const float* d_verts_xyz, uint64_t nv,
+                                        const uint32_t* d_tri_idx, uint64_t nt, const float first_cell[3],
+                                        const float cell_size[3], const uint64_t cell_count[3],
+                                        int sign_method, uint64_t x_begin, uint64_t x_end, float* d_out_slab);
+
+m2s_status m2s_generate_sdf_device(m2s_ctx* ctx, const float* d_verts_xyz, uint64_t nv,
+                                   const uint32_t* d_tri_idx, uint64_t nt, const float* d_queries_xyz,
+                                   uint64_t nq, int accel_method, int sign_method, float* d_out);
+
+/* ---- host-side helpers the facade shares with the tests --------------------------------------------- */
+
+/* Topology::get_triangles, src/lib.rs:175-193. `indices == NULL` is `None` (0..nv). index_bytes is 2
+ * (u16) or 4 (u32). Returns the triangle count; writes 3*count u32 when out != NULL.
+ * TriangleList drops a trailing partial tuple; TriangleStrip windows are not winding-flipped. */
+uint64_t m2s_expand_topology(int topology, const void* indices, int index_bytes, uint64_t n_indices,
+                             uint64_t nv, uint32_t* out);
+
+/* Grid::from_bounding_box, src/grid.rs:59-74. */
+void m2s_grid_from_bounding_box(const float bbox_min[3], const float bbox_max[3],
+                                const uint64_t cell_count[3], float first_cell[3], float cell_size[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M2S_H */

@@ -1,0 +1,413 @@
+// LBVH build on the GPU: triangle records -> 63-bit Morton keys -> radix sort -> Karras hierarchy
+// over leaves of K consecutive sorted triangles -> bottom-up refit.
+//
+// Replaces the reference's per-call acceleration-structure builds: bvh::Bvh::build_par
+// (mesh_to_sdf/src/generate/grid.rs:95-111, generic/bvh.rs:62-74, generic/rtree_bvh.rs:108-116) and
+// rstar::RTree::bulk_load (generic/rtree.rs:111, generic/rtree_bvh.rs:118). Leaf boxes are the
+// reference's padded triangle boxes (geo::triangle_bounding_box, src/geo.rs:4-22).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "m2s_geom.cuh"
+#include "m2s_internal.h"
+
+namespace m2s {
+
+cudaError_t DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) {
+        cudaError_t e = cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (e != cudaSuccess) return e;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return e;
+    }
+    cap = want;
+    return cudaSuccess;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+namespace {
+
+// order-preserving float <-> int mapping for atomicMin/atomicMax
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_status_init(BuildStatus* st) {
+    if (threadIdx.x == 0) {
+        st->bad_index = 0;
+        st->nonfinite = 0;
+        st->n_degenerate = 0;
+        st->stack_overflow = 0;
+        st->nan_distance = 0;
+        for (int i = 0; i < 3; ++i) {
+            st->lo[i] = f2ord(INFINITY);
+            st->hi[i] = f2ord(-INFINITY);
+        }
+    }
+}
+
+// K1: gather vertices by index, write the 48-byte record (original order), the padded AABB
+// (geo.rs:4-22) and reduce the scene bounds. One thread per triangle; float4 stores are coalesced.
+__global__ void __launch_bounds__(256)
+k_tri_setup(const float* __restrict__ verts, uint32_t nv, const uint32_t* __restrict__ tris, uint32_t nt,
+            float4* __restrict__ rec, float4* __restrict__ tri_lo, float4* __restrict__ tri_hi,
+            BuildStatus* __restrict__ st) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (t < nt) {
+        uint32_t i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+        if (i0 >= nv || i1 >= nv || i2 >= nv) {
+            atomicExch(&st->bad_index, 1);
+            i0 = i1 = i2 = 0;  // keep going with harmless data; the host reports M2S_EINDEX
+        }
+        const f3 a = {verts[3 * i0], verts[3 * i0 + 1], verts[3 * i0 + 2]};
+        const f3 b = {verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]};
+        const f3 c = {verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]};
+        const f3 n = v_cross(v_sub(b, a), v_sub(c, a));
+        rec[3 * t + 0] = make_float4(a.x, a.y, a.z, b.x);
+        rec[3 * t + 1] = make_float4(b.y, b.z, c.x, c.y);
+        rec[3 * t + 2] = make_float4(c.z, n.x, n.y, n.z);
+        const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(b.x) && isfinite(b.y) &&
+                         isfinite(b.z) && isfinite(c.x) && isfinite(c.y) && isfinite(c.z);
+        if (!fin) atomicExch(&st->nonfinite, 1);
+        const bool degen = v_eq(a, b) || v_eq(b, c) || v_eq(a, c);
+        if (degen) atomicAdd(&st->n_degenerate, 1);
+        const float EPS = 0.0001f;  // geo.rs:5
+        lo[0] = fsub(fminf(a.x, fminf(b.x, c.x)), EPS);
+        lo[1] = fsub(fminf(a.y, fminf(b.y, c.y)), EPS);
+        lo[2] = fsub(fminf(a.z, fminf(b.z, c.z)), EPS);
+        hi[0] = fadd(fmaxf(a.x, fmaxf(b.x, c.x)), EPS);
+        hi[1] = fadd(fmaxf(a.y, fmaxf(b.y, c.y)), EPS);
+        hi[2] = fadd(fmaxf(a.z, fmaxf(b.z, c.z)), EPS);
+        tri_lo[t] = make_float4(lo[0], lo[1], lo[2], degen ? 1.0f : 0.0f);
+        tri_hi[t] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        if (!fin) {
+            for (int i = 0; i < 3; ++i) {
+                lo[i] = INFINITY;
+                hi[i] = -INFINITY;
+            }
+        }
+    }
+    // warp reduce, one atomic per warp and axis
+    for (int i = 0; i < 3; ++i) {
+        float l = lo[i], h = hi[i];
+        for (int o = 16; o; o >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if ((threadIdx.x & 31) == 0 && l <= h) {
+            atomicMin(&st->lo[i], f2ord(l));
+            atomicMax(&st->hi[i], f2ord(h));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__device__ __forceinline__ uint64_t morton63(float x, float y, float z, const BuildStatus* st) {
+    const float lo[3] = {ord2f(st->lo[0]), ord2f(st->lo[1]), ord2f(st->lo[2])};
+    const float hi[3] = {ord2f(st->hi[0]), ord2f(st->hi[1]), ord2f(st->hi[2])};
+    const float p[3] = {x, y, z};
+    uint32_t q[3];
+    for (int i = 0; i < 3; ++i) {
+        float ext = hi[i] - lo[i];
+        float u = ext > 0.0f ? (p[i] - lo[i]) / ext : 0.0f;
+        u = fminf(fmaxf(u, 0.0f), 1.0f);
+        if (!(u == u)) u = 0.0f;
+        q[i] = min((uint32_t)(u * 2097152.0f), 2097151u);
+    }
+    return (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+}
+
+// K2: Morton key of the centre of the padded box.
+__global__ void __launch_bounds__(256)
+k_tri_morton(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi, uint32_t nt,
+             const BuildStatus* __restrict__ st, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const float4 l = tri_lo[t], h = tri_hi[t];
+    keys[t] = morton63(0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z), st);
+    vals[t] = t;
+}
+
+__global__ void __launch_bounds__(256)
+k_point_morton(const float* __restrict__ q, uint32_t nq, const BuildStatus* __restrict__ st,
+               uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    keys[i] = morton63(q[3 * i], q[3 * i + 1], q[3 * i + 2], st);
+    vals[i] = i;
+}
+
+// query bounds (so that query Morton codes use a box that contains the queries) + finite check
+__global__ void __launch_bounds__(256)
+k_point_bounds(const float* __restrict__ q, uint32_t nq, BuildStatus* __restrict__ st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (i < nq) {
+        const float x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            lo[0] = hi[0] = x;
+            lo[1] = hi[1] = y;
+            lo[2] = hi[2] = z;
+        } else {
+            atomicExch(&st->nonfinite, 1);
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        float l = lo[k], h = hi[k];
+        for (int o = 16; o; o >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if ((threadIdx.x & 31) == 0 && l <= h) {
+            atomicMin(&st->lo[k], f2ord(l));
+            atomicMax(&st->hi[k], f2ord(h));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_point_gather(const float* __restrict__ q, const uint32_t* __restrict__ perm, uint32_t nq,
+               float4* __restrict__ q_sorted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const uint32_t s = perm[i];
+    q_sorted[i] = make_float4(q[3 * s], q[3 * s + 1], q[3 * s + 2], __uint_as_float(s));
+}
+
+// K4a: permute the records into leaf (sorted) order.
+__global__ void __launch_bounds__(256)
+k_tri_permute(const float4* __restrict__ rec, const float4* __restrict__ tri_lo,
+              const uint32_t* __restrict__ order, uint32_t nt, float4* __restrict__ rec_sorted,
+              uint32_t* __restrict__ tri_id_sorted) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nt) return;
+    const uint32_t t = order[j];
+    rec_sorted[3 * j + 0] = rec[3 * t + 0];
+    rec_sorted[3 * j + 1] = rec[3 * t + 1];
+    rec_sorted[3 * j + 2] = rec[3 * t + 2];
+    tri_id_sorted[j] = t | (tri_lo[t].w != 0.0f ? TRI_DEGEN_BIT : 0u);
+}
+
+// Karras 2012 delta over the leaf keys (leaf l's key = key of its first sorted triangle).
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, int i, int j) {
+    if (j < 0 || j >= nleaf) return -1;
+    const uint64_t a = keys[(size_t)i * K], b = keys[(size_t)j * K];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+// K4b: one thread per internal node: children + parent links.
+__global__ void __launch_bounds__(256)
+k_hierarchy(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, float4* __restrict__ nodes,
+            uint32_t* __restrict__ leaf_parent, uint32_t* __restrict__ node_parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nleaf - 1) return;
+    const int d = (delta(keys, K, nleaf, i, i + 1) - delta(keys, K, nleaf, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, K, nleaf, i, i - d);
+    int lmax = 2;
+    while (delta(keys, K, nleaf, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, K, nleaf, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, K, nleaf, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, K, nleaf, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    uint32_t left, right;
+    if (lo == gamma) {
+        left = LEAF_BIT | (uint32_t)gamma;
+        leaf_parent[gamma] = ((uint32_t)i << 1);
+    } else {
+        left = (uint32_t)gamma;
+        node_parent[gamma] = ((uint32_t)i << 1);
+    }
+    if (hi == gamma + 1) {
+        right = LEAF_BIT | (uint32_t)(gamma + 1);
+        leaf_parent[gamma + 1] = ((uint32_t)i << 1) | 1u;
+    } else {
+        right = (uint32_t)(gamma + 1);
+        node_parent[gamma + 1] = ((uint32_t)i << 1) | 1u;
+    }
+    // boxes are filled by the refit; store the refs now (degenerate bits are OR-ed in by the refit).
+    nodes[4 * (size_t)i + 0].w = __uint_as_float(left);
+    nodes[4 * (size_t)i + 2].w = __uint_as_float(right);
+    if (i == 0) node_parent[0] = 0xffffffffu;
+}
+
+// K4c: bottom-up refit. One thread per leaf; the second thread to reach a node continues upwards.
+__global__ void __launch_bounds__(256)
+k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
+        const uint32_t* __restrict__ order, uint32_t nt, uint32_t K, int nleaf, float4* nodes,
+        const uint32_t* __restrict__ leaf_parent, const uint32_t* __restrict__ node_parent,
+        uint32_t* __restrict__ node_flag) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaf) return;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool degen = false;
+    const uint32_t b = (uint32_t)l * K, e = min(nt, b + K);
+    for (uint32_t j = b; j < e; ++j) {
+        const uint32_t t = order[j];
+        const float4 tl = tri_lo[t], th = tri_hi[t];
+        lo[0] = fminf(lo[0], tl.x); lo[1] = fminf(lo[1], tl.y); lo[2] = fminf(lo[2], tl.z);
+        hi[0] = fmaxf(hi[0], th.x); hi[1] = fmaxf(hi[1], th.y); hi[2] = fmaxf(hi[2], th.z);
+        degen |= (tl.w != 0.0f);
+    }
+    if (nleaf == 1) return;  // the root is this leaf; nothing to refit
+    uint32_t link = leaf_parent[l];
+    bool first_level = true;
+    for (;;) {
+        const uint32_t p = link >> 1, side = link & 1u;
+        float4* nd = nodes + 4 * (size_t)p;
+        // write my box into my side of the parent (the child ref lives in .w of n0 / n2, each
+        // written only by its own side)
+        float4* mine = nd + 2 * side;
+        uint32_t ref = __float_as_uint(mine[0].w);
+        if (first_level && degen) ref |= LEAF_DEGEN_BIT;
+        mine[0] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(ref));
+        mine[1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        first_level = false;
+        __threadfence();
+        if (atomicAdd(&node_flag[p], 1u) == 0u) return;  // sibling not there yet
+        __threadfence();
+        // both children present: union and go up
+        const volatile float4* vn = nd;
+        float4 a0 = make_float4(vn[0].x, vn[0].y, vn[0].z, 0.f), a1 = make_float4(vn[1].x, vn[1].y, vn[1].z, 0.f);
+        float4 b0 = make_float4(vn[2].x, vn[2].y, vn[2].z, 0.f), b1 = make_float4(vn[3].x, vn[3].y, vn[3].z, 0.f);
+        lo[0] = fminf(a0.x, b0.x); lo[1] = fminf(a0.y, b0.y); lo[2] = fminf(a0.z, b0.z);
+        hi[0] = fmaxf(a1.x, b1.x); hi[1] = fmaxf(a1.y, b1.y); hi[2] = fmaxf(a1.z, b1.z);
+        link = node_parent[p];
+        if (link == 0xffffffffu) return;  // root done
+    }
+}
+
+}  // namespace
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+#define CK(x)                          \
+    do {                               \
+        cudaError_t e__ = (x);         \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+// Builds records + LBVH for (d_verts, d_tris) on d.stream.
+cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
+                         uint32_t K) {
+    cudaStream_t s = d.stream;
+    CK(d.status.ensure(sizeof(BuildStatus)));
+    BuildStatus* st = d.status.as<BuildStatus>();
+    k_status_init<<<1, 32, 0, s>>>(st);
+    d.launches++;
+    d.bvh = Bvh{};
+    d.bvh.nt = (uint32_t)nt;
+    d.bvh.leaf_size = K;
+    d.bvh.st = st;
+    if (nt == 0) return cudaGetLastError();
+
+    const uint32_t nleaf = (uint32_t)((nt + K - 1) / K);
+    CK(d.rec_orig.ensure(nt * 48));
+    CK(d.rec_sorted.ensure(nt * 48));
+    CK(d.tri_lo.ensure(nt * 16));
+    CK(d.tri_hi.ensure(nt * 16));
+    CK(d.keys_in.ensure(nt * 8));
+    CK(d.keys_out.ensure(nt * 8));
+    CK(d.vals_in.ensure(nt * 4));
+    CK(d.vals_out.ensure(nt * 4));
+    CK(d.tri_id_sorted.ensure(nt * 4));
+    CK(d.nodes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * 64));
+    CK(d.leaf_parent.ensure((size_t)nleaf * 4));
+    CK(d.node_parent.ensure((size_t)nleaf * 4));
+    CK(d.node_flag.ensure((size_t)nleaf * 4));
+
+    const unsigned bs = 256;
+    k_tri_setup<<<blocks_for(nt, bs), bs, 0, s>>>(d_verts, (uint32_t)nv, d_tris, (uint32_t)nt,
+                                                  d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
+                                                  d.tri_hi.as<float4>(), st);
+    k_tri_morton<<<blocks_for(nt, bs), bs, 0, s>>>(d.tri_lo.as<float4>(), d.tri_hi.as<float4>(), (uint32_t)nt, st,
+                                                   d.keys_in.as<uint64_t>(), d.vals_in.as<uint32_t>());
+    d.launches += 2;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.keys_in.as<uint64_t>(), d.keys_out.as<uint64_t>(),
+                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, 63, s));
+    CK(d.cub_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(d.cub_tmp.p, tmp_bytes, d.keys_in.as<uint64_t>(), d.keys_out.as<uint64_t>(),
+                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, 63, s));
+    d.launches += 8;  // CUB onesweep: histogram + 8 digit passes (counted approximately)
+    k_tri_permute<<<blocks_for(nt, bs), bs, 0, s>>>(d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
+                                                    d.vals_out.as<uint32_t>(), (uint32_t)nt,
+                                                    d.rec_sorted.as<float4>(), d.tri_id_sorted.as<uint32_t>());
+    d.launches++;
+    if (nleaf > 1) {
+        CK(cudaMemsetAsync(d.node_flag.p, 0, (size_t)nleaf * 4, s));
+        k_hierarchy<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.keys_out.as<uint64_t>(), K, (int)nleaf,
+                                                             d.nodes.as<float4>(), d.leaf_parent.as<uint32_t>(),
+                                                             d.node_parent.as<uint32_t>());
+        k_refit<<<blocks_for(nleaf, bs), bs, 0, s>>>(d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),
+                                                     d.vals_out.as<uint32_t>(), (uint32_t)nt, K, (int)nleaf,
+                                                     d.nodes.as<float4>(), d.leaf_parent.as<uint32_t>(),
+                                                     d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
+        d.launches += 2;
+    }
+    d.bvh.rec = d.rec_sorted.as<float4>();
+    d.bvh.tri_id = d.tri_id_sorted.as<uint32_t>();
+    d.bvh.nodes = d.nodes.as<float4>();
+    d.bvh.nleaf = nleaf;
+    d.bvh.root = nleaf > 1 ? 0u : (LEAF_BIT | LEAF_DEGEN_BIT);  // single leaf: always take the guarded path
+    return cudaGetLastError();
+}
+
+// Sorts the queries along a Morton curve (coherent packets). Produces q_sorted (xyz + original index).
+cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq) {
+    cudaStream_t s = d.stream;
+    const unsigned bs = 256;
+    BuildStatus* st = d.status.as<BuildStatus>();
+    CK(d.q_sorted.ensure(nq * 16));
+    CK(d.q_keys_in.ensure(nq * 8));
+    CK(d.q_keys_out.ensure(nq * 8));
+    CK(d.q_vals_in.ensure(nq * 4));
+    CK(d.q_perm.ensure(nq * 4));
+    k_point_bounds<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, (uint32_t)nq, st);
+    k_point_morton<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, (uint32_t)nq, st, d.q_keys_in.as<uint64_t>(),
+                                                     d.q_vals_in.as<uint32_t>());
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.q_keys_in.as<uint64_t>(), d.q_keys_out.as<uint64_t>(),
+                                       d.q_vals_in.as<uint32_t>(), d.q_perm.as<uint32_t>(), (int)nq, 0, 63, s));
+    CK(d.cub_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(d.cub_tmp.p, tmp_bytes, d.q_keys_in.as<uint64_t>(),
+                                       d.q_keys_out.as<uint64_t>(), d.q_vals_in.as<uint32_t>(),
+                                       d.q_perm.as<uint32_t>(), (int)nq, 0, 63, s));
+    k_point_gather<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, d.q_perm.as<uint32_t>(), (uint32_t)nq,
+                                                     d.q_sorted.as<float4>());
+    d.launches += 11;
+    return cudaGetLastError();
+}
+
+}  // namespace m2s

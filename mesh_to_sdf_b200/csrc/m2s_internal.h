@@ -1,0 +1,131 @@
+// Internal declarations shared by the translation units of libm2s.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/m2s.h"
+
+namespace m2s {
+
+// ---------------------------------------------------------------------------------------------------
+// Device-side layouts (all in HBM; the whole mesh + LBVH of config C3 is ~14 MB and stays L2-resident)
+//
+//   triangle record, 48 B = 3 x float4 (one per triangle, two copies: original order for the
+//   brute-force / row kernels, leaf (Morton) order for the LBVH kernels):
+//       r0 = (a.x, a.y, a.z, b.x)   r1 = (b.y, b.z, c.x, c.y)   r2 = (c.z, n.x, n.y, n.z)
+//       n = cross(b - a, c - a), un-normalised, un-fused (geo.rs:60-64)
+//   LBVH internal node, 64 B = 4 x float4, both child boxes inline (padded -/+1e-4, geo.rs:18-21):
+//       n0 = (Lmin.xyz, bits(left ref))   n1 = (Lmax.xyz, 0)
+//       n2 = (Rmin.xyz, bits(right ref))  n3 = (Rmax.xyz, 0)
+//   child ref: >= 0 internal node index; < 0 leaf: bit31 set, bit30 = "leaf holds a degenerate
+//   triangle" (slow path with the geo.rs:73-88 guards), bits 0..29 = leaf index. Leaf l owns the
+//   sorted triangles [l*K, min((l+1)*K, nt)).
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t LEAF_BIT = 0x80000000u;
+constexpr uint32_t LEAF_DEGEN_BIT = 0x40000000u;
+constexpr uint32_t LEAF_INDEX_MASK = 0x3fffffffu;
+constexpr uint32_t TRI_DEGEN_BIT = 0x80000000u;  // in tri_id_sorted
+
+// Written by the build kernels, read back once per call (64 B).
+struct BuildStatus {
+    int bad_index;      // some triangle index >= nv
+    int nonfinite;      // some referenced vertex / query / grid parameter is NaN or +-inf
+    int n_degenerate;   // triangles with two equal vertices
+    int stack_overflow; // traversal stack overflow (cannot happen for depth <= 128; checked anyway)
+    int nan_distance;   // brute-force Normal fold hit the reference's "NaN distance" panic
+    int lo[3];          // scene bounds (padded boxes), order-preserving int encoding of float
+    int hi[3];
+    int pad[5];
+};
+static_assert(sizeof(BuildStatus) == 64, "BuildStatus must be 64 bytes");
+
+struct Bvh {
+    const float4* rec;        // leaf-order triangle records
+    const uint32_t* tri_id;   // leaf-order -> original triangle id (| TRI_DEGEN_BIT)
+    const float4* nodes;      // internal nodes
+    uint32_t nt;              // triangles
+    uint32_t nleaf;           // leaves
+    uint32_t leaf_size;       // K
+    uint32_t root;            // root ref (a leaf ref when nleaf == 1)
+    const BuildStatus* st;    // device pointer: scene bounds (-> pruning slack) and error flags
+};
+
+struct GridParams {
+    float fx, fy, fz;     // Grid::first_cell
+    float sx, sy, sz;     // Grid::cell_size
+    uint32_t nx, ny, nz;  // Grid::cell_count
+    uint32_t x0, x1;      // slab [x0, x1) computed by this launch
+};
+
+// Row parity bitmaps for the grid Raycast sign (generate/grid.rs:568-642). For axis A the rows are
+// the nB*nC rays starting on the face cell A=0; bit i of a row = parity of the hits whose last
+// incremented cell k satisfies k >= i. Layout: [word][row] per axis so neighbouring rows are adjacent.
+struct RowBits {
+    uint32_t* bits[3];
+    uint32_t rows[3];   // rows per axis: X: ny*nz, Y: nx*nz, Z: nx*ny
+    uint32_t words[3];  // ceil(n_axis / 32)
+};
+
+enum QueryMode : int {
+    MODE_UNSIGNED = 0,  // min |d|                      (Raycast paths)
+    MODE_NORMAL = 1,    // positive-wins near-tie rule  (lib.rs:242-259)
+    MODE_ARGMIN = 2     // sign of the single nearest triangle (rtree.rs:116-123)
+};
+
+// Growable device buffer, reused across calls (no cudaMalloc on the steady-state path).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes);
+    void release();
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Everything a context owns on one device.
+struct Device {
+    int ordinal = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+
+    // mesh + LBVH
+    DevBuf verts, tris;  // staging for the host entry points
+    DevBuf rec_orig, rec_sorted, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
+    DevBuf tri_id_sorted, nodes, leaf_parent, node_parent, node_flag, status;
+    DevBuf rows[3], big_list, big_count;
+    DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
+    BuildStatus* h_status = nullptr;  // pinned
+    cudaEvent_t ev[8] = {};
+
+    Bvh bvh{};
+};
+
+// ---- launchers (each returns the CUDA error of its enqueue) ------------------------------------------
+cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
+                         uint32_t leaf_size);
+cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
+
+cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb);
+
+cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out);
+
+cudaError_t launch_points(Device& d, const float* d_queries, uint64_t nq, int mode, bool ray_sign, float* d_out);
+
+cudaError_t launch_brute(Device& d, const float* d_queries, uint64_t nq, int sign, bool has_degenerate,
+                         float* d_out);
+
+cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value);
+
+}  // namespace m2s
+
+struct m2s_ctx {
+    int n_devices = 0;
+    m2s::Device* dev = nullptr;
+    std::string last_error;
+    m2s_timings timings{};
+    uint32_t leaf_size = 4;
+};

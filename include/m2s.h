@@ -28,6 +28,12 @@ extern "C" {
 
 #define M2S_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define M2S_API __attribute__((visibility("default")))
+#else
+#define M2S_API
+#endif
+
 typedef enum m2s_status {
     M2S_OK = 0,
     M2S_EINVAL = 1, /* bad argument (null pointer, unknown enum, zero cell count …)              */
@@ -72,27 +78,27 @@ typedef struct m2s_timings {
 /* Create a context on `n_devices` CUDA devices (`devices == NULL || n_devices == 0` -> device 0).
  * With more than one device, m2s_generate_grid_sdf shards the grid by slabs along x (the slowest
  * axis of get_cell_idx) and m2s_generate_sdf shards the queries by contiguous ranges. */
-m2s_status m2s_create(const int* devices, int n_devices, m2s_ctx** out);
+M2S_API m2s_status m2s_create(const int* devices, int n_devices, m2s_ctx** out);
 
 /* Same, single device, but all work is enqueued on the caller's `cudaStream_t` (passed as void*;
  * NULL = the legacy default stream). Lets a host framework time / order the library's work with
  * its own events. */
-m2s_status m2s_create_on_stream(int device, void* cuda_stream, m2s_ctx** out);
+M2S_API m2s_status m2s_create_on_stream(int device, void* cuda_stream, m2s_ctx** out);
 
-void m2s_destroy(m2s_ctx* ctx);
+M2S_API void m2s_destroy(m2s_ctx* ctx);
 
 /* Human-readable description of the last non-OK status on this context ("" if none). */
-const char* m2s_last_error(const m2s_ctx* ctx);
+M2S_API const char* m2s_last_error(const m2s_ctx* ctx);
 
-m2s_status m2s_last_timings(const m2s_ctx* ctx, m2s_timings* out);
+M2S_API m2s_status m2s_last_timings(const m2s_ctx* ctx, m2s_timings* out);
 
 /* Number of kernels this library launched on behalf of `ctx` since creation (bench.py's gpu_launches). */
-uint64_t m2s_launch_count(const m2s_ctx* ctx);
+M2S_API uint64_t m2s_launch_count(const m2s_ctx* ctx);
 
-int m2s_abi_version(void);
+M2S_API int m2s_abi_version(void);
 
 /* Number of devices the context drives. */
-int m2s_device_count(const m2s_ctx* ctx);
+M2S_API int m2s_device_count(const m2s_ctx* ctx);
 
 /* ---- host-buffer entry points: the drop-in boundary ----------------------------------------------- */
 
@@ -101,7 +107,7 @@ int m2s_device_count(const m2s_ctx* ctx);
  *   propagate_heap :495-558, compute_raycasts :568-642).
  * first_cell / cell_size / cell_count are Grid's three fields (src/grid.rs:30-37).
  * `out` has nx*ny*nz floats. nt == 0 fills f32::MAX (what the reference's un-seeded grid returns). */
-m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv,
+M2S_API m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv,
                                  const uint32_t* tri_idx, uint64_t nt, const float first_cell[3],
                                  const float cell_size[3], const uint64_t cell_count[3], int sign_method,
                                  float* out);
@@ -112,35 +118,40 @@ m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t 
  *   generic/rtree.rs:87-126 (RTREE), generic/rtree_bvh.rs:79-174 (RTREE_BVH).
  * `out` has nq floats, in query order. nt == 0: NONE/BVH fill f32::MAX per query; RTREE and
  * RTREE_BVH return M2S_EEMPTY without touching `out`. */
-m2s_status m2s_generate_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx,
+M2S_API m2s_status m2s_generate_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx,
                             uint64_t nt, const float* queries_xyz, uint64_t nq, int accel_method,
                             int sign_method, float* out);
 
 /* ---- device-buffer entry points (single-device contexts) --------------------------------------------
  * Same semantics, but every pointer is a device pointer on the context's device and all work is
- * only enqueued on the context's stream (no host synchronisation on the success path except one
- * 64-byte status read-back after the build). The grid variant computes the slab
+ * only ENQUEUED on the context's stream: the call returns without synchronising. Data errors
+ * (M2S_EINDEX, M2S_ENAN) are detected on the device and reported by the next m2s_synchronize().
+ * The grid variant computes the slab
  * x in [x_begin, x_end) of the full grid and writes it at out_slab[(x - x_begin)*ny*nz + y*nz + z]:
  * this is the per-rank call of the multi-GPU path (one process per GPU, slabs along x). */
-m2s_status m2s_generate_grid_sdf_device(m2s_ctx* ctx, const float* d_verts_xyz, uint64_t nv,
+M2S_API m2s_status m2s_generate_grid_sdf_device(m2s_ctx* ctx, const float* d_verts_xyz, uint64_t nv,
                                         const uint32_t* d_tri_idx, uint64_t nt, const float first_cell[3],
                                         const float cell_size[3], const uint64_t cell_count[3],
                                         int sign_method, uint64_t x_begin, uint64_t x_end, float* d_out_slab);
 
-m2s_status m2s_generate_sdf_device(m2s_ctx* ctx, const float* d_verts_xyz, uint64_t nv,
+M2S_API m2s_status m2s_generate_sdf_device(m2s_ctx* ctx, const float* d_verts_xyz, uint64_t nv,
                                    const uint32_t* d_tri_idx, uint64_t nt, const float* d_queries_xyz,
                                    uint64_t nq, int accel_method, int sign_method, float* d_out);
+
+/* Waits for the context's stream(s) and returns the deferred status of the device-buffer calls
+ * enqueued since the previous m2s_synchronize (M2S_OK, M2S_EINDEX, M2S_ENAN or M2S_ECUDA). */
+M2S_API m2s_status m2s_synchronize(m2s_ctx* ctx);
 
 /* ---- host-side helpers the facade shares with the tests --------------------------------------------- */
 
 /* Topology::get_triangles, src/lib.rs:175-193. `indices == NULL` is `None` (0..nv). index_bytes is 2
  * (u16) or 4 (u32). Returns the triangle count; writes 3*count u32 when out != NULL.
  * TriangleList drops a trailing partial tuple; TriangleStrip windows are not winding-flipped. */
-uint64_t m2s_expand_topology(int topology, const void* indices, int index_bytes, uint64_t n_indices,
+M2S_API uint64_t m2s_expand_topology(int topology, const void* indices, int index_bytes, uint64_t n_indices,
                              uint64_t nv, uint32_t* out);
 
 /* Grid::from_bounding_box, src/grid.rs:59-74. */
-void m2s_grid_from_bounding_box(const float bbox_min[3], const float bbox_max[3],
+M2S_API void m2s_grid_from_bounding_box(const float bbox_min[3], const float bbox_max[3],
                                 const uint64_t cell_count[3], float first_cell[3], float cell_size[3]);
 
 #ifdef __cplusplus

@@ -44,13 +44,15 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__global__ void k_status_init(BuildStatus* st) {
+__global__ void k_status_init(BuildStatus* st, int clear_errors) {
     if (threadIdx.x == 0) {
-        st->bad_index = 0;
-        st->nonfinite = 0;
+        if (clear_errors) {
+            st->bad_index = 0;
+            st->nonfinite = 0;
+            st->stack_overflow = 0;
+            st->nan_distance = 0;
+        }
         st->n_degenerate = 0;
-        st->stack_overflow = 0;
-        st->nan_distance = 0;
         for (int i = 0; i < 3; ++i) {
             st->lo[i] = f2ord(INFINITY);
             st->hi[i] = f2ord(-INFINITY);
@@ -318,14 +320,21 @@ static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((
         if (e__ != cudaSuccess) return e__; \
     } while (0)
 
-// Builds records + LBVH for (d_verts, d_tris) on d.stream.
+// Resets the per-call part of the status block (scene bounds, degenerate count) and, on request, the
+// sticky error flags.
+cudaError_t launch_status_reset(Device& d, bool clear_errors) {
+    const bool fresh = d.status.p == nullptr;
+    CK(d.status.ensure(sizeof(BuildStatus)));
+    k_status_init<<<1, 32, 0, d.stream>>>(d.status.as<BuildStatus>(), (clear_errors || fresh) ? 1 : 0);
+    d.launches++;
+    return cudaGetLastError();
+}
+
+// Builds records + LBVH for (d_verts, d_tris) on d.stream. launch_status_reset must have run.
 cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
                          uint32_t K) {
     cudaStream_t s = d.stream;
-    CK(d.status.ensure(sizeof(BuildStatus)));
     BuildStatus* st = d.status.as<BuildStatus>();
-    k_status_init<<<1, 32, 0, s>>>(st);
-    d.launches++;
     d.bvh = Bvh{};
     d.bvh.nt = (uint32_t)nt;
     d.bvh.leaf_size = K;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 #include "../../include/m2s.h"
@@ -34,6 +35,7 @@ struct BuildStatus {
     int nonfinite;      // some referenced vertex / query / grid parameter is NaN or +-inf
     int n_degenerate;   // triangles with two equal vertices
     int stack_overflow; // traversal stack overflow (cannot happen for depth <= 128; checked anyway)
+                        // the four error flags above/below are sticky until launch_status_reset(clear)
     int nan_distance;   // brute-force Normal fold hit the reference's "NaN distance" panic
     int lo[3];          // scene bounds (padded boxes), order-preserving int encoding of float
     int hi[3];
@@ -105,6 +107,7 @@ struct Device {
 };
 
 // ---- launchers (each returns the CUDA error of its enqueue) ------------------------------------------
+cudaError_t launch_status_reset(Device& d, bool clear_errors);
 cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
                          uint32_t leaf_size);
 cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
@@ -113,10 +116,9 @@ cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb);
 
 cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out);
 
-cudaError_t launch_points(Device& d, const float* d_queries, uint64_t nq, int mode, bool ray_sign, float* d_out);
-
-cudaError_t launch_brute(Device& d, const float* d_queries, uint64_t nq, int sign, bool has_degenerate,
-                         float* d_out);
+// queries must have been Morton-sorted into d.q_sorted by sort_queries().
+// sign_rule: 0 = value already signed / unsigned, 1 = +X ray parity, 3 = best of the three axes
+cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out);
 
 cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value);
 
@@ -128,4 +130,5 @@ struct m2s_ctx {
     std::string last_error;
     m2s_timings timings{};
     uint32_t leaf_size = 4;
+    std::mutex mu;  // a context serves one call at a time
 };

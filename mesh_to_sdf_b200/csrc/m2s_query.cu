@@ -1,0 +1,571 @@
+// Query kernels of libm2s.so: exact nearest-triangle search over the LBVH, the grid Raycast row
+// toggles, the per-query ray parity walks and the fused sign epilogues.
+//
+// Replaces, for every voxel / query point at once:
+//   - the splat + heap propagation of generate_grid_sdf (mesh_to_sdf/src/generate/grid.rs:383-558),
+//   - compute_raycasts / generate_raycasts (generate/grid.rs:568-684),
+//   - the per-query closures of generate_sdf_{default,bvh,rtree,rtree_bvh}
+//     (generate/generic/default.rs:28-73, bvh.rs:77-143, rtree.rs:114-124, rtree_bvh.rs:124-172)
+//     including bvh_ext.rs:59-169 (nearest candidates) and the bvh / rstar crate searches.
+// The leaf arithmetic (m2s_geom.cuh) is bit-identical to src/geo.rs; the tree only prunes, with a
+// conservative slack, so |d| equals the brute-force minimum of default.rs bit for bit.
+#include "m2s_geom.cuh"
+#include "m2s_internal.h"
+
+namespace m2s {
+namespace {
+
+constexpr int STACK_DEPTH = 128;  // >= depth of a Karras tree over 63-bit keys + index tie-break bits
+
+__device__ __forceinline__ float ord2f_q(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// Largest |coordinate| of the scene (mesh, plus queries once k_point_bounds ran): scales the
+// pruning slack (absolute rounding error of the leaf arithmetic is a few ulp(M)).
+__device__ __forceinline__ float scene_magnitude(const BuildStatus* __restrict__ st) {
+    float m = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float lo = ord2f_q(st->lo[i]), hi = ord2f_q(st->hi[i]);
+        if (lo <= hi) m = fmaxf(m, fmaxf(fabsf(lo), fabsf(hi)));
+    }
+    return m;
+}
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------------------------------
+// Nearest search state. bound2 is the squared pruning radius: a subtree / triangle whose squared
+// distance lower bound exceeds bound2 cannot change the result.
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+struct Near {
+    float best2;    // UNSIGNED / ARGMIN: min squared distance so far
+    float bound2;   // pruning radius^2
+    float m;        // NORMAL: current signed minimum under compare_distances (lib.rs:242-259)
+    uint32_t id;    // ARGMIN: original index of the arg-min triangle (ties -> smallest index)
+    uint32_t slot;  // ARGMIN: its position in leaf order
+    float eps;      // absolute length slack
+    bool nan;
+
+    __device__ __forceinline__ void init(float eps_len) {
+        best2 = INFINITY;
+        bound2 = INFINITY;
+        m = 3.402823466e+38f;  // f32::MAX, default.rs:54 / bvh.rs:83
+        id = 0xffffffffu;
+        slot = 0;
+        eps = eps_len;
+        nan = false;
+    }
+    __device__ __forceinline__ void set_bound(float dist) {
+        // (dist + slack)^2, rounded up a little. NORMAL keeps everything inside the near-tie window of
+        // compare_distances (2 ulps or 1e-6) alive: a positive near-tie must still be able to win.
+        float r = dist + eps;
+        if (MODE == MODE_NORMAL) r += fmaxf(1.0e-6f, dist * 2.4e-7f) * 1.5f;
+        bound2 = r * r * 1.000001f;
+    }
+};
+
+template <int MODE>
+__device__ __forceinline__ void visit_leaf(const Bvh& bvh, uint32_t ref, const f3 p, Near<MODE>& s) {
+    const uint32_t leaf = ref & LEAF_INDEX_MASK;
+    const bool degen = (ref & LEAF_DEGEN_BIT) != 0u;
+    const uint32_t b = leaf * bvh.leaf_size;
+    const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
+    for (uint32_t j = b; j < e; ++j) {
+        const float4 r0 = ldg4(bvh.rec + 3 * (size_t)j);
+        const float4 r1 = ldg4(bvh.rec + 3 * (size_t)j + 1);
+        const float4 r2 = ldg4(bvh.rec + 3 * (size_t)j + 2);
+        const f3 a = {r0.x, r0.y, r0.z}, bb = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
+        const f3 q = degen ? closest_point_triangle_any(p, a, bb, c) : closest_point_triangle(p, a, bb, c);
+        const f3 dir = v_sub(p, q);
+        const float d2 = v_dot(dir, dir);
+        if (MODE == MODE_UNSIGNED) {
+            if (d2 < s.best2) {
+                s.best2 = d2;
+                s.set_bound(sqrtf(d2));
+            }
+        } else if (MODE == MODE_ARGMIN) {
+            if (d2 <= s.best2) {
+                const uint32_t id = bvh.tri_id[j] & ~TRI_DEGEN_BIT;
+                if (d2 < s.best2 || id < s.id) {
+                    if (d2 < s.best2) s.set_bound(sqrtf(d2));
+                    s.best2 = d2;
+                    s.id = id;
+                    s.slot = j;
+                }
+            }
+        } else {  // MODE_NORMAL
+            if (d2 <= s.bound2 || !(d2 == d2)) {
+                // geo.rs:43-56: distance = |p - nearest|, sign = dot(p - nearest, ab x ac) > 0
+                const float dist = __fsqrt_rn(d2);
+                const f3 n = {r2.y, r2.z, r2.w};
+                const float sd = v_dot(dir, n) > 0.0f ? dist : -dist;
+                bool nan = false;
+                if (compare_distances(sd, s.m, &nan) < 0) {
+                    s.m = sd;
+                    s.set_bound(dist);
+                }
+                s.nan |= nan;
+            }
+        }
+    }
+}
+
+// Ordered depth-first traversal with a (ref, lower bound) stack; entries are re-checked against the
+// current radius when popped, so a subtree pushed early is skipped without touching memory.
+template <int MODE>
+__device__ __forceinline__ void nearest(const Bvh& bvh, const f3 p, Near<MODE>& s, int* overflow) {
+    if (bvh.nt == 0) return;
+    uint2 stack[STACK_DEPTH];
+    int sp = 0;
+    uint32_t cur = bvh.root;
+    for (;;) {
+        if (cur & LEAF_BIT) {
+            visit_leaf<MODE>(bvh, cur, p, s);
+        } else {
+            const float4* nd = bvh.nodes + 4 * (size_t)cur;
+            const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
+            const float dl = box_dist2(p.x, p.y, p.z, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z);
+            const float dr = box_dist2(p.x, p.y, p.z, n2.x, n2.y, n2.z, n3.x, n3.y, n3.z);
+            const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n2.w);
+            const bool hl = dl <= s.bound2, hr = dr <= s.bound2;
+            if (hl && hr) {
+                const bool left_first = dl <= dr;
+                if (sp < STACK_DEPTH) {
+                    stack[sp++] = left_first ? make_uint2(rref, __float_as_uint(dr))
+                                             : make_uint2(lref, __float_as_uint(dl));
+                } else {
+                    *overflow = 1;
+                }
+                cur = left_first ? lref : rref;
+                continue;
+            }
+            if (hl) { cur = lref; continue; }
+            if (hr) { cur = rref; continue; }
+        }
+        // pop
+        bool found = false;
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if (__uint_as_float(e.y) <= s.bound2) {
+                cur = e.x;
+                found = true;
+                break;
+            }
+        }
+        if (!found) return;
+    }
+}
+
+// Parity of the reference hits of the ray o + t * e_AXIS (t > 0) over all triangles: the sign vote of
+// bvh.rs:106-134 / rtree_bvh.rs:136-164 / default.rs:34-38. The tree walk plays the role of
+// bvh.traverse (a conservative box filter); hits are decided by geo.rs:165-216 alone.
+template <int AXIS>
+__device__ __forceinline__ uint32_t ray_parity(const Bvh& bvh, const f3 o, int* overflow) {
+    if (bvh.nt == 0) return 0u;
+    constexpr int IY = (AXIS + 1) % 3, IZ = (AXIS + 2) % 3;
+    const float oc[3] = {o.x, o.y, o.z};
+    const float ox = oc[AXIS], oy = oc[IY], oz = oc[IZ];
+    uint32_t stack[STACK_DEPTH];
+    int sp = 0;
+    uint32_t cur = bvh.root;
+    uint32_t count = 0;
+    for (;;) {
+        if (cur & LEAF_BIT) {
+            const uint32_t leaf = cur & LEAF_INDEX_MASK;
+            const uint32_t b = leaf * bvh.leaf_size;
+            const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
+            for (uint32_t j = b; j < e; ++j) {
+                const float4 r0 = ldg4(bvh.rec + 3 * (size_t)j);
+                const float4 r1 = ldg4(bvh.rec + 3 * (size_t)j + 1);
+                const float4 r2 = ldg4(bvh.rec + 3 * (size_t)j + 2);
+                const f3 a = {r0.x, r0.y, r0.z}, bb = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
+                float t;
+                if (ray_aligned<AXIS>(o, a, bb, c, &t)) ++count;
+            }
+        } else {
+            const float4* nd = bvh.nodes + 4 * (size_t)cur;
+            const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
+            const float llo[3] = {n0.x, n0.y, n0.z}, lhi[3] = {n1.x, n1.y, n1.z};
+            const float rlo[3] = {n2.x, n2.y, n2.z}, rhi[3] = {n3.x, n3.y, n3.z};
+            const bool hl = oy >= llo[IY] && oy <= lhi[IY] && oz >= llo[IZ] && oz <= lhi[IZ] && ox <= lhi[AXIS];
+            const bool hr = oy >= rlo[IY] && oy <= rhi[IY] && oz >= rlo[IZ] && oz <= rhi[IZ] && ox <= rhi[AXIS];
+            const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n2.w);
+            if (hl && hr) {
+                if (sp < STACK_DEPTH) stack[sp++] = rref;
+                else *overflow = 1;
+                cur = lref;
+                continue;
+            }
+            if (hl) { cur = lref; continue; }
+            if (hr) { cur = rref; continue; }
+        }
+        if (sp == 0) return count & 1u;
+        cur = stack[--sp];
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float finish(const Bvh& bvh, const f3 p, const Near<MODE>& s) {
+    if (bvh.nt == 0) return 3.402823466e+38f;
+    if (MODE == MODE_UNSIGNED) return __fsqrt_rn(s.best2);  // sqrt is monotone: min sqrt = sqrt min
+    if (MODE == MODE_NORMAL) return s.m;
+    // ARGMIN: point_triangle_signed_distance of THE nearest triangle (rtree.rs:118-123)
+    const uint32_t j = s.slot;
+    const float4 r0 = ldg4(bvh.rec + 3 * (size_t)j);
+    const float4 r1 = ldg4(bvh.rec + 3 * (size_t)j + 1);
+    const float4 r2 = ldg4(bvh.rec + 3 * (size_t)j + 2);
+    const f3 a = {r0.x, r0.y, r0.z}, bb = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
+    const f3 q = closest_point_triangle_any(p, a, bb, c);
+    const f3 dir = v_sub(p, q);
+    const float dist = __fsqrt_rn(v_dot(dir, dir));
+    const f3 n = {r2.y, r2.z, r2.w};
+    return v_dot(dir, n) > 0.0f ? dist : -dist;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Grid kernel. Block = 256 threads = a 4 x 8 x 8 (x, y, z) voxel brick; each warp owns a compact
+// 2 x 4 x 4 sub-brick so its 32 traversals stay coherent. Bricks are numbered z-fastest so that
+// consecutive blocks share tree nodes in L1/L2.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BX = 4, BY = 8, BZ = 8;
+
+template <int MODE, bool RAYSIGN>
+__global__ void __launch_bounds__(256)
+k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
+               const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
+               BuildStatus* __restrict__ st) {
+    const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZ - 1) / BZ;
+    uint32_t bid = blockIdx.x;
+    const uint32_t bz = bid % nbz;
+    bid /= nbz;
+    const uint32_t by = bid % nby;
+    const uint32_t bx = bid / nby;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp (wx, wy, wz) in 2 x 2 x 2; lane (lx, ly, lz) in 2 x 4 x 4, z fastest
+    const uint32_t lx = ((warp >> 2) & 1u) * 2u + (lane >> 4);
+    const uint32_t ly = ((warp >> 1) & 1u) * 4u + ((lane >> 2) & 3u);
+    const uint32_t lz = (warp & 1u) * 4u + (lane & 3u);
+    const uint32_t x = g.x0 + bx * BX + lx, y = by * BY + ly, z = bz * BZ + lz;
+    if (x >= g.x1 || y >= g.ny || z >= g.nz) return;
+
+    const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
+    Near<MODE> s;
+    s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
+    int overflow = 0;
+    nearest<MODE>(bvh, p, s, &overflow);
+    float d = finish<MODE>(bvh, p, s);
+
+    if (RAYSIGN) {
+        // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd. The parity
+        // bitmaps hold, per row, bit i = parity of the hits whose increment range 0..=k covers cell i.
+        const uint32_t rowx = y * g.nz + z, rowy = x * g.nz + z, rowz = x * g.ny + y;
+        const uint32_t rows_x = g.ny * g.nz, rows_y = g.nx * g.nz, rows_z = g.nx * g.ny;
+        const uint32_t ox = (px[(size_t)(x >> 5) * rows_x + rowx] >> (x & 31)) & 1u;
+        const uint32_t oy = (py[(size_t)(y >> 5) * rows_y + rowy] >> (y & 31)) & 1u;
+        const uint32_t oz = (pz[(size_t)(z >> 5) * rows_z + rowz] >> (z & 31)) & 1u;
+        if (ox + oy + oz >= 2u) d = -d;
+    }
+    out[((size_t)(x - g.x0) * g.ny + y) * g.nz + z] = d;
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+    if (MODE == MODE_NORMAL && s.nan) atomicExch(&st->nan_distance, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Grid Raycast rows (generate/grid.rs:568-684). Instead of walking a tree per ray, every triangle
+// finds the few rows whose start-cell centre falls inside its padded, projected box (the box is
+// the bvh crate's filter, geo.rs:4-22), evaluates geo.rs:165-216 there and toggles bit k
+// (k = last incremented cell, grid.rs:604-607) of that row. k_rows_scan turns toggles into parities.
+// ---------------------------------------------------------------------------------------------------
+struct RowRange {
+    uint32_t j0, j1, k0, k1;  // inclusive ranges along the two in-plane axes (IY, IZ); empty if j0 > j1
+};
+
+// candidate index range [i0, i1] of cells whose centre first + i*size lies in [lo, hi]; conservative
+// (callers re-test each centre exactly). Restricted to [c0, c1).
+__device__ __forceinline__ void axis_range(float first, float size, uint32_t c0, uint32_t c1, float lo, float hi,
+                                           uint32_t* i0, uint32_t* i1) {
+    if (c0 >= c1) { *i0 = 1; *i1 = 0; return; }
+    if (!(size > 0.0f) || !isfinite((hi - first) / size)) {  // zero / negative cell size: test every cell
+        *i0 = c0;
+        *i1 = c1 - 1;
+        return;
+    }
+    const float a = floorf((lo - first) / size) - 2.0f;
+    const float b = ceilf((hi - first) / size) + 2.0f;
+    if (b < (float)c0 || a > (float)(c1 - 1)) { *i0 = 1; *i1 = 0; return; }
+    *i0 = a <= (float)c0 ? c0 : (uint32_t)a;
+    *i1 = b >= (float)(c1 - 1) ? c1 - 1 : (uint32_t)b;
+}
+
+struct TriAxis {
+    f3 a, b, c;
+    float lo[3], hi[3];
+};
+
+__device__ __forceinline__ TriAxis load_tri(const float4* __restrict__ rec, uint32_t t) {
+    const float4 r0 = ldg4(rec + 3 * (size_t)t), r1 = ldg4(rec + 3 * (size_t)t + 1), r2 = ldg4(rec + 3 * (size_t)t + 2);
+    TriAxis T;
+    T.a = {r0.x, r0.y, r0.z};
+    T.b = {r0.w, r1.x, r1.y};
+    T.c = {r1.z, r1.w, r2.x};
+    const float EPS = 0.0001f;  // geo.rs:5,20-21
+    T.lo[0] = fsub(fminf(T.a.x, fminf(T.b.x, T.c.x)), EPS);
+    T.lo[1] = fsub(fminf(T.a.y, fminf(T.b.y, T.c.y)), EPS);
+    T.lo[2] = fsub(fminf(T.a.z, fminf(T.b.z, T.c.z)), EPS);
+    T.hi[0] = fadd(fmaxf(T.a.x, fmaxf(T.b.x, T.c.x)), EPS);
+    T.hi[1] = fadd(fmaxf(T.a.y, fmaxf(T.b.y, T.c.y)), EPS);
+    T.hi[2] = fadd(fmaxf(T.a.z, fmaxf(T.b.z, T.c.z)), EPS);
+    return T;
+}
+
+struct RowCtx {
+    float first[3], size[3];
+    uint32_t n[3];
+    uint32_t x0, x1;
+};
+
+__device__ __forceinline__ RowRange row_range(const RowCtx& g, const TriAxis& T, int axis) {
+    const int iy = (axis + 1) % 3, iz = (axis + 2) % 3;
+    RowRange r;
+    // rows of the Y and Z axes are only needed for the slab's own x range
+    const uint32_t y0 = iy == 0 ? g.x0 : 0u, y1 = iy == 0 ? g.x1 : g.n[iy];
+    const uint32_t z0 = iz == 0 ? g.x0 : 0u, z1 = iz == 0 ? g.x1 : g.n[iz];
+    axis_range(g.first[iy], g.size[iy], y0, y1, T.lo[iy], T.hi[iy], &r.j0, &r.j1);
+    axis_range(g.first[iz], g.size[iz], z0, z1, T.lo[iz], T.hi[iz], &r.k0, &r.k1);
+    if (r.k0 > r.k1) { r.j0 = 1; r.j1 = 0; }
+    // the ray starts at the centre of cell 0 and only sees what lies ahead: box must reach past it
+    const float o_ax = cell_center(g.first[axis], g.size[axis], 0u);
+    if (!(o_ax <= T.hi[axis])) { r.j0 = 1; r.j1 = 0; }
+    return r;
+}
+
+// one (row, triangle) test + toggle. (j, k) are the cell indices along (IY, IZ).
+__device__ __forceinline__ void row_test(const RowCtx& g, const TriAxis& T, int axis, uint32_t j, uint32_t k,
+                                         uint32_t* __restrict__ bits, uint32_t rows) {
+    const int iy = (axis + 1) % 3, iz = (axis + 2) % 3;
+    const float cy = cell_center(g.first[iy], g.size[iy], j), cz = cell_center(g.first[iz], g.size[iz], k);
+    if (!(cy >= T.lo[iy] && cy <= T.hi[iy] && cz >= T.lo[iz] && cz <= T.hi[iz])) return;
+    float oc[3];
+    oc[axis] = cell_center(g.first[axis], g.size[axis], 0u);
+    oc[iy] = cy;
+    oc[iz] = cz;
+    const f3 o = {oc[0], oc[1], oc[2]};
+    float t;
+    if (!ray_aligned_dyn(axis, o, T.a, T.b, T.c, &t)) return;
+    const uint32_t last = row_last_cell(t, g.size[axis], g.n[axis]);
+    // row index: X: y*nz + z   Y: x*nz + z   Z: x*ny + y   (the in-plane pair in (x,y,z) order)
+    uint32_t row;
+    if (axis == 0) row = j * g.n[2] + k;        // (iy, iz) = (y, z)
+    else if (axis == 1) row = k * g.n[2] + j;   // (iy, iz) = (z, x)
+    else row = j * g.n[1] + k;                  // (iy, iz) = (x, y)
+    atomicXor(bits + (size_t)(last >> 5) * rows + row, 1u << (last & 31));
+}
+
+constexpr uint32_t ROWS_INLINE_MAX = 48;
+
+__global__ void __launch_bounds__(256)
+k_rows_small(const float4* __restrict__ rec, uint32_t nt, const RowCtx g, uint32_t* __restrict__ b0,
+             uint32_t* __restrict__ b1, uint32_t* __restrict__ b2, uint32_t* __restrict__ big_list,
+             uint32_t* __restrict__ big_count) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const TriAxis T = load_tri(rec, t);
+#pragma unroll 1
+    for (int axis = 0; axis < 3; ++axis) {
+        const RowRange r = row_range(g, T, axis);
+        if (r.j0 > r.j1) continue;
+        const uint64_t cnt = (uint64_t)(r.j1 - r.j0 + 1) * (uint64_t)(r.k1 - r.k0 + 1);
+        if (cnt > ROWS_INLINE_MAX) {
+            big_list[atomicAdd(big_count, 1u)] = t * 4u + (uint32_t)axis;
+            continue;
+        }
+        uint32_t* bits = axis == 0 ? b0 : (axis == 1 ? b1 : b2);
+        const int iy = (axis + 1) % 3, iz = (axis + 2) % 3;
+        const uint32_t rows = g.n[iy] * g.n[iz];
+        for (uint32_t j = r.j0; j <= r.j1; ++j)
+            for (uint32_t k = r.k0; k <= r.k1; ++k) row_test(g, T, axis, j, k, bits, rows);
+    }
+}
+
+// triangles that cover many rows: one block per (triangle, axis), threads stride over the rows
+__global__ void __launch_bounds__(256)
+k_rows_big(const float4* __restrict__ rec, const RowCtx g, uint32_t* __restrict__ b0, uint32_t* __restrict__ b1,
+           uint32_t* __restrict__ b2, const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_count) {
+    const uint32_t n = *big_count;
+    for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint32_t code = big_list[e];
+        const uint32_t t = code >> 2;
+        const int axis = (int)(code & 3u);
+        const TriAxis T = load_tri(rec, t);
+        const RowRange r = row_range(g, T, axis);
+        if (r.j0 > r.j1) continue;
+        uint32_t* bits = axis == 0 ? b0 : (axis == 1 ? b1 : b2);
+        const int iy = (axis + 1) % 3, iz = (axis + 2) % 3;
+        const uint32_t rows = g.n[iy] * g.n[iz];
+        const uint64_t wk = (uint64_t)(r.k1 - r.k0 + 1);
+        const uint64_t cnt = (uint64_t)(r.j1 - r.j0 + 1) * wk;
+        for (uint64_t i = threadIdx.x; i < cnt; i += blockDim.x)
+            row_test(g, T, axis, r.j0 + (uint32_t)(i / wk), r.k0 + (uint32_t)(i % wk), bits, rows);
+    }
+}
+
+// toggles -> parities, in place: bit i <- XOR of the toggle bits k >= i of the row
+__global__ void __launch_bounds__(256)
+k_rows_scan(uint32_t* __restrict__ bits, uint32_t rows, uint32_t words) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    uint32_t carry = 0u;
+    for (int w = (int)words - 1; w >= 0; --w) {
+        uint32_t v = bits[(size_t)w * rows + r];
+        v ^= v >> 1;
+        v ^= v >> 2;
+        v ^= v >> 4;
+        v ^= v >> 8;
+        v ^= v >> 16;
+        if (carry) v = ~v;
+        carry = v & 1u;
+        bits[(size_t)w * rows + r] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Scattered query points (generate_sdf). Queries arrive Morton-sorted (xyz + original index) so a
+// warp's 32 traversals are coherent; results are scattered back to query order.
+// SIGN: 0 = value already signed (Normal / Rtree) 1 = +X parity (default.rs:65-72)
+//       3 = best of the 3 axes (bvh.rs:137-141, rtree_bvh.rs:167-171)
+// ---------------------------------------------------------------------------------------------------
+template <int MODE, int SIGN>
+__global__ void __launch_bounds__(256)
+k_points(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, float* __restrict__ out,
+         BuildStatus* __restrict__ st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float4 q = q_sorted[i];
+    const f3 p = {q.x, q.y, q.z};
+    Near<MODE> s;
+    s.init(4.0e-6f * scene_magnitude(st));
+    int overflow = 0;
+    nearest<MODE>(bvh, p, s, &overflow);
+    float d = finish<MODE>(bvh, p, s);
+    if (SIGN == 1) {
+        if (ray_parity<0>(bvh, p, &overflow)) d = -d;
+    } else if (SIGN == 3) {
+        const uint32_t insides = ray_parity<0>(bvh, p, &overflow) + ray_parity<1>(bvh, p, &overflow) +
+                                 ray_parity<2>(bvh, p, &overflow);
+        if (insides > 1u) d = -d;
+    }
+    out[__float_as_uint(q.w)] = d;
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+    if (MODE == MODE_NORMAL && s.nan) atomicExch(&st->nan_distance, 1);
+}
+
+__global__ void __launch_bounds__(256) k_fill(float* __restrict__ out, uint64_t n, float v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = v;
+}
+
+}  // namespace
+
+#define CK(x)                               \
+    do {                                    \
+        cudaError_t e__ = (x);              \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+static RowCtx make_row_ctx(const GridParams& g) {
+    RowCtx c;
+    c.first[0] = g.fx; c.first[1] = g.fy; c.first[2] = g.fz;
+    c.size[0] = g.sx; c.size[1] = g.sy; c.size[2] = g.sz;
+    c.n[0] = g.nx; c.n[1] = g.ny; c.n[2] = g.nz;
+    c.x0 = g.x0; c.x1 = g.x1;
+    return c;
+}
+
+// Row parity bitmaps for the slab [g.x0, g.x1) (all X rows; the Y and Z rows of the slab's planes).
+cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb) {
+    cudaStream_t s = d.stream;
+    const uint32_t n[3] = {g.nx, g.ny, g.nz};
+    for (int a = 0; a < 3; ++a) {
+        const int iy = (a + 1) % 3, iz = (a + 2) % 3;
+        rb->rows[a] = n[iy] * n[iz];
+        rb->words[a] = (n[a] + 31) / 32;
+        const size_t bytes = (size_t)rb->rows[a] * rb->words[a] * 4;
+        CK(d.rows[a].ensure(bytes));
+        rb->bits[a] = d.rows[a].as<uint32_t>();
+        CK(cudaMemsetAsync(rb->bits[a], 0, bytes, s));
+    }
+    const uint32_t nt = d.bvh.nt;
+    if (nt == 0) return cudaSuccess;
+    CK(d.big_list.ensure((size_t)nt * 3 * 4));
+    CK(d.big_count.ensure(4));
+    CK(cudaMemsetAsync(d.big_count.p, 0, 4, s));
+    const RowCtx c = make_row_ctx(g);
+    // original-order records would do as well; the sorted copy is the one that stays hot in L2
+    k_rows_small<<<blocks_for(nt, 256), 256, 0, s>>>(d.bvh.rec, nt, c, rb->bits[0], rb->bits[1], rb->bits[2],
+                                                     d.big_list.as<uint32_t>(), d.big_count.as<uint32_t>());
+    k_rows_big<<<d.sm_count * 4, 256, 0, s>>>(d.bvh.rec, c, rb->bits[0], rb->bits[1], rb->bits[2],
+                                              d.big_list.as<uint32_t>(), d.big_count.as<uint32_t>());
+    for (int a = 0; a < 3; ++a)
+        k_rows_scan<<<blocks_for(rb->rows[a], 256), 256, 0, s>>>(rb->bits[a], rb->rows[a], rb->words[a]);
+    d.launches += 5;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out) {
+    cudaStream_t s = d.stream;
+    const uint64_t nbx = (g.x1 - g.x0 + BX - 1) / BX, nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZ - 1) / BZ;
+    const uint64_t nblocks = nbx * nby * nbz;
+    if (nblocks == 0) return cudaSuccess;
+    if (nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    float mag = 0.0f;
+    {
+        const float f[3] = {g.fx, g.fy, g.fz}, sz[3] = {g.sx, g.sy, g.sz};
+        const uint32_t n[3] = {g.nx, g.ny, g.nz};
+        for (int i = 0; i < 3; ++i) {
+            mag = fmaxf(mag, fabsf(f[i]));
+            mag = fmaxf(mag, fabsf(f[i] + (float)n[i] * sz[i]));
+        }
+    }
+    BuildStatus* st = d.status.as<BuildStatus>();
+    const unsigned nb = (unsigned)nblocks;
+    if (rb) {
+        k_grid_nearest<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, rb->bits[0], rb->bits[1], rb->bits[2],
+                                                               d_out, st);
+    } else if (mode == MODE_NORMAL) {
+        k_grid_nearest<MODE_NORMAL, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, nullptr, nullptr, nullptr, d_out, st);
+    } else {
+        k_grid_nearest<MODE_UNSIGNED, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, nullptr, nullptr, nullptr, d_out, st);
+    }
+    d.launches++;
+    return cudaGetLastError();
+}
+
+// sign_rule: 0 none, 1 = +X parity, 3 = best of three axes
+cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out) {
+    cudaStream_t s = d.stream;
+    if (nq == 0) return cudaSuccess;
+    const unsigned nb = blocks_for(nq, 256);
+    const float4* q = d.q_sorted.as<float4>();
+    BuildStatus* st = d.status.as<BuildStatus>();
+    const uint32_t n = (uint32_t)nq;
+    if (mode == MODE_NORMAL) k_points<MODE_NORMAL, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+    else if (mode == MODE_ARGMIN) k_points<MODE_ARGMIN, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+    else if (sign_rule == 1) k_points<MODE_UNSIGNED, 1><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+    else if (sign_rule == 3) k_points<MODE_UNSIGNED, 3><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+    else k_points<MODE_UNSIGNED, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+    d.launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value) {
+    if (n == 0) return cudaSuccess;
+    const unsigned nb = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)d.sm_count * 16);
+    k_fill<<<nb, 256, 0, d.stream>>>(d_out, n, value);
+    d.launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace m2s

@@ -1,0 +1,110 @@
+"""GPU parity of generate_grid_sdf (CUDA path through the C ABI) against the oracle.
+
+Bars: Raycast |d| and sign are bit-exact against the exact oracle (same un-fused fp32 leaf arithmetic, exact
+min); Normal is within 1e-4 * mesh diagonal (north-star tolerance; in practice <= 2e-6: the near-tie fold of
+lib.rs:242-259 is order dependent) with identical signs."""
+import numpy as np
+import pytest
+
+from mesh_to_sdf_b200 import synth
+from conftest import mesh_diag
+
+pytestmark = pytest.mark.gpu
+
+RAYCAST, NORMAL = 0, 1
+
+
+def _grid_for(m2s, verts, n):
+    mn, mx = synth.padded_grid_box(verts)
+    return m2s.Grid.from_bounding_box(mn, mx, n)
+
+
+def test_doc_kat_grid_raycast(m2s):
+    # lib.rs:34-58: sdf[0] == 1.0
+    verts = np.array([[0.5, 1.5, 0.5], [1., 2., 3.], [1., 3., 7.]], np.float32)
+    grid = m2s.Grid.from_bounding_box([0., 0., 0.], [10., 10., 10.], [10, 10, 10])
+    sdf = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(np.array([0, 1, 2], np.uint32)), grid,
+                                m2s.SignMethod.Raycast)
+    assert sdf.shape == (1000,)
+    assert sdf[0] == 1.0
+
+
+def test_doc_kat_grid_rs(m2s):
+    # generate/grid.rs:205-231
+    verts = np.array([[0.5, 1.5, 0.5], [1., 2., 3.], [1., 3., 4.]], np.float32)
+    grid = m2s.Grid.from_bounding_box([0., 0., 0.], [10., 10., 10.], [10, 10, 10])
+    sdf = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(np.array([0, 1, 2], np.uint32)), grid,
+                                m2s.SignMethod.Raycast)
+    assert sdf[0] == 1.0
+
+
+def test_c1_single_triangle_normal_bit_exact(m2s, oracle):
+    # BASELINE config C1: single triangle, 8^3, Normal
+    verts = np.array([[0.5, 1.5, 0.5], [1., 2., 3.], [1., 3., 7.]], np.float32)
+    tris = np.array([[0, 1, 2]], np.uint32)
+    grid = m2s.Grid.from_bounding_box([0., 0., 0.], [10., 10., 10.], [8, 8, 8])
+    got = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(tris), grid, m2s.SignMethod.Normal)
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, NORMAL)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_generate_grid_equals_generic_none_raycast(m2s, oracle):
+    # generate/grid.rs:692-724 (assert_eq!, exact)
+    verts = np.array([[0., 1., 0.], [1., 2., 3.], [1., 3., 4.], [2., 0., 0.]], np.float32)
+    idx = np.array([0, 1, 2, 1, 2, 3], np.uint32)
+    grid = m2s.Grid.from_bounding_box([0., 0., 0.], [5., 5., 5.], [5, 5, 5])
+    q = np.array([grid.get_cell_center([x, y, z]) for x in range(5) for y in range(5) for z in range(5)], np.float32)
+    sdf = m2s.generate_sdf(verts, m2s.Topology.TriangleList(idx), q, m2s.AccelerationMethod.none(m2s.SignMethod.Raycast))
+    grid_sdf = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(idx), grid, m2s.SignMethod.Raycast)
+    assert np.array_equal(sdf, grid_sdf)
+    want = oracle.generate_sdf(verts, idx.reshape(-1, 3), q, oracle.ACCEL_NONE, oracle.RAYCAST)
+    assert np.array_equal(sdf.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("nu,nv,n", [(16, 10, 24), (48, 30, 40)])
+def test_torus_raycast_bit_exact(m2s, oracle, nu, nv, n):
+    verts, tris = synth.bumpy_torus(nu, nv)
+    grid = _grid_for(m2s, verts, [n, n + 3, n - 5])
+    got = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(tris), grid, m2s.SignMethod.Raycast)
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, RAYCAST)
+    assert np.array_equal(np.abs(got).view(np.uint32), np.abs(want).view(np.uint32))
+    assert np.array_equal(np.signbit(got), np.signbit(want))
+    assert (got < 0).any() and (got > 0).any()
+
+
+@pytest.mark.parametrize("nu,nv,n", [(16, 10, 24), (48, 30, 40)])
+def test_torus_normal_within_tolerance(m2s, oracle, nu, nv, n):
+    verts, tris = synth.bumpy_torus(nu, nv)
+    grid = _grid_for(m2s, verts, [n, n - 2, n + 1])
+    got = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(tris), grid, m2s.SignMethod.Normal)
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, NORMAL)
+    tol = 1e-4 * mesh_diag(verts)  # north-star tolerance
+    assert np.max(np.abs(got - want)) <= tol
+    assert np.max(np.abs(np.abs(got) - np.abs(want))) <= 4e-6
+    assert np.array_equal(np.signbit(got), np.signbit(want))
+
+
+def test_empty_mesh_fills_max(m2s):
+    grid = m2s.Grid([0., 0., 0.], [1., 1., 1.], [3, 4, 5])
+    out = m2s.generate_grid_sdf(np.zeros((0, 3), np.float32), m2s.Topology.TriangleList(np.zeros(0, np.uint32)), grid,
+                                m2s.SignMethod.Raycast)
+    assert out.shape == (60,) and np.all(out == np.finfo(np.float32).max)
+
+
+def test_slab_invariance_device_entry(m2s, oracle):
+    torch = pytest.importorskip("torch")
+    verts, tris = synth.bumpy_torus(32, 20)
+    grid = _grid_for(m2s, verts, [20, 17, 19])
+    whole = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(tris), grid, m2s.SignMethod.Raycast)
+    dv = torch.from_numpy(verts).cuda()
+    dt = torch.from_numpy(tris.astype(np.int64)).to(torch.int32).cuda()  # same bits as u32
+    plane = 17 * 19
+    with m2s.Context() as c:
+        parts = []
+        for x0, x1 in [(0, 7), (7, 8), (8, 20)]:
+            out = torch.empty((x1 - x0) * plane, dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            c.grid_sdf_device(dv.data_ptr(), len(verts), dt.data_ptr(), len(tris), grid, RAYCAST, x0, x1, out.data_ptr())
+            c.synchronize()
+            parts.append(out.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts).view(np.uint32), whole.view(np.uint32))

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -200,7 +201,9 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
             return M2S_ECUDA;
         }
         std::memset(d.h_status, 0, sizeof(BuildStatus));
+        if (const char* e = std::getenv("M2S_SEED_LEVELS")) d.seed_levels = std::max(0, std::min(2, std::atoi(e)));
     }
+    if (const char* e = std::getenv("M2S_LEAF_SIZE")) ctx->leaf_size = (uint32_t)std::max(1, std::min(32, std::atoi(e)));
     *out = ctx;
     return M2S_OK;
 }
@@ -229,7 +232,7 @@ void m2s_destroy(m2s_ctx* ctx) {
                           &d.keys_out, &d.vals_in, &d.vals_out, &d.cub_tmp, &d.tri_id_sorted, &d.nodes,
                           &d.leaf_parent, &d.node_parent, &d.node_flag, &d.status, &d.rows[0], &d.rows[1],
                           &d.rows[2], &d.big_list, &d.big_count, &d.queries, &d.q_sorted, &d.q_perm,
-                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out};
+                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1]};
         for (DevBuf* b : bufs) b->release();
         if (d.h_status) cudaFreeHost(d.h_status);
         for (int k = 0; k < 8; ++k)

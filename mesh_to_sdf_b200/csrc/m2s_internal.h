@@ -99,6 +99,8 @@ struct Device {
     DevBuf rec_orig, rec_sorted, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
     DevBuf tri_id_sorted, nodes, leaf_parent, node_parent, node_flag, status;
     DevBuf rows[3], big_list, big_count;
+    DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
+    int seed_levels = 2;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
     BuildStatus* h_status = nullptr;  // pinned
     cudaEvent_t ev[8] = {};

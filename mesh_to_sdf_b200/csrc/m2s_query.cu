@@ -65,54 +65,71 @@ struct Near {
     }
 };
 
+// One triangle (leaf-order slot j) against the query: the leaf arithmetic of geo.rs:26-56.
+template <int MODE>
+__device__ __forceinline__ void visit_tri(const Bvh& bvh, uint32_t j, bool degen, const f3 p, Near<MODE>& s) {
+    const float4 r0 = ldg4(bvh.rec + 3 * (size_t)j);
+    const float4 r1 = ldg4(bvh.rec + 3 * (size_t)j + 1);
+    const float4 r2 = ldg4(bvh.rec + 3 * (size_t)j + 2);
+    const f3 a = {r0.x, r0.y, r0.z}, bb = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
+    const f3 q = degen ? closest_point_triangle_any(p, a, bb, c) : closest_point_triangle(p, a, bb, c);
+    const f3 dir = v_sub(p, q);
+    const float d2 = v_dot(dir, dir);
+    if (MODE == MODE_UNSIGNED) {
+        if (d2 < s.best2) {
+            s.best2 = d2;
+            s.slot = j;
+            s.set_bound(sqrtf(d2));
+        }
+    } else if (MODE == MODE_ARGMIN) {
+        if (d2 <= s.best2) {
+            const uint32_t id = bvh.tri_id[j] & ~TRI_DEGEN_BIT;
+            if (d2 < s.best2 || id < s.id) {
+                if (d2 < s.best2) s.set_bound(sqrtf(d2));
+                s.best2 = d2;
+                s.id = id;
+                s.slot = j;
+            }
+        }
+    } else {  // MODE_NORMAL
+        if (d2 <= s.bound2 || !(d2 == d2)) {
+            // geo.rs:43-56: distance = |p - nearest|, sign = dot(p - nearest, ab x ac) > 0
+            const float dist = __fsqrt_rn(d2);
+            const f3 n = {r2.y, r2.z, r2.w};
+            const float sd = v_dot(dir, n) > 0.0f ? dist : -dist;
+            bool nan = false;
+            if (compare_distances(sd, s.m, &nan) < 0) {
+                s.m = sd;
+                s.slot = j;
+                s.set_bound(dist);
+            }
+            s.nan |= nan;
+        }
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void visit_leaf(const Bvh& bvh, uint32_t ref, const f3 p, Near<MODE>& s) {
     const uint32_t leaf = ref & LEAF_INDEX_MASK;
     const bool degen = (ref & LEAF_DEGEN_BIT) != 0u;
     const uint32_t b = leaf * bvh.leaf_size;
     const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
-    for (uint32_t j = b; j < e; ++j) {
-        const float4 r0 = ldg4(bvh.rec + 3 * (size_t)j);
-        const float4 r1 = ldg4(bvh.rec + 3 * (size_t)j + 1);
-        const float4 r2 = ldg4(bvh.rec + 3 * (size_t)j + 2);
-        const f3 a = {r0.x, r0.y, r0.z}, bb = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
-        const f3 q = degen ? closest_point_triangle_any(p, a, bb, c) : closest_point_triangle(p, a, bb, c);
-        const f3 dir = v_sub(p, q);
-        const float d2 = v_dot(dir, dir);
-        if (MODE == MODE_UNSIGNED) {
-            if (d2 < s.best2) {
-                s.best2 = d2;
-                s.set_bound(sqrtf(d2));
-            }
-        } else if (MODE == MODE_ARGMIN) {
-            if (d2 <= s.best2) {
-                const uint32_t id = bvh.tri_id[j] & ~TRI_DEGEN_BIT;
-                if (d2 < s.best2 || id < s.id) {
-                    if (d2 < s.best2) s.set_bound(sqrtf(d2));
-                    s.best2 = d2;
-                    s.id = id;
-                    s.slot = j;
-                }
-            }
-        } else {  // MODE_NORMAL
-            if (d2 <= s.bound2 || !(d2 == d2)) {
-                // geo.rs:43-56: distance = |p - nearest|, sign = dot(p - nearest, ab x ac) > 0
-                const float dist = __fsqrt_rn(d2);
-                const f3 n = {r2.y, r2.z, r2.w};
-                const float sd = v_dot(dir, n) > 0.0f ? dist : -dist;
-                bool nan = false;
-                if (compare_distances(sd, s.m, &nan) < 0) {
-                    s.m = sd;
-                    s.set_bound(dist);
-                }
-                s.nan |= nan;
-            }
-        }
-    }
+    for (uint32_t j = b; j < e; ++j) visit_tri<MODE>(bvh, j, degen, p, s);
 }
+
+// Seed: evaluate one known-near triangle first so the traversal starts with a tight radius (the
+// triangle is the nearest one of a neighbouring voxel / query, found by a coarser pass).
+template <int MODE>
+__device__ __forceinline__ void seed_tri(const Bvh& bvh, uint32_t j, const f3 p, Near<MODE>& s) {
+    if (j >= bvh.nt) return;
+    visit_tri<MODE>(bvh, j, (bvh.tri_id[j] & TRI_DEGEN_BIT) != 0u, p, s);
+}
+
+constexpr uint32_t TRAVERSAL_DONE = 0xffffffffu;  // has LEAF_BIT set; never a real leaf ref (nt < 2^30)
 
 // Ordered depth-first traversal with a (ref, lower bound) stack; entries are re-checked against the
 // current radius when popped, so a subtree pushed early is skipped without touching memory.
+// "while-while" shape: all lanes of a warp walk internal nodes together, then all visit leaves.
 template <int MODE>
 __device__ __forceinline__ void nearest(const Bvh& bvh, const f3 p, Near<MODE>& s, int* overflow) {
     if (bvh.nt == 0) return;
@@ -120,9 +137,7 @@ __device__ __forceinline__ void nearest(const Bvh& bvh, const f3 p, Near<MODE>& 
     int sp = 0;
     uint32_t cur = bvh.root;
     for (;;) {
-        if (cur & LEAF_BIT) {
-            visit_leaf<MODE>(bvh, cur, p, s);
-        } else {
+        while (!(cur & LEAF_BIT)) {
             const float4* nd = bvh.nodes + 4 * (size_t)cur;
             const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
             const float dl = box_dist2(p.x, p.y, p.z, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z);
@@ -138,22 +153,32 @@ __device__ __forceinline__ void nearest(const Bvh& bvh, const f3 p, Near<MODE>& 
                     *overflow = 1;
                 }
                 cur = left_first ? lref : rref;
-                continue;
+            } else if (hl) {
+                cur = lref;
+            } else if (hr) {
+                cur = rref;
+            } else {
+                cur = TRAVERSAL_DONE;
+                while (sp > 0) {
+                    const uint2 e = stack[--sp];
+                    if (__uint_as_float(e.y) <= s.bound2) {
+                        cur = e.x;
+                        break;
+                    }
+                }
             }
-            if (hl) { cur = lref; continue; }
-            if (hr) { cur = rref; continue; }
         }
-        // pop
-        bool found = false;
+        if (cur == TRAVERSAL_DONE) return;
+        visit_leaf<MODE>(bvh, cur, p, s);
+        cur = TRAVERSAL_DONE;
         while (sp > 0) {
             const uint2 e = stack[--sp];
             if (__uint_as_float(e.y) <= s.bound2) {
                 cur = e.x;
-                found = true;
                 break;
             }
         }
-        if (!found) return;
+        if (cur == TRAVERSAL_DONE) return;
     }
 }
 
@@ -224,18 +249,26 @@ __device__ __forceinline__ float finish(const Bvh& bvh, const f3 p, const Near<M
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Grid kernel. Block = 256 threads = a 4 x 8 x 8 (x, y, z) voxel brick; each warp owns a compact
+// Grid kernels. Block = 256 threads = a 4 x 8 x 8 (x, y, z) voxel brick; each warp owns a compact
 // 2 x 4 x 4 sub-brick so its 32 traversals stay coherent. Bricks are numbered z-fastest so that
 // consecutive blocks share tree nodes in L1/L2.
+//
+// Seeding hierarchy: the grid is searched coarse to fine. Level L visits one representative voxel
+// per S_L^3 block (S = 16, 4, 1) and starts each search with the nearest triangle its parent block's
+// representative found, so the pruning radius is tight from the first node on and the 32 lanes of a
+// warp walk almost the same root-to-leaf path. The seed only initialises the radius: the search
+// itself stays exact.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BX = 4, BY = 8, BZ = 8;
+constexpr uint32_t SEED_STRIDE = 4;  // ratio between consecutive levels
 
-template <int MODE, bool RAYSIGN>
-__global__ void __launch_bounds__(256)
-k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
-               const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
-               BuildStatus* __restrict__ st) {
-    const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZ - 1) / BZ;
+struct SeedLevel {
+    const uint32_t* parent;  // nearest-triangle slots of the parent level (nullptr: start unbounded)
+    uint32_t px, py, pz;     // parent level dims
+    uint32_t pstride;        // parent level stride in voxels
+};
+
+__device__ __forceinline__ void brick_coords(uint32_t nby, uint32_t nbz, uint32_t* x, uint32_t* y, uint32_t* z) {
     uint32_t bid = blockIdx.x;
     const uint32_t bz = bid % nbz;
     bid /= nbz;
@@ -243,15 +276,54 @@ k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const ui
     const uint32_t bx = bid / nby;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp (wx, wy, wz) in 2 x 2 x 2; lane (lx, ly, lz) in 2 x 4 x 4, z fastest
-    const uint32_t lx = ((warp >> 2) & 1u) * 2u + (lane >> 4);
-    const uint32_t ly = ((warp >> 1) & 1u) * 4u + ((lane >> 2) & 3u);
-    const uint32_t lz = (warp & 1u) * 4u + (lane & 3u);
-    const uint32_t x = g.x0 + bx * BX + lx, y = by * BY + ly, z = bz * BZ + lz;
+    *x = bx * BX + ((warp >> 2) & 1u) * 2u + (lane >> 4);
+    *y = by * BY + ((warp >> 1) & 1u) * 4u + ((lane >> 2) & 3u);
+    *z = bz * BZ + (warp & 1u) * 4u + (lane & 3u);
+}
+
+__device__ __forceinline__ uint32_t parent_seed(const SeedLevel& L, uint32_t xr, uint32_t y, uint32_t z) {
+    // (xr, y, z): voxel coordinates, x relative to the slab start
+    const uint32_t cx = min(xr / L.pstride, L.px - 1), cy = min(y / L.pstride, L.py - 1),
+                   cz = min(z / L.pstride, L.pz - 1);
+    return L.parent[((size_t)cx * L.py + cy) * L.pz + cz];
+}
+
+// Coarse level: one thread per S^3 block of the slab; searches the block's representative voxel and
+// stores the nearest triangle's slot.
+__global__ void __launch_bounds__(256)
+k_grid_seed(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t stride, const uint32_t cx,
+            const uint32_t cy, const uint32_t cz, const SeedLevel L, uint32_t* __restrict__ seeds,
+            BuildStatus* __restrict__ st) {
+    uint32_t bx, by, bz;
+    brick_coords((cy + BY - 1) / BY, (cz + BZ - 1) / BZ, &bx, &by, &bz);
+    if (bx >= cx || by >= cy || bz >= cz) return;
+    // representative voxel: the block centre, clamped into the slab / grid
+    const uint32_t xr = min(bx * stride + stride / 2, g.x1 - g.x0 - 1);
+    const uint32_t y = min(by * stride + stride / 2, g.ny - 1), z = min(bz * stride + stride / 2, g.nz - 1);
+    const f3 p = {cell_center(g.fx, g.sx, g.x0 + xr), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
+    Near<MODE_UNSIGNED> s;
+    s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
+    if (L.parent) seed_tri<MODE_UNSIGNED>(bvh, parent_seed(L, xr, y, z), p, s);
+    int overflow = 0;
+    nearest<MODE_UNSIGNED>(bvh, p, s, &overflow);
+    seeds[((size_t)bx * cy + by) * cz + bz] = s.slot;
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+}
+
+template <int MODE, bool RAYSIGN>
+__global__ void __launch_bounds__(256)
+k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
+               const uint32_t* __restrict__ px, const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz,
+               float* __restrict__ out, BuildStatus* __restrict__ st) {
+    uint32_t xr, y, z;
+    brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
+    const uint32_t x = g.x0 + xr;
     if (x >= g.x1 || y >= g.ny || z >= g.nz) return;
 
     const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
     Near<MODE> s;
     s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
+    if (L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
     int overflow = 0;
     nearest<MODE>(bvh, p, s, &overflow);
     float d = finish<MODE>(bvh, p, s);
@@ -266,7 +338,7 @@ k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const ui
         const uint32_t oz = (pz[(size_t)(z >> 5) * rows_z + rowz] >> (z & 31)) & 1u;
         if (ox + oy + oz >= 2u) d = -d;
     }
-    out[((size_t)(x - g.x0) * g.ny + y) * g.nz + z] = d;
+    out[((size_t)xr * g.ny + y) * g.nz + z] = d;
     if (overflow) atomicExch(&st->stack_overflow, 1);
     if (MODE == MODE_NORMAL && s.nan) atomicExch(&st->nan_distance, 1);
 }
@@ -435,16 +507,38 @@ k_rows_scan(uint32_t* __restrict__ bits, uint32_t rows, uint32_t words) {
 // SIGN: 0 = value already signed (Normal / Rtree) 1 = +X parity (default.rs:65-72)
 //       3 = best of the 3 axes (bvh.rs:137-141, rtree_bvh.rs:167-171)
 // ---------------------------------------------------------------------------------------------------
+constexpr uint32_t POINT_SEED_STRIDE = 32;  // one representative per warp of sorted queries
+
+// Coarse level over the Morton-sorted queries: thread t searches query min(t*stride + stride/2, nq-1).
+__global__ void __launch_bounds__(256)
+k_points_seed(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, uint32_t stride, uint32_t count,
+              const uint32_t* __restrict__ parent, uint32_t parent_count, uint32_t* __restrict__ seeds,
+              BuildStatus* __restrict__ st) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t i = min(t * stride + stride / 2, nq - 1);
+    const float4 q = q_sorted[i];
+    const f3 p = {q.x, q.y, q.z};
+    Near<MODE_UNSIGNED> s;
+    s.init(4.0e-6f * scene_magnitude(st));
+    if (parent) seed_tri<MODE_UNSIGNED>(bvh, parent[min(t / POINT_SEED_STRIDE, parent_count - 1)], p, s);
+    int overflow = 0;
+    nearest<MODE_UNSIGNED>(bvh, p, s, &overflow);
+    seeds[t] = s.slot;
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+}
+
 template <int MODE, int SIGN>
 __global__ void __launch_bounds__(256)
-k_points(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, float* __restrict__ out,
-         BuildStatus* __restrict__ st) {
+k_points(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, const uint32_t* __restrict__ parent,
+         uint32_t parent_count, float* __restrict__ out, BuildStatus* __restrict__ st) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     const float4 q = q_sorted[i];
     const f3 p = {q.x, q.y, q.z};
     Near<MODE> s;
     s.init(4.0e-6f * scene_magnitude(st));
+    if (parent) seed_tri<MODE>(bvh, parent[min(i / POINT_SEED_STRIDE, parent_count - 1)], p, s);
     int overflow = 0;
     nearest<MODE>(bvh, p, s, &overflow);
     float d = finish<MODE>(bvh, p, s);
@@ -514,30 +608,52 @@ cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb) {
     return cudaGetLastError();
 }
 
+static float grid_magnitude(const GridParams& g) {
+    float mag = 0.0f;
+    const float f[3] = {g.fx, g.fy, g.fz}, sz[3] = {g.sx, g.sy, g.sz};
+    const uint32_t n[3] = {g.nx, g.ny, g.nz};
+    for (int i = 0; i < 3; ++i) {
+        mag = fmaxf(mag, fabsf(f[i]));
+        mag = fmaxf(mag, fabsf(f[i] + (float)n[i] * sz[i]));
+    }
+    return mag;
+}
+
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
 cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out) {
     cudaStream_t s = d.stream;
-    const uint64_t nbx = (g.x1 - g.x0 + BX - 1) / BX, nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZ - 1) / BZ;
-    const uint64_t nblocks = nbx * nby * nbz;
+    const uint32_t sx = g.x1 - g.x0;
+    const uint64_t nblocks = (uint64_t)cdiv(sx, BX) * cdiv(g.ny, BY) * cdiv(g.nz, BZ);
     if (nblocks == 0) return cudaSuccess;
     if (nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    float mag = 0.0f;
-    {
-        const float f[3] = {g.fx, g.fy, g.fz}, sz[3] = {g.sx, g.sy, g.sz};
-        const uint32_t n[3] = {g.nx, g.ny, g.nz};
-        for (int i = 0; i < 3; ++i) {
-            mag = fmaxf(mag, fabsf(f[i]));
-            mag = fmaxf(mag, fabsf(f[i] + (float)n[i] * sz[i]));
+    const float mag = grid_magnitude(g);
+    BuildStatus* st = d.status.as<BuildStatus>();
+
+    // coarse-to-fine seeding: strides 16 and 4 (skipped for grids that are too small to profit)
+    SeedLevel L{nullptr, 0, 0, 0, 0};
+    if (d.seed_levels > 0 && (uint64_t)sx * g.ny * g.nz >= 4096) {
+        const int nlev = d.seed_levels > 2 ? 2 : d.seed_levels;
+        for (int lev = nlev; lev >= 1; --lev) {
+            uint32_t stride = 1;
+            for (int k = 0; k < lev; ++k) stride *= SEED_STRIDE;
+            const uint32_t cx = cdiv(sx, stride), cy = cdiv(g.ny, stride), cz = cdiv(g.nz, stride);
+            DevBuf& buf = d.seeds[lev - 1];
+            CK(buf.ensure((size_t)cx * cy * cz * 4));
+            const unsigned nb = cdiv(cx, BX) * cdiv(cy, BY) * cdiv(cz, BZ);
+            k_grid_seed<<<nb, 256, 0, s>>>(d.bvh, g, mag, stride, cx, cy, cz, L, buf.as<uint32_t>(), st);
+            d.launches++;
+            L = SeedLevel{buf.as<uint32_t>(), cx, cy, cz, stride};
         }
     }
-    BuildStatus* st = d.status.as<BuildStatus>();
     const unsigned nb = (unsigned)nblocks;
     if (rb) {
-        k_grid_nearest<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, rb->bits[0], rb->bits[1], rb->bits[2],
+        k_grid_nearest<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2],
                                                                d_out, st);
     } else if (mode == MODE_NORMAL) {
-        k_grid_nearest<MODE_NORMAL, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, nullptr, nullptr, nullptr, d_out, st);
+        k_grid_nearest<MODE_NORMAL, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st);
     } else {
-        k_grid_nearest<MODE_UNSIGNED, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, nullptr, nullptr, nullptr, d_out, st);
+        k_grid_nearest<MODE_UNSIGNED, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st);
     }
     d.launches++;
     return cudaGetLastError();
@@ -547,15 +663,33 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
 cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out) {
     cudaStream_t s = d.stream;
     if (nq == 0) return cudaSuccess;
-    const unsigned nb = blocks_for(nq, 256);
     const float4* q = d.q_sorted.as<float4>();
     BuildStatus* st = d.status.as<BuildStatus>();
     const uint32_t n = (uint32_t)nq;
-    if (mode == MODE_NORMAL) k_points<MODE_NORMAL, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
-    else if (mode == MODE_ARGMIN) k_points<MODE_ARGMIN, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
-    else if (sign_rule == 1) k_points<MODE_UNSIGNED, 1><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
-    else if (sign_rule == 3) k_points<MODE_UNSIGNED, 3><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
-    else k_points<MODE_UNSIGNED, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+
+    const uint32_t* parent = nullptr;
+    uint32_t parent_count = 0;
+    if (d.seed_levels > 0 && n >= 4096) {
+        const int nlev = d.seed_levels > 2 ? 2 : d.seed_levels;
+        for (int lev = nlev; lev >= 1; --lev) {
+            uint32_t stride = 1;
+            for (int k = 0; k < lev; ++k) stride *= POINT_SEED_STRIDE;
+            const uint32_t count = cdiv(n, stride);
+            DevBuf& buf = d.seeds[lev - 1];
+            CK(buf.ensure((size_t)count * 4));
+            k_points_seed<<<blocks_for(count, 256), 256, 0, s>>>(d.bvh, q, n, stride, count, parent, parent_count,
+                                                                 buf.as<uint32_t>(), st);
+            d.launches++;
+            parent = buf.as<uint32_t>();
+            parent_count = count;
+        }
+    }
+    const unsigned nb = blocks_for(nq, 256);
+    if (mode == MODE_NORMAL) k_points<MODE_NORMAL, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, parent, parent_count, d_out, st);
+    else if (mode == MODE_ARGMIN) k_points<MODE_ARGMIN, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, parent, parent_count, d_out, st);
+    else if (sign_rule == 1) k_points<MODE_UNSIGNED, 1><<<nb, 256, 0, s>>>(d.bvh, q, n, parent, parent_count, d_out, st);
+    else if (sign_rule == 3) k_points<MODE_UNSIGNED, 3><<<nb, 256, 0, s>>>(d.bvh, q, n, parent, parent_count, d_out, st);
+    else k_points<MODE_UNSIGNED, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, parent, parent_count, d_out, st);
     d.launches++;
     return cudaGetLastError();
 }

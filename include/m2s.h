@@ -97,6 +97,10 @@ M2S_API uint64_t m2s_launch_count(const m2s_ctx* ctx);
 
 M2S_API int m2s_abi_version(void);
 
+/* Diagnostics: with M2S_STATS=1 in the environment at context creation, the traversal counts
+ * {internal nodes visited, leaves visited, searches, 0} of the last call on device 0 (else zeros). */
+M2S_API m2s_status m2s_debug_stats(m2s_ctx* ctx, uint64_t out[4]);
+
 /* Number of devices the context drives. */
 M2S_API int m2s_device_count(const m2s_ctx* ctx);
 

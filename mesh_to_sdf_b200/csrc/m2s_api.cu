@@ -201,6 +201,8 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
             return M2S_ECUDA;
         }
         std::memset(d.h_status, 0, sizeof(BuildStatus));
+        if (const char* e = std::getenv("M2S_DYNAMIC")) d.dynamic_fetch = std::atoi(e) != 0;
+        if (const char* e = std::getenv("M2S_STATS")) { d.want_stats = std::atoi(e) != 0; d.stats_mode = std::atoi(e); }
         if (const char* e = std::getenv("M2S_SEED_LEVELS")) d.seed_levels = std::max(0, std::min(2, std::atoi(e)));
     }
     if (const char* e = std::getenv("M2S_LEAF_SIZE")) ctx->leaf_size = (uint32_t)std::max(1, std::min(32, std::atoi(e)));
@@ -232,7 +234,7 @@ void m2s_destroy(m2s_ctx* ctx) {
                           &d.keys_out, &d.vals_in, &d.vals_out, &d.cub_tmp, &d.tri_id_sorted, &d.nodes,
                           &d.leaf_parent, &d.node_parent, &d.node_flag, &d.status, &d.rows[0], &d.rows[1],
                           &d.rows[2], &d.big_list, &d.big_count, &d.queries, &d.q_sorted, &d.q_perm,
-                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1]};
+                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.pill};
         for (DevBuf* b : bufs) b->release();
         if (d.h_status) cudaFreeHost(d.h_status);
         for (int k = 0; k < 8; ++k)
@@ -260,6 +262,18 @@ uint64_t m2s_launch_count(const m2s_ctx* ctx) {
 }
 
 int m2s_device_count(const m2s_ctx* ctx) { return ctx ? ctx->n_devices : 0; }
+
+m2s_status m2s_debug_stats(m2s_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return M2S_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    Device& d = ctx->dev[0];
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!d.stats.p) return M2S_OK;
+    CU(ctx, cudaSetDevice(d.ordinal));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    CU(ctx, cudaMemcpy(out, d.stats.p, 32, cudaMemcpyDeviceToHost));
+    return M2S_OK;
+}
 
 // ---- host-buffer entry points ------------------------------------------------------------------------
 

@@ -44,6 +44,15 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
+__device__ __forceinline__ float scene_mag(const BuildStatus* __restrict__ st) {
+    float m = 0.0f;
+    for (int i = 0; i < 3; ++i) {
+        const float lo = ord2f(st->lo[i]), hi = ord2f(st->hi[i]);
+        if (lo <= hi) m = fmaxf(m, fmaxf(fabsf(lo), fabsf(hi)));
+    }
+    return m;
+}
+
 __global__ void k_status_init(BuildStatus* st, int clear_errors) {
     if (threadIdx.x == 0) {
         if (clear_errors) {
@@ -199,17 +208,127 @@ k_point_gather(const float* __restrict__ q, const uint32_t* __restrict__ perm, u
 }
 
 // K4a: permute the records into leaf (sorted) order.
+// Pillbox (flat cylinder) around a vertex set: centre c, unit axis u, radius rho, half-height h such
+// that every point x of the convex hull has |dot(x-c,u)| <= h and |x - c - dot(x-c,u)u| <= rho. The
+// distance from a query p to anything inside is then >= hypot(max(0,|a|-h), max(0,l-rho)) with a, l
+// the axial / lateral offsets of p. For a (nearly) flat patch seen from far away this bound is tight
+// to first order where an axis-aligned box of a tilted patch is loose by about a third of its size,
+// which is what makes far-field searches cheap. u = 0 degrades gracefully to a bounding sphere.
+struct PillAcc {
+    float cx, cy, cz, ux, uy, uz, h, rho;
+    __device__ __forceinline__ void start(float3 c, float3 nsum) {
+        cx = c.x; cy = c.y; cz = c.z;
+        const float len2 = nsum.x * nsum.x + nsum.y * nsum.y + nsum.z * nsum.z;
+        if (len2 > 1e-30f && isfinite(len2)) {
+            const float inv = rsqrtf(len2);
+            ux = nsum.x * inv; uy = nsum.y * inv; uz = nsum.z * inv;
+        } else {
+            ux = uy = uz = 0.0f;
+        }
+        h = 0.0f;
+        rho = 0.0f;
+    }
+    __device__ __forceinline__ void add(float x, float y, float z) {
+        const float dx = x - cx, dy = y - cy, dz = z - cz;
+        const float a = dx * ux + dy * uy + dz * uz;
+        const float lx = dx - a * ux, ly = dy - a * uy, lz = dz - a * uz;
+        h = fmaxf(h, fabsf(a));
+        rho = fmaxf(rho, sqrtf(lx * lx + ly * ly + lz * lz));
+    }
+    // inflate for the rounding of this computation and of the query-side evaluation
+    __device__ __forceinline__ void finish(float mag) {
+        const float slack = 4.0e-6f * mag;
+        h = h * 1.0001f + slack;
+        rho = rho * 1.0001f + slack;
+    }
+};
+
+// K4a: permute the records into leaf (sorted) order; per-triangle pillbox = the triangle's plane
+// disc (centroid, unit normal, circumscribing radius).
 __global__ void __launch_bounds__(256)
 k_tri_permute(const float4* __restrict__ rec, const float4* __restrict__ tri_lo,
-              const uint32_t* __restrict__ order, uint32_t nt, float4* __restrict__ rec_sorted,
-              uint32_t* __restrict__ tri_id_sorted) {
+              const uint32_t* __restrict__ order, uint32_t nt, const BuildStatus* __restrict__ st,
+              float4* __restrict__ rec_sorted, float4* __restrict__ pill, uint32_t* __restrict__ tri_id_sorted) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nt) return;
     const uint32_t t = order[j];
-    rec_sorted[3 * j + 0] = rec[3 * t + 0];
-    rec_sorted[3 * j + 1] = rec[3 * t + 1];
-    rec_sorted[3 * j + 2] = rec[3 * t + 2];
+    const float4 r0 = rec[3 * t + 0], r1 = rec[3 * t + 1], r2 = rec[3 * t + 2];
+    rec_sorted[3 * j + 0] = r0;
+    rec_sorted[3 * j + 1] = r1;
+    rec_sorted[3 * j + 2] = r2;
     tri_id_sorted[j] = t | (tri_lo[t].w != 0.0f ? TRI_DEGEN_BIT : 0u);
+    PillAcc P;
+    const float third = 1.0f / 3.0f;
+    P.start(make_float3((r0.x + r0.w + r1.z) * third, (r0.y + r1.x + r1.w) * third, (r0.z + r1.y + r2.x) * third),
+            make_float3(r2.y, r2.z, r2.w));
+    P.add(r0.x, r0.y, r0.z);
+    P.add(r0.w, r1.x, r1.y);
+    P.add(r1.z, r1.w, r2.x);
+    P.finish(scene_mag(st));
+    pill[2 * j + 0] = make_float4(P.cx, P.cy, P.cz, P.rho);
+    pill[2 * j + 1] = make_float4(P.ux, P.uy, P.uz, P.h);
+}
+
+// K4d: pillbox of every child slot of every internal node: one warp per slot strides over the
+// slot's (contiguous, leaf-order) triangles twice — normal sum, then extents. Slots covering more
+// than PILL_MAX_TRIS triangles keep a bounding sphere (u = 0): large curved regions do not profit.
+constexpr uint32_t PILL_MAX_TRIS = 2048;
+
+__global__ void __launch_bounds__(256)
+k_pillbox(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nleaf, float4* __restrict__ nodes,
+          const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (slot >= 2u * (uint32_t)(nleaf - 1)) return;
+    float4* ch = nodes + NODE_F4 * (size_t)(slot >> 1) + CHILD_F4 * (slot & 1u);
+    const float4 c0 = ch[0], c1 = ch[1];
+    const uint32_t ref = __float_as_uint(c0.w);
+    uint32_t l0, l1;
+    if (ref & LEAF_BIT) {
+        l0 = l1 = ref & LEAF_INDEX_MASK;
+    } else {
+        const uint2 r = node_range[ref];
+        l0 = r.x;
+        l1 = r.y;
+    }
+    const uint32_t b = l0 * K, e = min(nt, (l1 + 1) * K);
+    const float3 centre = make_float3(0.5f * (c0.x + c1.x), 0.5f * (c0.y + c1.y), 0.5f * (c0.z + c1.z));
+    PillAcc P;
+    if (e - b > PILL_MAX_TRIS) {
+        P.start(centre, make_float3(0.f, 0.f, 0.f));
+        P.h = 0.0f;
+        const float dx = c1.x - centre.x, dy = c1.y - centre.y, dz = c1.z - centre.z;
+        P.rho = sqrtf(dx * dx + dy * dy + dz * dz);
+    } else {
+        float3 ns = make_float3(0.f, 0.f, 0.f);
+        for (uint32_t j = b + lane; j < e; j += 32) {
+            const float4 r2 = rec_sorted[3 * (size_t)j + 2];
+            ns.x += r2.y; ns.y += r2.z; ns.z += r2.w;
+        }
+        for (int o = 16; o; o >>= 1) {
+            ns.x += __shfl_xor_sync(0xffffffffu, ns.x, o);
+            ns.y += __shfl_xor_sync(0xffffffffu, ns.y, o);
+            ns.z += __shfl_xor_sync(0xffffffffu, ns.z, o);
+        }
+        P.start(centre, ns);  // identical on all lanes (xor-butterfly sums are bitwise equal)
+        for (uint32_t j = b + lane; j < e; j += 32) {
+            const float4 r0 = rec_sorted[3 * (size_t)j], r1 = rec_sorted[3 * (size_t)j + 1],
+                         r2 = rec_sorted[3 * (size_t)j + 2];
+            P.add(r0.x, r0.y, r0.z);
+            P.add(r0.w, r1.x, r1.y);
+            P.add(r1.z, r1.w, r2.x);
+        }
+        for (int o = 16; o; o >>= 1) {
+            P.h = fmaxf(P.h, __shfl_xor_sync(0xffffffffu, P.h, o));
+            P.rho = fmaxf(P.rho, __shfl_xor_sync(0xffffffffu, P.rho, o));
+        }
+    }
+    P.finish(scene_mag(st));
+    if (lane == 0) {
+        ch[1].w = P.rho;
+        ch[2] = make_float4(P.cx, P.cy, P.cz, P.h);
+        ch[3] = make_float4(P.ux, P.uy, P.uz, 0.0f);
+    }
 }
 
 // Karras 2012 delta over the leaf keys (leaf l's key = key of its first sorted triangle).
@@ -223,7 +342,8 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint32_t
 // K4b: one thread per internal node: children + parent links.
 __global__ void __launch_bounds__(256)
 k_hierarchy(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, float4* __restrict__ nodes,
-            uint32_t* __restrict__ leaf_parent, uint32_t* __restrict__ node_parent) {
+            uint32_t* __restrict__ leaf_parent, uint32_t* __restrict__ node_parent,
+            uint2* __restrict__ node_range) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nleaf - 1) return;
     const int d = (delta(keys, K, nleaf, i, i + 1) - delta(keys, K, nleaf, i, i - 1)) >= 0 ? 1 : -1;
@@ -259,8 +379,9 @@ k_hierarchy(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, float4* __
         node_parent[gamma + 1] = ((uint32_t)i << 1) | 1u;
     }
     // boxes are filled by the refit; store the refs now (degenerate bits are OR-ed in by the refit).
-    nodes[4 * (size_t)i + 0].w = __uint_as_float(left);
-    nodes[4 * (size_t)i + 2].w = __uint_as_float(right);
+    nodes[NODE_F4 * (size_t)i + 0].w = __uint_as_float(left);
+    nodes[NODE_F4 * (size_t)i + CHILD_F4].w = __uint_as_float(right);
+    node_range[i] = make_uint2((uint32_t)lo, (uint32_t)hi);  // leaves covered by node i (inclusive)
     if (i == 0) node_parent[0] = 0xffffffffu;
 }
 
@@ -287,10 +408,10 @@ k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
     bool first_level = true;
     for (;;) {
         const uint32_t p = link >> 1, side = link & 1u;
-        float4* nd = nodes + 4 * (size_t)p;
-        // write my box into my side of the parent (the child ref lives in .w of n0 / n2, each
-        // written only by its own side)
-        float4* mine = nd + 2 * side;
+        float4* nd = nodes + NODE_F4 * (size_t)p;
+        // write my box into my side of the parent (the child ref lives in .w of the side's first
+        // float4, each written only by its own side)
+        float4* mine = nd + CHILD_F4 * side;
         uint32_t ref = __float_as_uint(mine[0].w);
         if (first_level && degen) ref |= LEAF_DEGEN_BIT;
         mine[0] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(ref));
@@ -302,7 +423,8 @@ k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
         // both children present: union and go up
         const volatile float4* vn = nd;
         float4 a0 = make_float4(vn[0].x, vn[0].y, vn[0].z, 0.f), a1 = make_float4(vn[1].x, vn[1].y, vn[1].z, 0.f);
-        float4 b0 = make_float4(vn[2].x, vn[2].y, vn[2].z, 0.f), b1 = make_float4(vn[3].x, vn[3].y, vn[3].z, 0.f);
+        float4 b0 = make_float4(vn[CHILD_F4].x, vn[CHILD_F4].y, vn[CHILD_F4].z, 0.f),
+               b1 = make_float4(vn[CHILD_F4 + 1].x, vn[CHILD_F4 + 1].y, vn[CHILD_F4 + 1].z, 0.f);
         lo[0] = fminf(a0.x, b0.x); lo[1] = fminf(a0.y, b0.y); lo[2] = fminf(a0.z, b0.z);
         hi[0] = fmaxf(a1.x, b1.x); hi[1] = fmaxf(a1.y, b1.y); hi[2] = fmaxf(a1.z, b1.z);
         link = node_parent[p];
@@ -351,7 +473,9 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     CK(d.vals_in.ensure(nt * 4));
     CK(d.vals_out.ensure(nt * 4));
     CK(d.tri_id_sorted.ensure(nt * 4));
-    CK(d.nodes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * 64));
+    CK(d.nodes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * NODE_F4 * 16));
+    CK(d.node_range.ensure((size_t)nleaf * 8));
+    CK(d.pill.ensure(nt * 32));
     CK(d.leaf_parent.ensure((size_t)nleaf * 4));
     CK(d.node_parent.ensure((size_t)nleaf * 4));
     CK(d.node_flag.ensure((size_t)nleaf * 4));
@@ -371,24 +495,34 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
                                        d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, 63, s));
     d.launches += 8;  // CUB onesweep: histogram + 8 digit passes (counted approximately)
     k_tri_permute<<<blocks_for(nt, bs), bs, 0, s>>>(d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
-                                                    d.vals_out.as<uint32_t>(), (uint32_t)nt,
-                                                    d.rec_sorted.as<float4>(), d.tri_id_sorted.as<uint32_t>());
+                                                    d.vals_out.as<uint32_t>(), (uint32_t)nt, st,
+                                                    d.rec_sorted.as<float4>(), d.pill.as<float4>(),
+                                                    d.tri_id_sorted.as<uint32_t>());
     d.launches++;
     if (nleaf > 1) {
         CK(cudaMemsetAsync(d.node_flag.p, 0, (size_t)nleaf * 4, s));
         k_hierarchy<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.keys_out.as<uint64_t>(), K, (int)nleaf,
                                                              d.nodes.as<float4>(), d.leaf_parent.as<uint32_t>(),
-                                                             d.node_parent.as<uint32_t>());
+                                                             d.node_parent.as<uint32_t>(), d.node_range.as<uint2>());
         k_refit<<<blocks_for(nleaf, bs), bs, 0, s>>>(d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),
                                                      d.vals_out.as<uint32_t>(), (uint32_t)nt, K, (int)nleaf,
                                                      d.nodes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                      d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
-        d.launches += 2;
+        k_pillbox<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
+            d.rec_sorted.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.nodes.as<float4>(), d.node_range.as<uint2>(), st);
+        d.launches += 3;
     }
     d.bvh.rec = d.rec_sorted.as<float4>();
+    d.bvh.pill = d.pill.as<float4>();
     d.bvh.tri_id = d.tri_id_sorted.as<uint32_t>();
     d.bvh.nodes = d.nodes.as<float4>();
     d.bvh.nleaf = nleaf;
+    if (d.want_stats) {
+        CK(d.stats.ensure(64));
+        CK(cudaMemsetAsync(d.stats.p, 0, 64, s));
+        if (d.stats_mode == 2) CK(cudaMemsetAsync((char*)d.stats.p + 24, 2, 1, s));
+        d.bvh.stats = d.stats.as<unsigned long long>();
+    }
     d.bvh.root = nleaf > 1 ? 0u : (LEAF_BIT | LEAF_DEGEN_BIT);  // single leaf: always take the guarded path
     return cudaGetLastError();
 }

@@ -17,13 +17,17 @@ namespace m2s {
 //   brute-force / row kernels, leaf (Morton) order for the LBVH kernels):
 //       r0 = (a.x, a.y, a.z, b.x)   r1 = (b.y, b.z, c.x, c.y)   r2 = (c.z, n.x, n.y, n.z)
 //       n = cross(b - a, c - a), un-normalised, un-fused (geo.rs:60-64)
-//   LBVH internal node, 64 B = 4 x float4, both child boxes inline (padded -/+1e-4, geo.rs:18-21):
-//       n0 = (Lmin.xyz, bits(left ref))   n1 = (Lmax.xyz, 0)
-//       n2 = (Rmin.xyz, bits(right ref))  n3 = (Rmax.xyz, 0)
+//   triangle pillbox, 32 B = 2 x float4 (leaf order): (centroid.xyz, rho) (unit normal.xyz, h)
+//   LBVH internal node, 128 B = 8 x float4: per child 4 x float4, box (padded -/+1e-4, geo.rs:18-21)
+//   plus pillbox (flat cylinder: centre, axis, radius, half height; see m2s_build.cu):
+//       c0 = (min.xyz, bits(child ref))  c1 = (max.xyz, rho)  c2 = (centre.xyz, h)  c3 = (axis.xyz, 0)
+//       left child at float4 0..3, right child at 4..7
 //   child ref: >= 0 internal node index; < 0 leaf: bit31 set, bit30 = "leaf holds a degenerate
 //   triangle" (slow path with the geo.rs:73-88 guards), bits 0..29 = leaf index. Leaf l owns the
 //   sorted triangles [l*K, min((l+1)*K, nt)).
 // ---------------------------------------------------------------------------------------------------
+constexpr int NODE_F4 = 8;   // float4 per node
+constexpr int CHILD_F4 = 4;  // float4 per child slot
 constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr uint32_t LEAF_DEGEN_BIT = 0x40000000u;
 constexpr uint32_t LEAF_INDEX_MASK = 0x3fffffffu;
@@ -45,6 +49,7 @@ static_assert(sizeof(BuildStatus) == 64, "BuildStatus must be 64 bytes");
 
 struct Bvh {
     const float4* rec;        // leaf-order triangle records
+    const float4* pill;       // leaf-order triangle pillboxes
     const uint32_t* tri_id;   // leaf-order -> original triangle id (| TRI_DEGEN_BIT)
     const float4* nodes;      // internal nodes
     uint32_t nt;              // triangles
@@ -52,6 +57,7 @@ struct Bvh {
     uint32_t leaf_size;       // K
     uint32_t root;            // root ref (a leaf ref when nleaf == 1)
     const BuildStatus* st;    // device pointer: scene bounds (-> pruning slack) and error flags
+    unsigned long long* stats; // optional traversal counters (M2S_STATS=1): nodes, leaves, searches
 };
 
 struct GridParams {
@@ -97,8 +103,12 @@ struct Device {
     // mesh + LBVH
     DevBuf verts, tris;  // staging for the host entry points
     DevBuf rec_orig, rec_sorted, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
-    DevBuf tri_id_sorted, nodes, leaf_parent, node_parent, node_flag, status;
+    DevBuf tri_id_sorted, nodes, leaf_parent, node_parent, node_flag, node_range, pill, status;
     DevBuf rows[3], big_list, big_count;
+    DevBuf stats;             // traversal counters, only with M2S_STATS=1
+    bool want_stats = false;
+    int stats_mode = 0;
+    bool dynamic_fetch = true; // M2S_DYNAMIC=0 selects the static voxel-per-thread kernel
     DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
     int seed_levels = 2;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;

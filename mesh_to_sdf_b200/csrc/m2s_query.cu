@@ -33,6 +33,32 @@ __device__ __forceinline__ float scene_magnitude(const BuildStatus* __restrict__
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// squared lower bound of the distance from p to anything inside the pillbox (centre c, unit axis u,
+// radius rho, half height h); see m2s_build.cu. Plain fp32: a pruning bound, never a result.
+__device__ __forceinline__ float pill_dist2(const f3 p, float cx, float cy, float cz, float ux, float uy, float uz,
+                                            float rho, float h) {
+    const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+    const float a = dx * ux + dy * uy + dz * uz;
+    const float lx = dx - a * ux, ly = dy - a * uy, lz = dz - a * uz;
+    const float l = sqrt_approx(lx * lx + ly * ly + lz * lz);  // 1 MUFU; its 1-2 ulp are inside the slack
+    const float da = fmaxf(fabsf(a) - h, 0.0f), dl = fmaxf(l - rho, 0.0f);
+    return da * da + dl * dl;
+}
+
+// lower bound for one child slot (4 x float4): max(box, pillbox)
+__device__ __forceinline__ float child_dist2(const f3 p, const float4 c0, const float4 c1, const float4 c2,
+                                             const float4 c3) {
+    const float b = box_dist2(p.x, p.y, p.z, c0.x, c0.y, c0.z, c1.x, c1.y, c1.z);
+    const float q = pill_dist2(p, c2.x, c2.y, c2.z, c3.x, c3.y, c3.z, c1.w, c2.w);
+    return fmaxf(b, q);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Nearest search state. bound2 is the squared pruning radius: a subtree / triangle whose squared
 // distance lower bound exceeds bound2 cannot change the result.
@@ -79,13 +105,13 @@ __device__ __forceinline__ void visit_tri(const Bvh& bvh, uint32_t j, bool degen
         if (d2 < s.best2) {
             s.best2 = d2;
             s.slot = j;
-            s.set_bound(sqrtf(d2));
+            s.set_bound(sqrt_approx(d2));
         }
     } else if (MODE == MODE_ARGMIN) {
         if (d2 <= s.best2) {
             const uint32_t id = bvh.tri_id[j] & ~TRI_DEGEN_BIT;
             if (d2 < s.best2 || id < s.id) {
-                if (d2 < s.best2) s.set_bound(sqrtf(d2));
+                if (d2 < s.best2) s.set_bound(sqrt_approx(d2));
                 s.best2 = d2;
                 s.id = id;
                 s.slot = j;
@@ -114,7 +140,13 @@ __device__ __forceinline__ void visit_leaf(const Bvh& bvh, uint32_t ref, const f
     const bool degen = (ref & LEAF_DEGEN_BIT) != 0u;
     const uint32_t b = leaf * bvh.leaf_size;
     const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
-    for (uint32_t j = b; j < e; ++j) visit_tri<MODE>(bvh, j, degen, p, s);
+    for (uint32_t j = b; j < e; ++j) {
+        // plane-disc pretest: skips the exact (un-fused, ~10x costlier) leaf arithmetic for triangles
+        // that provably cannot change the result
+        const float4 q0 = ldg4(bvh.pill + 2 * (size_t)j), q1 = ldg4(bvh.pill + 2 * (size_t)j + 1);
+        if (pill_dist2(p, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q0.w, q1.w) > s.bound2) continue;
+        visit_tri<MODE>(bvh, j, degen, p, s);
+    }
 }
 
 // Seed: evaluate one known-near triangle first so the traversal starts with a tight radius (the
@@ -129,57 +161,103 @@ constexpr uint32_t TRAVERSAL_DONE = 0xffffffffu;  // has LEAF_BIT set; never a r
 
 // Ordered depth-first traversal with a (ref, lower bound) stack; entries are re-checked against the
 // current radius when popped, so a subtree pushed early is skipped without touching memory.
-// "while-while" shape: all lanes of a warp walk internal nodes together, then all visit leaves.
 template <int MODE>
-__device__ __forceinline__ void nearest(const Bvh& bvh, const f3 p, Near<MODE>& s, int* overflow) {
+__device__ __forceinline__ uint32_t pop_next(const uint2* stack, int& sp, const Near<MODE>& s) {
+    while (sp > 0) {
+        const uint2 e = stack[--sp];
+        if (__uint_as_float(e.y) <= s.bound2) return e.x;
+    }
+    return TRAVERSAL_DONE;
+}
+
+// One internal node: returns the next ref to visit (a child, a popped entry or TRAVERSAL_DONE).
+template <int MODE>
+__device__ __forceinline__ uint32_t node_step(const Bvh& bvh, uint32_t cur, const f3 p, const Near<MODE>& s,
+                                              uint2* stack, int& sp, int* overflow) {
+    const float4* nd = bvh.nodes + NODE_F4 * (size_t)cur;
+    const float4 l0 = ldg4(nd), l1 = ldg4(nd + 1), l2 = ldg4(nd + 2), l3 = ldg4(nd + 3);
+    const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
+    const float dl = child_dist2(p, l0, l1, l2, l3);
+    const float dr = child_dist2(p, r0, r1, r2, r3);
+    const uint32_t lref = __float_as_uint(l0.w), rref = __float_as_uint(r0.w);
+    const bool hl = dl <= s.bound2, hr = dr <= s.bound2;
+    if (hl && hr) {
+        const bool left_first = dl <= dr;
+        if (sp < STACK_DEPTH) {
+            stack[sp++] = left_first ? make_uint2(rref, __float_as_uint(dr)) : make_uint2(lref, __float_as_uint(dl));
+        } else {
+            *overflow = 1;
+        }
+        return left_first ? lref : rref;
+    }
+    if (hl) return lref;
+    if (hr) return rref;
+    return pop_next<MODE>(stack, sp, s);
+}
+
+// Phase-batched traversal. Measured on config C3: the 32 voxels of a warp do almost the same total
+// work (sum / (32 * max) = 0.92) but interleave node and leaf steps differently, so a plain
+// while-while loop ran with 11 of 32 threads active. Here every lane first walks internal nodes
+// until it has collected LEAF_BATCH candidate leaves (or is done), then all lanes run the cheap
+// plane-disc / thin-box pretests of their leaves and collect the surviving triangles, then all lanes
+// run the exact (un-fused, reference-order) arithmetic on their survivors. The seed makes the radius
+// tight from the start, so postponing the leaves costs almost no extra nodes.
+constexpr int LEAF_BATCH = 6;
+constexpr int TRI_BATCH = 24;  // >= LEAF_BATCH * typical survivors; flushed when full
+
+template <int MODE>
+__device__ __forceinline__ void nearest(const Bvh& bvh, const f3 p, Near<MODE>& s, int* overflow,
+                                        uint32_t* work = nullptr) {
     if (bvh.nt == 0) return;
     uint2 stack[STACK_DEPTH];
+    uint32_t leafbuf[LEAF_BATCH];
+    uint32_t tribuf[TRI_BATCH];
     int sp = 0;
     uint32_t cur = bvh.root;
+    uint32_t n_nodes = 0, n_leaves = 0;
     for (;;) {
-        while (!(cur & LEAF_BIT)) {
-            const float4* nd = bvh.nodes + 4 * (size_t)cur;
-            const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
-            const float dl = box_dist2(p.x, p.y, p.z, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z);
-            const float dr = box_dist2(p.x, p.y, p.z, n2.x, n2.y, n2.z, n3.x, n3.y, n3.z);
-            const uint32_t lref = __float_as_uint(n0.w), rref = __float_as_uint(n2.w);
-            const bool hl = dl <= s.bound2, hr = dr <= s.bound2;
-            if (hl && hr) {
-                const bool left_first = dl <= dr;
-                if (sp < STACK_DEPTH) {
-                    stack[sp++] = left_first ? make_uint2(rref, __float_as_uint(dr))
-                                             : make_uint2(lref, __float_as_uint(dl));
-                } else {
-                    *overflow = 1;
-                }
-                cur = left_first ? lref : rref;
-            } else if (hl) {
-                cur = lref;
-            } else if (hr) {
-                cur = rref;
+        // ---- phase 1: internal nodes ----
+        int nl = 0;
+        while (cur != TRAVERSAL_DONE && nl < LEAF_BATCH) {
+            if (cur & LEAF_BIT) {
+                leafbuf[nl++] = cur;
+                cur = pop_next<MODE>(stack, sp, s);
             } else {
-                cur = TRAVERSAL_DONE;
-                while (sp > 0) {
-                    const uint2 e = stack[--sp];
-                    if (__uint_as_float(e.y) <= s.bound2) {
-                        cur = e.x;
-                        break;
-                    }
+                ++n_nodes;
+                cur = node_step<MODE>(bvh, cur, p, s, stack, sp, overflow);
+            }
+        }
+        if (nl == 0) break;
+        n_leaves += nl;
+        // ---- phase 2: pretests ----
+        int ntri = 0;
+        for (int k = 0; k < nl; ++k) {
+            const uint32_t ref = leafbuf[k];
+            const uint32_t leaf = ref & LEAF_INDEX_MASK;
+            const uint32_t dg = (ref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u;
+            const uint32_t b = leaf * bvh.leaf_size;
+            const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
+            for (uint32_t j = b; j < e; ++j) {
+                const float4 q0 = ldg4(bvh.pill + 2 * (size_t)j), q1 = ldg4(bvh.pill + 2 * (size_t)j + 1);
+                if (pill_dist2(p, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q0.w, q1.w) > s.bound2) continue;
+                if (ntri == TRI_BATCH) {  // rare: flush
+                    for (int t = 0; t < ntri; ++t)
+                        visit_tri<MODE>(bvh, tribuf[t] & ~TRI_DEGEN_BIT, (tribuf[t] & TRI_DEGEN_BIT) != 0u, p, s);
+                    ntri = 0;
                 }
+                tribuf[ntri++] = j | dg;
             }
         }
-        if (cur == TRAVERSAL_DONE) return;
-        visit_leaf<MODE>(bvh, cur, p, s);
-        cur = TRAVERSAL_DONE;
-        while (sp > 0) {
-            const uint2 e = stack[--sp];
-            if (__uint_as_float(e.y) <= s.bound2) {
-                cur = e.x;
-                break;
-            }
-        }
-        if (cur == TRAVERSAL_DONE) return;
+        // ---- phase 3: exact leaf arithmetic ----
+        for (int t = 0; t < ntri; ++t)
+            visit_tri<MODE>(bvh, tribuf[t] & ~TRI_DEGEN_BIT, (tribuf[t] & TRI_DEGEN_BIT) != 0u, p, s);
     }
+    if (bvh.stats) {
+        atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
+        atomicAdd(bvh.stats + 1, (unsigned long long)n_leaves);
+        atomicAdd(bvh.stats + 2, 1ull);
+    }
+    if (work) *work = n_nodes | (n_leaves << 16);
 }
 
 // Parity of the reference hits of the ray o + t * e_AXIS (t > 0) over all triangles: the sign vote of
@@ -209,8 +287,8 @@ __device__ __forceinline__ uint32_t ray_parity(const Bvh& bvh, const f3 o, int* 
                 if (ray_aligned<AXIS>(o, a, bb, c, &t)) ++count;
             }
         } else {
-            const float4* nd = bvh.nodes + 4 * (size_t)cur;
-            const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
+            const float4* nd = bvh.nodes + NODE_F4 * (size_t)cur;
+            const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + CHILD_F4), n3 = ldg4(nd + CHILD_F4 + 1);
             const float llo[3] = {n0.x, n0.y, n0.z}, lhi[3] = {n1.x, n1.y, n1.z};
             const float rlo[3] = {n2.x, n2.y, n2.z}, rhi[3] = {n3.x, n3.y, n3.z};
             const bool hl = oy >= llo[IY] && oy <= lhi[IY] && oz >= llo[IZ] && oz <= lhi[IZ] && ox <= lhi[AXIS];
@@ -325,8 +403,13 @@ k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const Se
     s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
     if (L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
     int overflow = 0;
-    nearest<MODE>(bvh, p, s, &overflow);
+    uint32_t work = 0;
+    nearest<MODE>(bvh, p, s, &overflow, &work);
     float d = finish<MODE>(bvh, p, s);
+    if (bvh.stats && bvh.stats[3] == 2ull) {  // M2S_STATS=2: emit the per-voxel work instead of the distance
+        out[((size_t)xr * g.ny + y) * g.nz + z] = __uint_as_float(work);
+        return;
+    }
 
     if (RAYSIGN) {
         // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd. The parity

@@ -5,7 +5,7 @@ import numpy as np
 import mesh_to_sdf_b200 as m2s
 from mesh_to_sdf_b200 import synth
 
-def run_grid(name, nu, nv, n, sign, reps=3):
+def run_grid(name, nu, nv, n, sign, reps=int(os.environ.get("REPS", "3"))):
     verts, tris = synth.bumpy_torus(nu, nv)
     mn, mx = synth.padded_grid_box(verts)
     grid = m2s.Grid.from_bounding_box(mn, mx, [n, n, n])

@@ -68,9 +68,10 @@ typedef struct m2s_timings {
     float h2d_ms;   /* host -> device copies (0 for the *_device entry points)             */
     float build_ms; /* triangle records, Morton sort, LBVH hierarchy + refit               */
     float sign_ms;  /* raycast row toggles + scan (grid) / per-query ray walks (points)    */
-    float dist_ms;  /* nearest-triangle kernel (sign applied in its epilogue for grids)    */
+    float dist_ms;  /* the final nearest-triangle kernel alone (sign applied in its epilogue) */
     float d2h_ms;   /* device -> host copy of the result                                   */
     float total_ms; /* first event to last event                                           */
+    float seed_ms;  /* coarse seeding passes that run before the final kernel              */
 } m2s_timings;
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -115,6 +116,14 @@ M2S_API m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, u
                                  const uint32_t* tri_idx, uint64_t nt, const float first_cell[3],
                                  const float cell_size[3], const uint64_t cell_count[3], int sign_method,
                                  float* out);
+
+/* One slab of the same grid, host buffers, single-device context: cells x in [x_begin, x_end) are written
+ * at out_slab[(x - x_begin)*ny*nz + y*nz + z]. This is the per-process call of a one-process-per-GPU
+ * deployment (each rank owns a contiguous range of the flat Vec<f32>, src/grid.rs:122-124). */
+M2S_API m2s_status m2s_generate_grid_sdf_slab(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv,
+                                              const uint32_t* tri_idx, uint64_t nt, const float first_cell[3],
+                                              const float cell_size[3], const uint64_t cell_count[3],
+                                              int sign_method, uint64_t x_begin, uint64_t x_end, float* out_slab);
 
 /* generate_sdf(vertices, indices, query_points, acceleration_method) -> Vec<f32>
  *   replaces src/lib.rs:291-311 and the four drivers it dispatches to:

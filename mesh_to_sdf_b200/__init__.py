@@ -48,7 +48,7 @@ _STATUS_NAMES = {0: "M2S_OK", 1: "M2S_EINVAL", 2: "M2S_EINDEX", 3: "M2S_ENAN", 4
 
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("build_ms", C.c_float), ("sign_ms", C.c_float), ("dist_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("total_ms", C.c_float)]
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("seed_ms", C.c_float)]
 
     def as_dict(self):
         return {k: float(getattr(self, k)) for k, _ in self._fields_}
@@ -81,6 +81,9 @@ def lib() -> C.CDLL:
             L.m2s_device_count.argtypes = [vp]
             L.m2s_synchronize.argtypes = [vp]
             L.m2s_generate_grid_sdf.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, _f, _f, _u64, C.c_int, vp]
+            L.m2s_generate_grid_sdf_slab.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, _f, _f, _u64, C.c_int,
+                                                     C.c_uint64, C.c_uint64, vp]
+            L.m2s_debug_stats.argtypes = [vp, _u64]
             L.m2s_generate_sdf.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, C.c_int, C.c_int, vp]
             L.m2s_generate_grid_sdf_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, _f, _f, _u64, C.c_int,
                                                        C.c_uint64, C.c_uint64, vp]
@@ -326,6 +329,26 @@ class Context:
                                                 grid.first_cell.ctypes.data_as(_f), grid.cell_size.ctypes.data_as(_f),
                                                 cc.ctypes.data_as(_u64), int(sign), out.ctypes.data))
         return out
+
+    def grid_sdf_slab(self, verts: np.ndarray, tris: np.ndarray, grid: Grid, sign: int, x_begin: int, x_end: int,
+                      out: Optional[np.ndarray] = None):
+        """Cells x in [x_begin, x_end) of ``grid`` (the per-rank call of a one-process-per-GPU deployment)."""
+        verts, tris = _mesh_arrays(verts, tris)
+        n = (x_end - x_begin) * grid.cell_count[1] * grid.cell_count[2]
+        if out is None:
+            out = np.empty(n, np.float32)
+        assert out.dtype == np.float32 and out.size == n and out.flags.c_contiguous
+        cc = np.asarray(grid.cell_count, np.uint64)
+        self._check(lib().m2s_generate_grid_sdf_slab(self._h, verts.ctypes.data, len(verts), tris.ctypes.data,
+                                                     len(tris), grid.first_cell.ctypes.data_as(_f),
+                                                     grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
+                                                     int(sign), x_begin, x_end, out.ctypes.data))
+        return out
+
+    def debug_stats(self):
+        a = (C.c_uint64 * 4)()
+        lib().m2s_debug_stats(self._h, a)
+        return [int(x) for x in a]
 
     def sdf(self, verts: np.ndarray, tris: np.ndarray, queries: np.ndarray, accel: int, sign: int,
             out: Optional[np.ndarray] = None):

@@ -77,7 +77,7 @@ cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t
     const uint64_t slab_cells = (uint64_t)(g.x1 - g.x0) * g.ny * g.nz;
     if (nt == 0) {
         d.bvh = Bvh{};
-        if (timed) { cudaEventRecord(d.ev[2], d.stream); cudaEventRecord(d.ev[3], d.stream); }
+        if (timed) { cudaEventRecord(d.ev[2], d.stream); cudaEventRecord(d.ev[3], d.stream); cudaEventRecord(d.ev[6], d.stream); }
         e = launch_fill(d, d_out, slab_cells, FLT_MAX);  // un-seeded cells stay f32::MAX (grid.rs:137-143)
         if (timed) cudaEventRecord(d.ev[4], d.stream);
         return e;
@@ -88,7 +88,8 @@ cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t
     const bool raycast = sign == M2S_SIGN_RAYCAST;
     if (raycast && (e = launch_grid_rows(d, g, &rb)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev[3], d.stream);
-    e = launch_grid_nearest(d, g, raycast ? MODE_UNSIGNED : MODE_NORMAL, raycast ? &rb : nullptr, d_out);
+    e = launch_grid_nearest(d, g, raycast ? MODE_UNSIGNED : MODE_NORMAL, raycast ? &rb : nullptr, d_out,
+                            timed ? d.ev[6] : nullptr);
     if (timed) cudaEventRecord(d.ev[4], d.stream);
     return e;
 }
@@ -126,7 +127,7 @@ cudaError_t enqueue_points(m2s_ctx* ctx, Device& d, const float* d_verts, uint64
     if ((e = launch_status_reset(d, clear_errors)) != cudaSuccess) return e;
     if (nt == 0) {
         d.bvh = Bvh{};
-        if (timed) { cudaEventRecord(d.ev[2], d.stream); cudaEventRecord(d.ev[3], d.stream); }
+        if (timed) { cudaEventRecord(d.ev[2], d.stream); cudaEventRecord(d.ev[3], d.stream); cudaEventRecord(d.ev[6], d.stream); }
         e = launch_fill(d, d_out, nq, FLT_MAX);  // default.rs:54 / bvh.rs:83 fold from f32::MAX
         if (timed) cudaEventRecord(d.ev[4], d.stream);
         return e;
@@ -134,7 +135,7 @@ cudaError_t enqueue_points(m2s_ctx* ctx, Device& d, const float* d_verts, uint64
     if ((e = launch_build(d, d_verts, nv, d_tris, nt, ctx->leaf_size)) != cudaSuccess) return e;
     if ((e = sort_queries(d, d_queries, nq)) != cudaSuccess) return e;
     if (timed) { cudaEventRecord(d.ev[2], d.stream); cudaEventRecord(d.ev[3], d.stream); }
-    e = launch_points(d, nq, plan.mode, plan.sign_rule, d_out);
+    e = launch_points(d, nq, plan.mode, plan.sign_rule, d_out, timed ? d.ev[6] : nullptr);
     if (timed) cudaEventRecord(d.ev[4], d.stream);
     return e;
 }
@@ -152,7 +153,8 @@ void collect_timings(m2s_ctx* ctx, Device& d) {
     cudaEventElapsedTime(&t.h2d_ms, d.ev[0], d.ev[1]);
     cudaEventElapsedTime(&t.build_ms, d.ev[1], d.ev[2]);
     cudaEventElapsedTime(&t.sign_ms, d.ev[2], d.ev[3]);
-    cudaEventElapsedTime(&t.dist_ms, d.ev[3], d.ev[4]);
+    cudaEventElapsedTime(&t.seed_ms, d.ev[3], d.ev[6]);
+    cudaEventElapsedTime(&t.dist_ms, d.ev[6], d.ev[4]);
     cudaEventElapsedTime(&t.d2h_ms, d.ev[4], d.ev[5]);
     cudaEventElapsedTime(&t.total_ms, d.ev[0], d.ev[5]);
     ctx->timings = t;
@@ -277,27 +279,19 @@ m2s_status m2s_debug_stats(m2s_ctx* ctx, uint64_t out[4]) {
 
 // ---- host-buffer entry points ------------------------------------------------------------------------
 
-m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx,
-                                 uint64_t nt, const float first_cell[3], const float cell_size[3],
-                                 const uint64_t cell_count[3], int sign_method, float* out) {
-    if (!ctx) return M2S_EINVAL;
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    ctx->last_error.clear();
-    GridArgs ga{};
-    m2s_status s = check_grid(ctx, first_cell, cell_size, cell_count, sign_method, &ga);
-    if (s != M2S_OK) return s;
-    if ((s = check_mesh(ctx, verts_xyz, nv, tri_idx, nt)) != M2S_OK) return s;
-    if (ga.total == 0) return M2S_OK;  // empty Vec
-    if (!out) return fail(ctx, M2S_EINVAL, "null output pointer");
-
-    const int nd = std::min<uint64_t>((uint64_t)ctx->n_devices, (uint64_t)ga.g.nx);
+// Shared by the whole-grid and the slab entry points: cells x in [xa, xb) are split over the context's
+// devices and written at out[(x - xa) * ny * nz + ...].
+static m2s_status grid_host(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx, uint64_t nt,
+                            const GridArgs& ga, int sign_method, uint64_t xa, uint64_t xb, float* out) {
+    const uint64_t span = xb - xa;
+    const int nd = (int)std::min<uint64_t>((uint64_t)ctx->n_devices, span);
     const uint64_t plane = (uint64_t)ga.g.ny * ga.g.nz;
     // enqueue on every device, then wait for all of them
     for (int i = 0; i < nd; ++i) {
         Device& d = ctx->dev[i];
         GridParams g = ga.g;
-        g.x0 = (uint32_t)((uint64_t)ga.g.nx * i / nd);
-        g.x1 = (uint32_t)((uint64_t)ga.g.nx * (i + 1) / nd);
+        g.x0 = (uint32_t)(xa + span * i / nd);
+        g.x1 = (uint32_t)(xa + span * (i + 1) / nd);
         const uint64_t cells = (uint64_t)(g.x1 - g.x0) * plane;
         CU(ctx, cudaSetDevice(d.ordinal));
         const bool timed = i == 0;
@@ -312,7 +306,8 @@ m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t 
         if (timed) cudaEventRecord(d.ev[1], d.stream);
         CU(ctx, enqueue_grid(ctx, d, d.verts.as<float>(), nv, d.tris.as<uint32_t>(), nt, g, sign_method,
                              d.out.as<float>(), true, timed));
-        CU(ctx, cudaMemcpyAsync(out + (uint64_t)g.x0 * plane, d.out.p, cells * 4, cudaMemcpyDeviceToHost, d.stream));
+        CU(ctx, cudaMemcpyAsync(out + (uint64_t)(g.x0 - xa) * plane, d.out.p, cells * 4, cudaMemcpyDeviceToHost,
+                                d.stream));
         CU(ctx, cudaMemcpyAsync(d.h_status, d.status.p, sizeof(BuildStatus), cudaMemcpyDeviceToHost, d.stream));
         if (timed) cudaEventRecord(d.ev[5], d.stream);
     }
@@ -325,6 +320,38 @@ m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t 
     }
     collect_timings(ctx, ctx->dev[0]);
     return result;
+}
+
+m2s_status m2s_generate_grid_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx,
+                                 uint64_t nt, const float first_cell[3], const float cell_size[3],
+                                 const uint64_t cell_count[3], int sign_method, float* out) {
+    if (!ctx) return M2S_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->last_error.clear();
+    GridArgs ga{};
+    m2s_status s = check_grid(ctx, first_cell, cell_size, cell_count, sign_method, &ga);
+    if (s != M2S_OK) return s;
+    if ((s = check_mesh(ctx, verts_xyz, nv, tri_idx, nt)) != M2S_OK) return s;
+    if (ga.total == 0) return M2S_OK;  // empty Vec
+    if (!out) return fail(ctx, M2S_EINVAL, "null output pointer");
+    return grid_host(ctx, verts_xyz, nv, tri_idx, nt, ga, sign_method, 0, ga.g.nx, out);
+}
+
+m2s_status m2s_generate_grid_sdf_slab(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx,
+                                      uint64_t nt, const float first_cell[3], const float cell_size[3],
+                                      const uint64_t cell_count[3], int sign_method, uint64_t x_begin,
+                                      uint64_t x_end, float* out_slab) {
+    if (!ctx) return M2S_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->last_error.clear();
+    GridArgs ga{};
+    m2s_status s = check_grid(ctx, first_cell, cell_size, cell_count, sign_method, &ga);
+    if (s != M2S_OK) return s;
+    if ((s = check_mesh(ctx, verts_xyz, nv, tri_idx, nt)) != M2S_OK) return s;
+    if (x_begin > x_end || x_end > ga.g.nx) return fail(ctx, M2S_EINVAL, "slab outside the grid");
+    if (x_begin == x_end || ga.total == 0) return M2S_OK;
+    if (!out_slab) return fail(ctx, M2S_EINVAL, "null output pointer");
+    return grid_host(ctx, verts_xyz, nv, tri_idx, nt, ga, sign_method, x_begin, x_end, out_slab);
 }
 
 m2s_status m2s_generate_sdf(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, const uint32_t* tri_idx,

@@ -126,11 +126,13 @@ cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
 
 cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb);
 
-cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out);
+cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,
+                                cudaEvent_t after_seeds = nullptr);
 
 // queries must have been Morton-sorted into d.q_sorted by sort_queries().
 // sign_rule: 0 = value already signed / unsigned, 1 = +X ray parity, 3 = best of the three axes
-cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out);
+cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out,
+                          cudaEvent_t after_seeds = nullptr);
 
 cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value);
 

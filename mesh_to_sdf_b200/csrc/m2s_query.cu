@@ -704,7 +704,8 @@ static float grid_magnitude(const GridParams& g) {
 
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out) {
+cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,
+                                cudaEvent_t after_seeds) {
     cudaStream_t s = d.stream;
     const uint32_t sx = g.x1 - g.x0;
     const uint64_t nblocks = (uint64_t)cdiv(sx, BX) * cdiv(g.ny, BY) * cdiv(g.nz, BZ);
@@ -729,6 +730,7 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
             L = SeedLevel{buf.as<uint32_t>(), cx, cy, cz, stride};
         }
     }
+    if (after_seeds) cudaEventRecord(after_seeds, s);
     const unsigned nb = (unsigned)nblocks;
     if (rb) {
         k_grid_nearest<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2],
@@ -743,7 +745,7 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
 }
 
 // sign_rule: 0 none, 1 = +X parity, 3 = best of three axes
-cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out) {
+cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out, cudaEvent_t after_seeds) {
     cudaStream_t s = d.stream;
     if (nq == 0) return cudaSuccess;
     const float4* q = d.q_sorted.as<float4>();
@@ -767,6 +769,7 @@ cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float
             parent_count = count;
         }
     }
+    if (after_seeds) cudaEventRecord(after_seeds, s);
     const unsigned nb = blocks_for(nq, 256);
     if (mode == MODE_NORMAL) k_points<MODE_NORMAL, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, parent, parent_count, d_out, st);
     else if (mode == MODE_ARGMIN) k_points<MODE_ARGMIN, 0><<<nb, 256, 0, s>>>(d.bvh, q, n, parent, parent_count, d_out, st);

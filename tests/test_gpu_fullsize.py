@@ -1,0 +1,83 @@
+"""GPU checks at BASELINE.json's full sizes (C2, C3, C4): a seeded random sample against the exact oracle plus
+size-independent properties of a distance field — 1-Lipschitz between neighbouring cells, sign changes only
+next to the surface, slab decomposition invariance, agreement between the grid and the generic path."""
+import numpy as np
+import pytest
+
+from mesh_to_sdf_b200 import synth
+from conftest import mesh_diag
+
+pytestmark = pytest.mark.gpu
+
+
+def grid_case(m2s, nu, nv, n):
+    verts, tris = synth.bumpy_torus(nu, nv)
+    mn, mx = synth.padded_grid_box(verts)
+    return verts, tris, m2s.Grid.from_bounding_box(mn, mx, [n, n, n])
+
+
+def lipschitz_and_sign(sdf, grid, n):
+    a = np.abs(sdf).reshape(n, n, n)
+    s = np.signbit(sdf).reshape(n, n, n)
+    for axis in range(3):
+        h = float(abs(grid.cell_size[axis]))
+        assert np.max(np.abs(np.diff(a, axis=axis))) <= h * (1 + 1e-4) + 1e-6
+        # generate/grid.rs:784-805: the sign only changes within one cell of the surface
+        flip = np.diff(s.astype(np.int8), axis=axis) != 0
+        lo = np.minimum(np.take(a, range(0, n - 1), axis=axis), np.take(a, range(1, n), axis=axis))
+        assert np.all(lo[flip] <= h * (1 + 1e-4))
+
+
+def test_c2_normal_128(m2s, oracle):
+    verts, tris, grid = grid_case(m2s, 64, 40, 128)
+    sdf = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(tris), grid, m2s.SignMethod.Normal)
+    idx = np.random.default_rng(2).choice(128 ** 3, 20000, replace=False).astype(np.uint64)
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, 1, idx)
+    tol = 1e-4 * mesh_diag(verts)
+    assert np.max(np.abs(sdf[idx] - want)) <= tol
+    assert np.max(np.abs(np.abs(sdf[idx]) - np.abs(want))) <= 4e-6
+    assert np.array_equal(np.signbit(sdf[idx]), np.signbit(want))
+    lipschitz_and_sign(sdf, grid, 128)
+    # outward-wound watertight mesh: Normal and Raycast agree on the sign
+    ray = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(tris), grid, m2s.SignMethod.Raycast)
+    assert np.mean(np.signbit(ray) != np.signbit(sdf)) < 1e-4
+    assert np.max(np.abs(np.abs(ray) - np.abs(sdf))) <= 4e-6
+
+
+def test_c3_raycast_256(m2s, oracle):
+    verts, tris, grid = grid_case(m2s, 256, 196, 256)
+    assert len(tris) == 100352
+    sdf = m2s.generate_grid_sdf(verts, m2s.Topology.TriangleList(tris), grid, m2s.SignMethod.Raycast)
+    idx = np.random.default_rng(3).choice(256 ** 3, 4000, replace=False).astype(np.uint64)
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, 0, idx)
+    assert np.array_equal(sdf[idx].view(np.uint32), want.view(np.uint32))  # bit-exact, value and sign
+    lipschitz_and_sign(sdf, grid, 256)
+    frac_inside = float(np.mean(sdf < 0))
+    assert 0.10 < frac_inside < 0.20
+    # slab invariance: two half-grids through the slab entry point == the whole grid
+    ctx = m2s.default_context()
+    lo = ctx.grid_sdf_slab(verts, tris, grid, 0, 0, 100)
+    hi = ctx.grid_sdf_slab(verts, tris, grid, 0, 100, 256)
+    assert np.array_equal(np.concatenate([lo, hi]).view(np.uint32), sdf.view(np.uint32))
+    # the generic path at the same cell centres gives the same field (generate/grid.rs:692-724 at scale)
+    cells = idx[:2000]
+    q = np.array([grid.get_cell_center(grid.get_cell_integer_coordinates(int(i))) for i in cells], np.float32)
+    gen = m2s.generate_sdf(verts, m2s.Topology.TriangleList(tris), q, m2s.AccelerationMethod.RtreeBvh)
+    assert np.array_equal(np.abs(gen).view(np.uint32), np.abs(sdf[cells]).view(np.uint32))
+    assert np.mean(np.signbit(gen) != np.signbit(sdf[cells])) < 1e-3
+
+
+def test_c4_points_1m(m2s, oracle):
+    verts, tris = synth.bumpy_torus(640, 392)
+    assert len(tris) == 501760
+    mn, mx = synth.padded_grid_box(verts)
+    q = synth.splitmix64_points(1_000_000, mn, mx)
+    sdf = m2s.generate_sdf(verts, m2s.Topology.TriangleList(tris), q, m2s.AccelerationMethod.RtreeBvh)
+    pick = np.random.default_rng(4).choice(len(q), 1500, replace=False)
+    want = oracle.generate_sdf(verts, tris, q[pick], 3)
+    assert np.array_equal(sdf[pick].view(np.uint32), want.view(np.uint32))
+    # 1-Lipschitz between arbitrary query pairs
+    i, j = np.random.default_rng(5).integers(0, len(q), (2, 200000))
+    gap = np.linalg.norm(q[i].astype(np.float64) - q[j].astype(np.float64), axis=1)
+    assert np.all(np.abs(np.abs(sdf[i]) - np.abs(sdf[j])) <= gap * (1 + 1e-5) + 1e-6)
+    assert 0.10 < float(np.mean(sdf < 0)) < 0.20

@@ -203,7 +203,7 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
             return M2S_ECUDA;
         }
         std::memset(d.h_status, 0, sizeof(BuildStatus));
-        if (const char* e = std::getenv("M2S_DYNAMIC")) d.dynamic_fetch = std::atoi(e) != 0;
+        if (const char* e = std::getenv("M2S_PACKET")) d.packet = std::atoi(e) != 0;
         if (const char* e = std::getenv("M2S_STATS")) { d.want_stats = std::atoi(e) != 0; d.stats_mode = std::atoi(e); }
         if (const char* e = std::getenv("M2S_SEED_LEVELS")) d.seed_levels = std::max(0, std::min(2, std::atoi(e)));
     }

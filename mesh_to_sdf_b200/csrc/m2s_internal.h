@@ -108,7 +108,7 @@ struct Device {
     DevBuf stats;             // traversal counters, only with M2S_STATS=1
     bool want_stats = false;
     int stats_mode = 0;
-    bool dynamic_fetch = true; // M2S_DYNAMIC=0 selects the static voxel-per-thread kernel
+    bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
     DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
     int seed_levels = 2;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;

@@ -427,6 +427,146 @@ k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const Se
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Packet variant of the grid kernel (the default). The 32 voxels of a warp tile (2 x 4 x 4 cells)
+// need almost the same nodes, so the warp walks the tree ONCE with a shared stack in shared memory:
+// node loads are warp-uniform (one L1 wavefront instead of up to 32 — the per-lane kernel saturated
+// the L1 data pipe at 94 %), control flow is uniform (no SIMT divergence in the node loop) and every
+// lane still prunes with its own radius, so each voxel's result is the same exact minimum. A child
+// is entered if any lane needs it; children are ordered by the warp-min lower bound; a stack entry
+// is dropped when its warp-min bound exceeds the warp-max radius. Triangles that survive a lane's
+// plane-disc pretest are queued per lane and evaluated with the exact arithmetic in batches.
+// ---------------------------------------------------------------------------------------------------
+constexpr int PKT_STACK = 128;
+constexpr int PKT_TRI_BATCH = 16;   // per-lane queue of surviving triangles
+constexpr int PKT_FLUSH_AT = 6;     // flush all lanes' queues once any lane holds this many
+
+template <int MODE>
+__device__ __forceinline__ float warp_max_bound(const Near<MODE>& s, bool valid) {
+    const unsigned b = valid ? __float_as_uint(s.bound2) : 0u;  // bound2 >= 0: uint order == float order
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, b));
+}
+
+template <int MODE, bool RAYSIGN>
+__global__ void __launch_bounds__(256)
+k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
+                   const uint32_t* __restrict__ px, const uint32_t* __restrict__ py,
+                   const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st) {
+    __shared__ uint2 s_stack[8][PKT_STACK];
+    const unsigned full = 0xffffffffu;
+    const uint32_t warp = threadIdx.x >> 5;
+    uint32_t xr, y, z;
+    brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
+    const uint32_t x = g.x0 + xr;
+    const bool valid = x < g.x1 && y < g.ny && z < g.nz;
+    if (!__any_sync(full, valid)) return;  // warp-uniform
+
+    const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
+    Near<MODE> s;
+    s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
+    if (valid && L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
+    float max_b = warp_max_bound<MODE>(s, valid);
+
+    uint32_t tribuf[PKT_TRI_BATCH];
+    int ntri = 0;
+    int sp = 0;
+    int overflow = 0;
+    uint32_t n_nodes = 0, n_leaves = 0;
+    uint2* stack = s_stack[warp];
+    uint32_t cur = bvh.nt ? bvh.root : TRAVERSAL_DONE;
+
+    auto pop = [&]() -> uint32_t {
+        uint32_t r = TRAVERSAL_DONE;
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if (__uint_as_float(e.y) <= max_b) {
+                r = e.x;
+                break;
+            }
+        }
+        __syncwarp();  // every lane has read its entry before lane 0 may overwrite the slot
+        return r;
+    };
+    auto flush = [&]() {
+        const int most = __reduce_max_sync(full, ntri);
+        for (int t = 0; t < most; ++t)
+            if (t < ntri) visit_tri<MODE>(bvh, tribuf[t] & ~TRI_DEGEN_BIT, (tribuf[t] & TRI_DEGEN_BIT) != 0u, p, s);
+        ntri = 0;
+        max_b = warp_max_bound<MODE>(s, valid);
+    };
+
+    while (cur != TRAVERSAL_DONE) {
+        if (!(cur & LEAF_BIT)) {
+            ++n_nodes;
+            const float4* nd = bvh.nodes + NODE_F4 * (size_t)cur;  // warp-uniform address
+            const float4 l0 = ldg4(nd), l1 = ldg4(nd + 1), l2 = ldg4(nd + 2), l3 = ldg4(nd + 3);
+            const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
+            const float dl = child_dist2(p, l0, l1, l2, l3);
+            const float dr = child_dist2(p, r0, r1, r2, r3);
+            const bool hl = valid && dl <= s.bound2, hr = valid && dr <= s.bound2;
+            const unsigned bl = __ballot_sync(full, hl), br = __ballot_sync(full, hr);
+            const uint32_t lref = __float_as_uint(l0.w), rref = __float_as_uint(r0.w);
+            if (bl && br) {
+                // warp-min lower bounds over the lanes that want the child
+                const unsigned ml = __reduce_min_sync(full, hl ? __float_as_uint(dl) : 0x7f800000u);
+                const unsigned mr = __reduce_min_sync(full, hr ? __float_as_uint(dr) : 0x7f800000u);
+                const bool left_first = ml <= mr;
+                if (sp < PKT_STACK) {
+                    if ((threadIdx.x & 31) == 0) stack[sp] = left_first ? make_uint2(rref, mr) : make_uint2(lref, ml);
+                    ++sp;
+                    __syncwarp();
+                } else {
+                    overflow = 1;
+                }
+                cur = left_first ? lref : rref;
+            } else if (bl) {
+                cur = lref;
+            } else if (br) {
+                cur = rref;
+            } else {
+                cur = pop();
+            }
+        } else {
+            ++n_leaves;
+            const uint32_t leaf = cur & LEAF_INDEX_MASK;
+            const uint32_t dg = (cur & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u;
+            const uint32_t b = leaf * bvh.leaf_size;
+            const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
+            for (uint32_t j = b; j < e; ++j) {  // warp-uniform loop, uniform loads
+                const float4 q0 = ldg4(bvh.pill + 2 * (size_t)j), q1 = ldg4(bvh.pill + 2 * (size_t)j + 1);
+                const bool want = valid && pill_dist2(p, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q0.w, q1.w) <= s.bound2;
+                if (want) tribuf[ntri++] = j | dg;
+                // a full queue anywhere forces a flush before the next triangle
+                if (__any_sync(full, ntri == PKT_TRI_BATCH)) flush();
+            }
+            if (__any_sync(full, ntri >= PKT_FLUSH_AT)) flush();
+            cur = pop();
+        }
+    }
+    flush();
+
+    if (valid) {
+        float d = finish<MODE>(bvh, p, s);
+        if (RAYSIGN) {
+            // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd.
+            const uint32_t rowx = y * g.nz + z, rowy = x * g.nz + z, rowz = x * g.ny + y;
+            const uint32_t rows_x = g.ny * g.nz, rows_y = g.nx * g.nz, rows_z = g.nx * g.ny;
+            const uint32_t hx = (px[(size_t)(x >> 5) * rows_x + rowx] >> (x & 31)) & 1u;
+            const uint32_t hy = (py[(size_t)(y >> 5) * rows_y + rowy] >> (y & 31)) & 1u;
+            const uint32_t hz = (pz[(size_t)(z >> 5) * rows_z + rowz] >> (z & 31)) & 1u;
+            if (hx + hy + hz >= 2u) d = -d;
+        }
+        out[((size_t)xr * g.ny + y) * g.nz + z] = d;
+        if (MODE == MODE_NORMAL && s.nan) atomicExch(&st->nan_distance, 1);
+    }
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+    if (bvh.stats && (threadIdx.x & 31) == 0) {
+        atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
+        atomicAdd(bvh.stats + 1, (unsigned long long)n_leaves);
+        atomicAdd(bvh.stats + 2, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Grid Raycast rows (generate/grid.rs:568-684). Instead of walking a tree per ray, every triangle
 // finds the few rows whose start-cell centre falls inside its padded, projected box (the box is
 // the bvh crate's filter, geo.rs:4-22), evaluates geo.rs:165-216 there and toggles bit k
@@ -446,8 +586,10 @@ __device__ __forceinline__ void axis_range(float first, float size, uint32_t c0,
         *i1 = c1 - 1;
         return;
     }
-    const float a = floorf((lo - first) / size) - 2.0f;
-    const float b = ceilf((hi - first) / size) + 2.0f;
+    // exact index set is [ceil(xlo), floor(xhi)]; floor / ceil the other way absorbs the rounding of the
+    // quotient (far below one cell unless the grid has > 2^20 cells per axis) — callers re-test exactly
+    const float a = floorf((lo - first) / size) - ((hi - lo) > 1048576.0f * size ? 1.0f : 0.0f);
+    const float b = ceilf((hi - first) / size) + ((hi - lo) > 1048576.0f * size ? 1.0f : 0.0f);
     if (b < (float)c0 || a > (float)(c1 - 1)) { *i0 = 1; *i1 = 0; return; }
     *i0 = a <= (float)c0 ? c0 : (uint32_t)a;
     *i1 = b >= (float)(c1 - 1) ? c1 - 1 : (uint32_t)b;
@@ -517,7 +659,7 @@ __device__ __forceinline__ void row_test(const RowCtx& g, const TriAxis& T, int 
     atomicXor(bits + (size_t)(last >> 5) * rows + row, 1u << (last & 31));
 }
 
-constexpr uint32_t ROWS_INLINE_MAX = 48;
+constexpr uint32_t ROWS_INLINE_MAX = 96;
 
 __global__ void __launch_bounds__(256)
 k_rows_small(const float4* __restrict__ rec, uint32_t nt, const RowCtx g, uint32_t* __restrict__ b0,
@@ -732,6 +874,20 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
     }
     if (after_seeds) cudaEventRecord(after_seeds, s);
     const unsigned nb = (unsigned)nblocks;
+    if (d.packet) {
+        if (rb) {
+            k_grid_nearest_pkt<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, rb->bits[0], rb->bits[1],
+                                                                       rb->bits[2], d_out, st);
+        } else if (mode == MODE_NORMAL) {
+            k_grid_nearest_pkt<MODE_NORMAL, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, nullptr, nullptr, nullptr,
+                                                                      d_out, st);
+        } else {
+            k_grid_nearest_pkt<MODE_UNSIGNED, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, nullptr, nullptr, nullptr,
+                                                                        d_out, st);
+        }
+        d.launches++;
+        return cudaGetLastError();
+    }
     if (rb) {
         k_grid_nearest<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2],
                                                                d_out, st);

@@ -11,8 +11,8 @@ def stats(ctx):
     L.m2s_debug_stats(ctx._h, a)
     return [int(x) for x in a]
 import itertools
-for dyn, lev, leaf in itertools.product((0,), (0, 1, 2), (2, 4, 8)):
-    os.environ["M2S_SEED_LEVELS"] = str(lev); os.environ["M2S_LEAF_SIZE"] = str(leaf); os.environ["M2S_DYNAMIC"] = str(dyn)
+for dyn, lev, leaf in itertools.product((0, 1), (1, 2), (4, 8)):
+    os.environ["M2S_SEED_LEVELS"] = str(lev); os.environ["M2S_LEAF_SIZE"] = str(leaf); os.environ["M2S_PACKET"] = str(dyn)
     with m2s.Context() as ctx:
         for name, nu, nv, n, sign in (("C2", 64, 40, 128, 1), ("C3", 256, 196, 256, 0)):
             verts, tris = synth.bumpy_torus(nu, nv)
@@ -21,7 +21,7 @@ for dyn, lev, leaf in itertools.product((0,), (0, 1, 2), (2, 4, 8)):
             out = ctx.grid_sdf(verts, tris, grid, sign)
             out = ctx.grid_sdf(verts, tris, grid, sign)
             s = stats(ctx)
-            print(f"dyn={dyn} seeds={lev} leaf={leaf} {name}: searches {s[2]} nodes/search {s[0]/max(s[2],1):.1f} leaves/search {s[1]/max(s[2],1):.1f} dist_ms {ctx.timings()['dist_ms']:.2f}", flush=True)
+            print(f"packet={dyn} seeds={lev} leaf={leaf} {name}: searches {s[2]} nodes/search {s[0]/max(s[2],1):.1f} leaves/search {s[1]/max(s[2],1):.1f} dist_ms {ctx.timings()['dist_ms']:.2f}", flush=True)
             if name == "C3" and lev == 0 and leaf == 4:
                 # far vs near split: histogram of |d|
                 a = np.abs(out)

@@ -1,0 +1,226 @@
+// mesh_to_sdf.hpp — header-only C++17 host facade over the C ABI of m2s.h, mirroring the public API of the Rust
+// crate Azkellas/mesh_to_sdf 0.4.0 (mesh_to_sdf/src/lib.rs:146-311, src/grid.rs:30-170): same names, argument
+// meaning and error behaviour. The reference's toolchain (Rust) is absent from this build environment, so this is
+// the compiled-language host side that is actually built and tested here; the Rust facade with the identical
+// surface is in rust/mesh_to_sdf.
+//
+//   Rust                                   C++ (namespace mesh_to_sdf)
+//   generate_sdf(&v, Topology, &q, accel)  generate_sdf(v, topology, q, accel)         -> std::vector<float>
+//   generate_grid_sdf(&v, Topology, &g, s) generate_grid_sdf(v, topology, grid, sign)  -> std::vector<float>
+//   panic!                                 throws mesh_to_sdf::Panic
+//   trait Point                            any type with .x .y .z floats or operator[] (see point_traits)
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <limits>
+#include <mutex>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <variant>
+#include <vector>
+
+#include "m2s.h"
+
+namespace mesh_to_sdf {
+
+struct Panic : std::runtime_error {
+    int status;
+    Panic(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+// ---- Point (src/point.rs:21-62): constructor + x/y/z ------------------------------------------------------------
+template <class V, class = void>
+struct point_traits {  // default: indexable (std::array<float,3>, float[3]-likes)
+    static V make(float x, float y, float z) { return V{x, y, z}; }
+    static float x(const V& v) { return v[0]; }
+    static float y(const V& v) { return v[1]; }
+    static float z(const V& v) { return v[2]; }
+};
+template <class V>
+struct point_traits<V, std::void_t<decltype(std::declval<V>().x), decltype(std::declval<V>().z)>> {  // .x .y .z
+    static V make(float x, float y, float z) { return V{x, y, z}; }
+    static float x(const V& v) { return v.x; }
+    static float y(const V& v) { return v.y; }
+    static float z(const V& v) { return v.z; }
+};
+
+// ---- enums (declaration order of lib.rs:204-239) ----------------------------------------------------------------
+enum class SignMethod { Raycast = 0, Normal = 1 };
+
+struct AccelerationMethod {
+    enum Kind { None = 0, Bvh = 1, Rtree = 2, RtreeBvh = 3 } kind = RtreeBvh;  // #[default] RtreeBvh
+    SignMethod sign = SignMethod::Raycast;
+    static AccelerationMethod none(SignMethod s) { return {None, s}; }
+    static AccelerationMethod bvh(SignMethod s) { return {Bvh, s}; }
+    static AccelerationMethod rtree() { return {Rtree, SignMethod::Raycast}; }
+    static AccelerationMethod rtree_bvh() { return {RtreeBvh, SignMethod::Raycast}; }
+};
+
+// ---- Topology (lib.rs:151-193) ------------------------------------------------------------------------------------
+template <class I>
+struct Topology {
+    enum Kind { TriangleList = 0, TriangleStrip = 1 } kind;
+    const I* indices;  // nullptr == None: 0..vertices.len()
+    size_t count;
+    static Topology triangle_list(const std::vector<I>& idx) { return {TriangleList, idx.data(), idx.size()}; }
+    static Topology triangle_strip(const std::vector<I>& idx) { return {TriangleStrip, idx.data(), idx.size()}; }
+    static Topology triangle_list() { return {TriangleList, nullptr, 0}; }
+    static Topology triangle_strip() { return {TriangleStrip, nullptr, 0}; }
+    std::vector<uint32_t> get_triangles(size_t n_vertices) const {
+        static_assert(sizeof(I) == 2 || sizeof(I) == 4, "I must be u16 or u32");
+        const uint64_t nt = m2s_expand_topology(kind, indices, (int)sizeof(I), count, n_vertices, nullptr);
+        std::vector<uint32_t> out(nt * 3);
+        if (nt) m2s_expand_topology(kind, indices, (int)sizeof(I), count, n_vertices, out.data());
+        return out;
+    }
+};
+
+// ---- Grid / SnapResult (src/grid.rs) ------------------------------------------------------------------------------
+struct SnapResult {
+    bool inside;
+    std::array<size_t, 3> cell;
+    bool operator==(const SnapResult& o) const { return inside == o.inside && cell == o.cell; }
+};
+
+template <class V>
+class Grid {
+    using T = point_traits<V>;
+    V first_cell_, cell_size_;
+    std::array<size_t, 3> cell_count_;
+
+  public:
+    Grid(V first_cell, V cell_size, std::array<size_t, 3> cell_count)
+        : first_cell_(first_cell), cell_size_(cell_size), cell_count_(cell_count) {}
+    static Grid from_bounding_box(const V& bbox_min, const V& bbox_max, std::array<size_t, 3> cell_count) {
+        const float mn[3] = {T::x(bbox_min), T::y(bbox_min), T::z(bbox_min)};
+        const float mx[3] = {T::x(bbox_max), T::y(bbox_max), T::z(bbox_max)};
+        const uint64_t cc[3] = {cell_count[0], cell_count[1], cell_count[2]};
+        float first[3], size[3];
+        m2s_grid_from_bounding_box(mn, mx, cc, first, size);
+        return Grid(T::make(first[0], first[1], first[2]), T::make(size[0], size[1], size[2]), cell_count);
+    }
+    V get_first_cell() const { return first_cell_; }
+    V get_cell_size() const { return cell_size_; }
+    std::array<size_t, 3> get_cell_count() const { return cell_count_; }
+    size_t get_total_cell_count() const { return cell_count_[0] * cell_count_[1] * cell_count_[2]; }
+    V get_last_cell() const {
+        return T::make(T::x(first_cell_) + (float)cell_count_[0] * T::x(cell_size_),
+                       T::y(first_cell_) + (float)cell_count_[1] * T::y(cell_size_),
+                       T::z(first_cell_) + (float)cell_count_[2] * T::z(cell_size_));
+    }
+    std::pair<V, V> get_bounding_box() const {
+        const float lo[3] = {T::x(first_cell_) - T::x(cell_size_) * 0.5f, T::y(first_cell_) - T::y(cell_size_) * 0.5f,
+                             T::z(first_cell_) - T::z(cell_size_) * 0.5f};
+        return {T::make(lo[0], lo[1], lo[2]),
+                T::make(lo[0] + (float)cell_count_[0] * T::x(cell_size_), lo[1] + (float)cell_count_[1] * T::y(cell_size_),
+                        lo[2] + (float)cell_count_[2] * T::z(cell_size_))};
+    }
+    size_t get_cell_idx(const std::array<size_t, 3>& c) const {
+        return c[2] + cell_count_[2] * (c[1] + cell_count_[1] * c[0]);
+    }
+    std::array<size_t, 3> get_cell_integer_coordinates(size_t idx) const {
+        return {idx / (cell_count_[1] * cell_count_[2]), (idx / cell_count_[2]) % cell_count_[1], idx % cell_count_[2]};
+    }
+    V get_cell_center(const std::array<size_t, 3>& c) const {
+        return T::make(T::x(first_cell_) + (float)c[0] * T::x(cell_size_), T::y(first_cell_) + (float)c[1] * T::y(cell_size_),
+                       T::z(first_cell_) + (float)c[2] * T::z(cell_size_));
+    }
+    SnapResult snap_point_to_grid(const V& p) const {
+        const V lo = get_bounding_box().first;
+        const float q[3] = {(T::x(p) - T::x(lo)) / T::x(cell_size_), (T::y(p) - T::y(lo)) / T::y(cell_size_),
+                            (T::z(p) - T::z(lo)) / T::z(cell_size_)};
+        SnapResult r{true, {0, 0, 0}};
+        for (int i = 0; i < 3; ++i) {
+            const float f = std::floor(q[i]);
+            long long raw = f != f ? 0 : (f >= 9.2e18f ? std::numeric_limits<long long>::max()
+                                                       : (f <= -9.2e18f ? std::numeric_limits<long long>::min() : (long long)f));
+            long long hi = (long long)cell_count_[i] - 1;
+            long long c = raw < 0 ? 0 : (raw > hi ? hi : raw);
+            if (c != raw) r.inside = false;
+            r.cell[i] = (size_t)c;
+        }
+        return r;
+    }
+};
+
+// ---- process-global context (the Rust facade keeps a OnceLock<Mutex<..>> the same way) --------------------------
+namespace detail {
+inline m2s_ctx* context() {
+    static m2s_ctx* ctx = [] {
+        std::vector<int> devices;
+        if (const char* e = std::getenv("M2S_DEVICES")) {
+            std::string s(e);
+            size_t pos = 0;
+            while (pos < s.size()) {
+                size_t next = s.find(',', pos);
+                if (next == std::string::npos) next = s.size();
+                if (next > pos) devices.push_back(std::atoi(s.substr(pos, next - pos).c_str()));
+                pos = next + 1;
+            }
+        }
+        m2s_ctx* c = nullptr;
+        const m2s_status rc = m2s_create(devices.empty() ? nullptr : devices.data(), (int)devices.size(), &c);
+        if (rc != M2S_OK) throw Panic(rc, "mesh_to_sdf: no usable CUDA device; libm2s has no CPU fallback");
+        return c;
+    }();
+    return ctx;
+}
+inline void check(m2s_ctx* c, m2s_status rc) {
+    if (rc == M2S_OK) return;
+    const std::string msg = m2s_last_error(c);
+    if (rc == M2S_ENAN) throw Panic(rc, "NaN distance (" + msg + ")");           // lib.rs:257
+    if (rc == M2S_EINDEX) throw Panic(rc, "index out of bounds (" + msg + ")");  // slice index panic
+    if (rc == M2S_EEMPTY) throw Panic(rc, "called `Option::unwrap()` on a `None` value (" + msg + ")");  // rtree.rs:117
+    throw Panic(rc, "mesh_to_sdf backend error: " + msg);
+}
+template <class V>
+std::vector<float> pack(const std::vector<V>& v) {
+    std::vector<float> out;
+    out.reserve(v.size() * 3);
+    for (const V& p : v) {
+        out.push_back(point_traits<V>::x(p));
+        out.push_back(point_traits<V>::y(p));
+        out.push_back(point_traits<V>::z(p));
+    }
+    return out;
+}
+}  // namespace detail
+
+// generate_sdf(vertices, indices, query_points, acceleration_method) -> Vec<f32>       (lib.rs:291-311)
+template <class V, class I>
+std::vector<float> generate_sdf(const std::vector<V>& vertices, Topology<I> indices, const std::vector<V>& query_points,
+                                AccelerationMethod method = {}) {
+    const std::vector<uint32_t> tris = indices.get_triangles(vertices.size());
+    if (tris.empty() && method.kind == AccelerationMethod::RtreeBvh) return {};  // rtree_bvh.rs:104-106
+    const std::vector<float> v = detail::pack(vertices), q = detail::pack(query_points);
+    std::vector<float> out(query_points.size());
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    m2s_ctx* c = detail::context();
+    detail::check(c, m2s_generate_sdf(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, q.data(),
+                                      query_points.size(), (int)method.kind, (int)method.sign, out.data()));
+    return out;
+}
+
+// generate_grid_sdf(vertices, indices, grid, sign_method) -> Vec<f32>                   (generate/grid.rs:265-378)
+template <class V, class I>
+std::vector<float> generate_grid_sdf(const std::vector<V>& vertices, Topology<I> indices, const Grid<V>& grid,
+                                     SignMethod sign_method = SignMethod::Raycast) {
+    using T = point_traits<V>;
+    const std::vector<uint32_t> tris = indices.get_triangles(vertices.size());
+    const std::vector<float> v = detail::pack(vertices);
+    const V f = grid.get_first_cell(), s = grid.get_cell_size();
+    const float first[3] = {T::x(f), T::y(f), T::z(f)}, size[3] = {T::x(s), T::y(s), T::z(s)};
+    const auto n = grid.get_cell_count();
+    const uint64_t count[3] = {n[0], n[1], n[2]};
+    std::vector<float> out(grid.get_total_cell_count());
+    m2s_ctx* c = detail::context();
+    detail::check(c, m2s_generate_grid_sdf(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, first, size, count,
+                                           (int)sign_method, out.data()));
+    return out;
+}
+
+}  // namespace mesh_to_sdf

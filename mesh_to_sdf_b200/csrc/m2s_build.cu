@@ -276,7 +276,7 @@ constexpr uint32_t PILL_MAX_TRIS = 2048;
 
 __global__ void __launch_bounds__(256)
 k_pillbox(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nleaf, float4* __restrict__ nodes,
-          const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st) {
+          const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st, float flat_thresh) {
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (slot >= 2u * (uint32_t)(nleaf - 1)) return;
@@ -294,7 +294,9 @@ k_pillbox(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nl
     const uint32_t b = l0 * K, e = min(nt, (l1 + 1) * K);
     const float3 centre = make_float3(0.5f * (c0.x + c1.x), 0.5f * (c0.y + c1.y), 0.5f * (c0.z + c1.z));
     PillAcc P;
+    float kind = CHILD_BOTH;
     if (e - b > PILL_MAX_TRIS) {
+        kind = CHILD_BOX_ONLY;  // the sphere below never beats the box
         P.start(centre, make_float3(0.f, 0.f, 0.f));
         P.h = 0.0f;
         const float dx = c1.x - centre.x, dy = c1.y - centre.y, dz = c1.z - centre.z;
@@ -324,10 +326,19 @@ k_pillbox(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nl
         }
     }
     P.finish(scene_mag(st));
+    if (kind == CHILD_BOTH) {
+        if (P.ux == 0.0f && P.uy == 0.0f && P.uz == 0.0f) {
+            kind = CHILD_BOX_ONLY;
+        } else {
+            // a patch that is flat compared with its box: the pillbox alone prunes as well as both
+            const float he = 0.5f * fminf(fminf(c1.x - c0.x, c1.y - c0.y), c1.z - c0.z);
+            if (P.h <= flat_thresh * he) kind = CHILD_PILL_ONLY;
+        }
+    }
     if (lane == 0) {
         ch[1].w = P.rho;
         ch[2] = make_float4(P.cx, P.cy, P.cz, P.h);
-        ch[3] = make_float4(P.ux, P.uy, P.uz, 0.0f);
+        ch[3] = make_float4(P.ux, P.uy, P.uz, kind);
     }
 }
 
@@ -509,7 +520,8 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
                                                      d.nodes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                      d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
         k_pillbox<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
-            d.rec_sorted.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.nodes.as<float4>(), d.node_range.as<uint2>(), st);
+            d.rec_sorted.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.nodes.as<float4>(), d.node_range.as<uint2>(), st,
+            d.flat_thresh);
         d.launches += 3;
     }
     d.bvh.rec = d.rec_sorted.as<float4>();

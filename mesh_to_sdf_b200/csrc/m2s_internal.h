@@ -20,7 +20,8 @@ namespace m2s {
 //   triangle pillbox, 32 B = 2 x float4 (leaf order): (centroid.xyz, rho) (unit normal.xyz, h)
 //   LBVH internal node, 128 B = 8 x float4: per child 4 x float4, box (padded -/+1e-4, geo.rs:18-21)
 //   plus pillbox (flat cylinder: centre, axis, radius, half height; see m2s_build.cu):
-//       c0 = (min.xyz, bits(child ref))  c1 = (max.xyz, rho)  c2 = (centre.xyz, h)  c3 = (axis.xyz, 0)
+//       c0 = (min.xyz, bits(child ref))  c1 = (max.xyz, rho)  c2 = (centre.xyz, h)  c3 = (axis.xyz, kind)
+//       kind: which of the two bounds a traversal needs to evaluate (CHILD_BOTH / _PILL_ONLY / _BOX_ONLY)
 //       left child at float4 0..3, right child at 4..7
 //   child ref: >= 0 internal node index; < 0 leaf: bit31 set, bit30 = "leaf holds a degenerate
 //   triangle" (slow path with the geo.rs:73-88 guards), bits 0..29 = leaf index. Leaf l owns the
@@ -28,6 +29,7 @@ namespace m2s {
 // ---------------------------------------------------------------------------------------------------
 constexpr int NODE_F4 = 8;   // float4 per node
 constexpr int CHILD_F4 = 4;  // float4 per child slot
+constexpr float CHILD_BOTH = 0.0f, CHILD_PILL_ONLY = 1.0f, CHILD_BOX_ONLY = 2.0f;
 constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr uint32_t LEAF_DEGEN_BIT = 0x40000000u;
 constexpr uint32_t LEAF_INDEX_MASK = 0x3fffffffu;
@@ -108,9 +110,10 @@ struct Device {
     DevBuf stats;             // traversal counters, only with M2S_STATS=1
     bool want_stats = false;
     int stats_mode = 0;
+    float flat_thresh = 0.3f;  // pillbox-only children when h <= flat_thresh * min box half extent (M2S_FLAT)
     bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
     DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
-    int seed_levels = 2;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
+    int seed_levels = 1;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
     BuildStatus* h_status = nullptr;  // pinned
     cudaEvent_t ev[8] = {};
@@ -143,6 +146,6 @@ struct m2s_ctx {
     m2s::Device* dev = nullptr;
     std::string last_error;
     m2s_timings timings{};
-    uint32_t leaf_size = 4;
+    uint32_t leaf_size = 2;
     std::mutex mu;  // a context serves one call at a time
 };

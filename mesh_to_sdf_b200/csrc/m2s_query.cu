@@ -54,8 +54,10 @@ __device__ __forceinline__ float pill_dist2(const f3 p, float cx, float cy, floa
 // lower bound for one child slot (4 x float4): max(box, pillbox)
 __device__ __forceinline__ float child_dist2(const f3 p, const float4 c0, const float4 c1, const float4 c2,
                                              const float4 c3) {
-    const float b = box_dist2(p.x, p.y, p.z, c0.x, c0.y, c0.z, c1.x, c1.y, c1.z);
-    const float q = pill_dist2(p, c2.x, c2.y, c2.z, c3.x, c3.y, c3.z, c1.w, c2.w);
+    // c3.w says which bound is worth evaluating (decided at build time; warp-uniform in the packet kernel)
+    float b = 0.0f, q = 0.0f;
+    if (c3.w != CHILD_PILL_ONLY) b = box_dist2(p.x, p.y, p.z, c0.x, c0.y, c0.z, c1.x, c1.y, c1.z);
+    if (c3.w != CHILD_BOX_ONLY) q = pill_dist2(p, c2.x, c2.y, c2.z, c3.x, c3.y, c3.z, c1.w, c2.w);
     return fmaxf(b, q);
 }
 
@@ -446,18 +448,31 @@ __device__ __forceinline__ float warp_max_bound(const Near<MODE>& s, bool valid)
     return __uint_as_float(__reduce_max_sync(0xffffffffu, b));
 }
 
-template <int MODE, bool RAYSIGN>
+// SEEDPASS: the same walk over the representative voxels of the stride^3 blocks (cdim = block counts),
+// storing the nearest triangle's slot instead of a distance.
+template <int MODE, bool RAYSIGN, bool SEEDPASS>
 __global__ void __launch_bounds__(256)
 k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
                    const uint32_t* __restrict__ px, const uint32_t* __restrict__ py,
-                   const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st) {
+                   const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st,
+                   const uint32_t stride, const uint3 cdim) {
     __shared__ uint2 s_stack[8][PKT_STACK];
     const unsigned full = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5;
     uint32_t xr, y, z;
-    brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
+    uint32_t bxs = 0, bys = 0, bzs = 0;
+    bool valid;
+    if (SEEDPASS) {
+        brick_coords((cdim.y + BY - 1) / BY, (cdim.z + BZ - 1) / BZ, &bxs, &bys, &bzs);
+        valid = bxs < cdim.x && bys < cdim.y && bzs < cdim.z;
+        xr = min(bxs * stride + stride / 2, g.x1 - g.x0 - 1);
+        y = min(bys * stride + stride / 2, g.ny - 1);
+        z = min(bzs * stride + stride / 2, g.nz - 1);
+    } else {
+        brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
+        valid = g.x0 + xr < g.x1 && y < g.ny && z < g.nz;
+    }
     const uint32_t x = g.x0 + xr;
-    const bool valid = x < g.x1 && y < g.ny && z < g.nz;
     if (!__any_sync(full, valid)) return;  // warp-uniform
 
     const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
@@ -535,8 +550,9 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
                 const float4 q0 = ldg4(bvh.pill + 2 * (size_t)j), q1 = ldg4(bvh.pill + 2 * (size_t)j + 1);
                 const bool want = valid && pill_dist2(p, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q0.w, q1.w) <= s.bound2;
                 if (want) tribuf[ntri++] = j | dg;
-                // a full queue anywhere forces a flush before the next triangle
-                if (__any_sync(full, ntri == PKT_TRI_BATCH)) flush();
+                // a full queue anywhere forces a flush before the next triangle (only leaves with
+                // more triangles than the queue has room for after the per-leaf flush can get here)
+                if (bvh.leaf_size > PKT_TRI_BATCH - PKT_FLUSH_AT && __any_sync(full, ntri == PKT_TRI_BATCH)) flush();
             }
             if (__any_sync(full, ntri >= PKT_FLUSH_AT)) flush();
             cur = pop();
@@ -544,7 +560,9 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
     }
     flush();
 
-    if (valid) {
+    if (SEEDPASS) {
+        if (valid) reinterpret_cast<uint32_t*>(out)[((size_t)bxs * cdim.y + bys) * cdim.z + bzs] = s.slot;
+    } else if (valid) {
         float d = finish<MODE>(bvh, p, s);
         if (RAYSIGN) {
             // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd.
@@ -867,7 +885,11 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
             DevBuf& buf = d.seeds[lev - 1];
             CK(buf.ensure((size_t)cx * cy * cz * 4));
             const unsigned nb = cdiv(cx, BX) * cdiv(cy, BY) * cdiv(cz, BZ);
-            k_grid_seed<<<nb, 256, 0, s>>>(d.bvh, g, mag, stride, cx, cy, cz, L, buf.as<uint32_t>(), st);
+            if (d.packet)
+                k_grid_nearest_pkt<MODE_UNSIGNED, false, true><<<nb, 256, 0, s>>>(
+                    d.bvh, g, mag, L, nullptr, nullptr, nullptr, buf.as<float>(), st, stride, make_uint3(cx, cy, cz));
+            else
+                k_grid_seed<<<nb, 256, 0, s>>>(d.bvh, g, mag, stride, cx, cy, cz, L, buf.as<uint32_t>(), st);
             d.launches++;
             L = SeedLevel{buf.as<uint32_t>(), cx, cy, cz, stride};
         }
@@ -876,14 +898,14 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
     const unsigned nb = (unsigned)nblocks;
     if (d.packet) {
         if (rb) {
-            k_grid_nearest_pkt<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, rb->bits[0], rb->bits[1],
-                                                                       rb->bits[2], d_out, st);
+            k_grid_nearest_pkt<MODE_UNSIGNED, true, false><<<nb, 256, 0, s>>>(
+                d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2], d_out, st, 1u, make_uint3(0, 0, 0));
         } else if (mode == MODE_NORMAL) {
-            k_grid_nearest_pkt<MODE_NORMAL, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, nullptr, nullptr, nullptr,
-                                                                      d_out, st);
+            k_grid_nearest_pkt<MODE_NORMAL, false, false><<<nb, 256, 0, s>>>(
+                d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st, 1u, make_uint3(0, 0, 0));
         } else {
-            k_grid_nearest_pkt<MODE_UNSIGNED, false><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, nullptr, nullptr, nullptr,
-                                                                        d_out, st);
+            k_grid_nearest_pkt<MODE_UNSIGNED, false, false><<<nb, 256, 0, s>>>(
+                d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st, 1u, make_uint3(0, 0, 0));
         }
         d.launches++;
         return cudaGetLastError();

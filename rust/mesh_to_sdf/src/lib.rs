@@ -1,0 +1,156 @@
+//! mesh_to_sdf — the public surface of Azkellas/mesh_to_sdf 0.4.0 (`generate_sdf`, `generate_grid_sdf`, `Grid`,
+//! `SnapResult`, `Topology`, `SignMethod`, `AccelerationMethod`, `Point`) as a thin facade over `libm2s.so`, the
+//! B200-native CUDA implementation of the hot path. There is no CPU fallback: without a CUDA device the first call
+//! panics. Signatures stay infallible like the reference's; every non-OK status becomes a panic.
+mod ffi;
+mod grid;
+mod point;
+
+pub use grid::{Grid, SnapResult};
+pub use point::Point;
+
+use std::sync::{Mutex, OnceLock};
+
+/// How indices are stored. `None` means `0..vertices.len()`.
+#[derive(Copy, Clone)]
+pub enum Topology<'a, I: Into<u32>> {
+    TriangleList(Option<&'a [I]>),
+    TriangleStrip(Option<&'a [I]>),
+}
+
+#[derive(Debug, Copy, Clone, Default, PartialEq, Eq)]
+pub enum SignMethod {
+    #[default]
+    Raycast,
+    Normal,
+}
+
+#[derive(Debug, Copy, Clone, Default, PartialEq, Eq)]
+pub enum AccelerationMethod {
+    None(SignMethod),
+    Bvh(SignMethod),
+    Rtree,
+    #[default]
+    RtreeBvh,
+}
+
+struct Ctx(*mut ffi::m2s_ctx);
+unsafe impl Send for Ctx {}
+
+fn ctx() -> &'static Mutex<Ctx> {
+    static CTX: OnceLock<Mutex<Ctx>> = OnceLock::new();
+    CTX.get_or_init(|| {
+        // M2S_DEVICES="0,1,..." shards grids by x-slabs and queries by ranges over several GPUs of one box.
+        let devices: Vec<i32> = std::env::var("M2S_DEVICES")
+            .map(|s| s.split(',').filter_map(|t| t.trim().parse().ok()).collect())
+            .unwrap_or_default();
+        let mut raw = core::ptr::null_mut();
+        let rc = unsafe { ffi::m2s_create(if devices.is_empty() { core::ptr::null() } else { devices.as_ptr() }, devices.len() as i32, &mut raw) };
+        assert!(rc == ffi::M2S_OK, "mesh_to_sdf: no usable CUDA device (libm2s status {rc}); there is no CPU fallback");
+        Mutex::new(Ctx(raw))
+    })
+}
+
+fn check(c: &Ctx, rc: i32) {
+    if rc != ffi::M2S_OK {
+        let msg = unsafe { std::ffi::CStr::from_ptr(ffi::m2s_last_error(c.0)) }.to_string_lossy().into_owned();
+        match rc {
+            ffi::M2S_ENAN => panic!("NaN distance ({msg})"),
+            ffi::M2S_EINDEX => panic!("index out of bounds ({msg})"),
+            ffi::M2S_EEMPTY => panic!("called `Option::unwrap()` on a `None` value (empty mesh: {msg})"),
+            _ => panic!("mesh_to_sdf backend error {rc}: {msg}"),
+        }
+    }
+}
+
+fn pack<V: Point>(v: &[V]) -> Vec<f32> {
+    let mut out = Vec::with_capacity(v.len() * 3);
+    for p in v {
+        out.extend_from_slice(&[p.x(), p.y(), p.z()]);
+    }
+    out
+}
+
+fn triangles<I: Copy + Into<u32>>(nv: usize, topology: Topology<'_, I>) -> Vec<u32> {
+    let (kind, idx): (i32, Option<Vec<u32>>) = match topology {
+        Topology::TriangleList(i) => (0, i.map(|s| s.iter().map(|x| (*x).into()).collect())),
+        Topology::TriangleStrip(i) => (1, i.map(|s| s.iter().map(|x| (*x).into()).collect())),
+    };
+    let (ptr, n) = idx.as_ref().map_or((core::ptr::null(), 0), |v| (v.as_ptr().cast(), v.len() as u64));
+    let count = unsafe { ffi::m2s_expand_topology(kind, ptr, 4, n, nv as u64, core::ptr::null_mut()) } as usize;
+    let mut out = vec![0u32; count * 3];
+    unsafe { ffi::m2s_expand_topology(kind, ptr, 4, n, nv as u64, out.as_mut_ptr()) };
+    out
+}
+
+/// Signed distance from every query point to the mesh, in query order.
+pub fn generate_sdf<V, I>(vertices: &[V], indices: Topology<I>, query_points: &[V], acceleration_method: AccelerationMethod) -> Vec<f32>
+where
+    V: Point + 'static,
+    I: Copy + Into<u32> + Sync + Send,
+{
+    let tris = triangles(vertices.len(), indices);
+    if tris.is_empty() && acceleration_method == AccelerationMethod::RtreeBvh {
+        return vec![]; // what the reference returns for an empty mesh on this path
+    }
+    let (accel, sign) = match acceleration_method {
+        AccelerationMethod::None(s) => (0, s as i32),
+        AccelerationMethod::Bvh(s) => (1, s as i32),
+        AccelerationMethod::Rtree => (2, 0),
+        AccelerationMethod::RtreeBvh => (3, 0),
+    };
+    let (v, q) = (pack(vertices), pack(query_points));
+    let mut out = vec![0f32; query_points.len()];
+    let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+    let rc = unsafe {
+        ffi::m2s_generate_sdf(c.0, v.as_ptr(), vertices.len() as u64, tris.as_ptr(), (tris.len() / 3) as u64, q.as_ptr(),
+                              query_points.len() as u64, accel, sign, out.as_mut_ptr())
+    };
+    check(&c, rc);
+    out
+}
+
+/// Signed distance at every cell centre of `grid`, flat in `Grid::get_cell_idx` order.
+pub fn generate_grid_sdf<V, I>(vertices: &[V], indices: Topology<I>, grid: &Grid<V>, sign_method: SignMethod) -> Vec<f32>
+where
+    V: Point + 'static,
+    I: Copy + Into<u32> + Sync + Send,
+{
+    let tris = triangles(vertices.len(), indices);
+    let v = pack(vertices);
+    let (f, s, n) = (grid.get_first_cell(), grid.get_cell_size(), grid.get_cell_count());
+    let (first, size) = ([f.x(), f.y(), f.z()], [s.x(), s.y(), s.z()]);
+    let count = [n[0] as u64, n[1] as u64, n[2] as u64];
+    let mut out = vec![0f32; grid.get_total_cell_count()];
+    let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+    let rc = unsafe {
+        ffi::m2s_generate_grid_sdf(c.0, v.as_ptr(), vertices.len() as u64, tris.as_ptr(), (tris.len() / 3) as u64,
+                                   first.as_ptr(), size.as_ptr(), count.as_ptr(), sign_method as i32, out.as_mut_ptr())
+    };
+    check(&c, rc);
+    out
+}
+
+#[cfg(test)]
+mod tests {
+    use super::*;
+
+    // the reference's doc-tests, unchanged in meaning
+    #[test]
+    fn doc_generate_sdf() {
+        let vertices: Vec<[f32; 3]> = vec![[0.5, 1.5, 0.5], [1., 2., 3.], [1., 3., 7.]];
+        let indices: Vec<u32> = vec![0, 1, 2];
+        let sdf = generate_sdf(&vertices, Topology::TriangleList(Some(&indices)), &[[0.5, 0.5, 0.5]], AccelerationMethod::RtreeBvh);
+        assert_eq!(sdf, vec![1.0]);
+    }
+
+    #[test]
+    fn doc_generate_grid_sdf() {
+        let vertices: Vec<[f32; 3]> = vec![[0.5, 1.5, 0.5], [1., 2., 3.], [1., 3., 7.]];
+        let indices: Vec<u32> = vec![0, 1, 2];
+        let grid = Grid::from_bounding_box(&[0., 0., 0.], &[10., 10., 10.], [10, 10, 10]);
+        let sdf = generate_grid_sdf(&vertices, Topology::TriangleList(Some(&indices)), &grid, SignMethod::Raycast);
+        assert_eq!(sdf.len(), 1000);
+        assert_eq!(sdf[0], 1.0);
+    }
+}

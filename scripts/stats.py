@@ -11,7 +11,7 @@ def stats(ctx):
     L.m2s_debug_stats(ctx._h, a)
     return [int(x) for x in a]
 import itertools
-for dyn, lev, leaf in itertools.product((0, 1), (1, 2), (4, 8)):
+for dyn, lev, leaf in itertools.product((1,), (0, 1), (2, 4)):
     os.environ["M2S_SEED_LEVELS"] = str(lev); os.environ["M2S_LEAF_SIZE"] = str(leaf); os.environ["M2S_PACKET"] = str(dyn)
     with m2s.Context() as ctx:
         for name, nu, nv, n, sign in (("C2", 64, 40, 128, 1), ("C3", 256, 196, 256, 0)):

@@ -142,7 +142,7 @@ def run_reference(args):
     import oracle
 
     oracle.build()
-    verts, tris, grid, sign, n = make_workload(args.workload, 1, "weak")
+    verts, tris, grid, sign, n = make_workload(args.workload, max(1, args.gpus), "weak")
     cores = oracle.hardware_threads()
     planes = args.ref_planes
     for _ in range(args.warmup):
@@ -159,7 +159,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, verts, tris, grid, sign, 1, "weak"),
+        "config": workload_config(args.workload, verts, tris, grid, sign, max(1, args.gpus), "weak"),
         "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -44,7 +44,7 @@ struct GridArgs {
 m2s_status check_mesh(m2s_ctx* ctx, const void* verts, uint64_t nv, const void* tris, uint64_t nt) {
     if (nt > 0 && (!tris || !verts)) return fail(ctx, M2S_EINVAL, "null vertex / index pointer");
     if (nt > 0 && nv == 0) return fail(ctx, M2S_EINDEX, "triangles reference an empty vertex array");
-    if (nt >= (1ull << 30)) return fail(ctx, M2S_EINVAL, "more than 2^30 triangles");
+    if (nt >= (1ull << 29)) return fail(ctx, M2S_EINVAL, "more than 2^29 triangles");
     if (nv > 0xffffffffull) return fail(ctx, M2S_EINVAL, "more than 2^32 vertices");
     return M2S_OK;
 }
@@ -63,15 +63,17 @@ m2s_status check_grid(m2s_ctx* ctx, const float first[3], const float size[3], c
     out->g.fx = first[0]; out->g.fy = first[1]; out->g.fz = first[2];
     out->g.sx = size[0]; out->g.sy = size[1]; out->g.sz = size[2];
     out->g.nx = (uint32_t)count[0]; out->g.ny = (uint32_t)count[1]; out->g.nz = (uint32_t)count[2];
-    out->g.x0 = 0;
-    out->g.x1 = out->g.nx;
+    out->g.x0 = out->g.xa = 0;
+    out->g.x1 = out->g.xb = out->g.nx;
     return M2S_OK;
 }
 
 // Enqueue: records + LBVH + (row parities) + nearest kernel for one slab, all on d.stream.
+// host_out != nullptr: the slab is computed in x-chunks and every finished chunk is copied to
+// host_out on the device's copy stream while the next chunk's kernel runs.
 cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris,
                          uint64_t nt, const GridParams& g, int sign, float* d_out, bool clear_errors,
-                         bool timed) {
+                         bool timed, float* host_out = nullptr) {
     cudaError_t e;
     if ((e = launch_status_reset(d, clear_errors)) != cudaSuccess) return e;
     const uint64_t slab_cells = (uint64_t)(g.x1 - g.x0) * g.ny * g.nz;
@@ -88,10 +90,51 @@ cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t
     const bool raycast = sign == M2S_SIGN_RAYCAST;
     if (raycast && (e = launch_grid_rows(d, g, &rb)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev[3], d.stream);
-    e = launch_grid_nearest(d, g, raycast ? MODE_UNSIGNED : MODE_NORMAL, raycast ? &rb : nullptr, d_out,
-                            timed ? d.ev[6] : nullptr);
+    const int mode = raycast ? MODE_UNSIGNED : MODE_NORMAL;
+    const uint32_t span = g.x1 - g.x0;
+    const uint64_t plane = (uint64_t)g.ny * g.nz;
+    int chunks = host_out ? d.host_chunks : 1;
+    if (slab_cells < (4u << 20) || span < 32u * (uint32_t)chunks) chunks = 1;  // small slabs: one kernel, one copy
+    if (chunks > 8) chunks = 8;
+    if (chunks == 1) {
+        e = launch_grid_nearest(d, g, mode, raycast ? &rb : nullptr, d_out, timed ? d.ev[6] : nullptr);
+        if (timed) cudaEventRecord(d.ev[4], d.stream);
+        return e;
+    }
+    // one seeding pass for the slab, then the distance kernel chunk by chunk. Every chunk's kernel is
+    // enqueued before the copies: a D2H into pageable memory blocks the calling thread, which must not
+    // delay the launch of the following chunks.
+    SeedLevel L{};
+    if ((e = launch_grid_seeds(d, g, &L)) != cudaSuccess) return e;
+    if (timed) cudaEventRecord(d.ev[6], d.stream);
+    uint32_t cx0[8], cx1[8];
+    for (int c = 0; c < chunks; ++c) {
+        GridParams gc = g;
+        gc.xa = cx0[c] = g.x0 + (uint32_t)((uint64_t)span * c / chunks) / 4u * 4u;
+        gc.xb = cx1[c] = c + 1 == chunks ? g.x1 : g.x0 + (uint32_t)((uint64_t)span * (c + 1) / chunks) / 4u * 4u;
+        if (gc.xb > gc.xa && (e = launch_grid_final(d, gc, L, mode, raycast ? &rb : nullptr, d_out)) != cudaSuccess)
+            return e;
+        if ((e = cudaEventRecord(d.ev_chunk[c], d.stream)) != cudaSuccess) return e;
+    }
+    for (int c = 0; c < chunks; ++c) {
+        if (cx1[c] <= cx0[c]) continue;
+        if ((e = cudaStreamWaitEvent(d.copy_stream, d.ev_chunk[c], 0)) != cudaSuccess) return e;
+        const uint64_t off = (uint64_t)(cx0[c] - g.x0) * plane;
+        if ((e = cudaMemcpyAsync(host_out + off, d_out + off, (uint64_t)(cx1[c] - cx0[c]) * plane * 4,
+                                 cudaMemcpyDeviceToHost, d.copy_stream)) != cudaSuccess)
+            return e;
+    }
     if (timed) cudaEventRecord(d.ev[4], d.stream);
-    return e;
+    // the caller's stream continues only after the last chunk has landed
+    if ((e = cudaEventRecord(d.ev_copied, d.copy_stream)) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(d.stream, d.ev_copied, 0);
+}
+
+// true when enqueue_grid(host_out) already copied the slab to the host
+static bool grid_copied_by_chunks(const Device& d, const GridParams& g, uint64_t nt) {
+    const uint64_t slab_cells = (uint64_t)(g.x1 - g.x0) * g.ny * g.nz;
+    int chunks = d.host_chunks > 8 ? 8 : d.host_chunks;
+    return nt > 0 && chunks > 1 && slab_cells >= (4u << 20) && (g.x1 - g.x0) >= 32u * (uint32_t)chunks;
 }
 
 struct PointPlan {
@@ -197,6 +240,10 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.ordinal);
         if (e == cudaSuccess) e = cudaMallocHost((void**)&d.h_status, sizeof(BuildStatus));
         for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreate(&d.ev[k]);
+        for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&d.ev_chunk[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_copied, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
+        if (const char* c = std::getenv("M2S_HOST_CHUNKS")) d.host_chunks = std::max(1, std::min(8, std::atoi(c)));
         if (e != cudaSuccess) {
             cudaGetLastError();
             m2s_destroy(ctx);
@@ -204,7 +251,7 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         }
         std::memset(d.h_status, 0, sizeof(BuildStatus));
         if (const char* e = std::getenv("M2S_PACKET")) d.packet = std::atoi(e) != 0;
-        if (const char* e = std::getenv("M2S_FLAT")) d.flat_thresh = (float)std::atof(e);
+        if (const char* e = std::getenv("M2S_OBB_BIAS")) d.obb_bias = (float)std::atof(e);
         if (const char* e = std::getenv("M2S_STATS")) { d.want_stats = std::atoi(e) != 0; d.stats_mode = std::atoi(e); }
         if (const char* e = std::getenv("M2S_SEED_LEVELS")) d.seed_levels = std::max(0, std::min(2, std::atoi(e)));
     }
@@ -237,11 +284,15 @@ void m2s_destroy(m2s_ctx* ctx) {
                           &d.keys_out, &d.vals_in, &d.vals_out, &d.cub_tmp, &d.tri_id_sorted, &d.nodes,
                           &d.leaf_parent, &d.node_parent, &d.node_flag, &d.status, &d.rows[0], &d.rows[1],
                           &d.rows[2], &d.big_list, &d.big_count, &d.queries, &d.q_sorted, &d.q_perm,
-                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.pill};
+                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.tobb, &d.boxes};
         for (DevBuf* b : bufs) b->release();
         if (d.h_status) cudaFreeHost(d.h_status);
         for (int k = 0; k < 8; ++k)
             if (d.ev[k]) cudaEventDestroy(d.ev[k]);
+        for (int k = 0; k < 8; ++k)
+            if (d.ev_chunk[k]) cudaEventDestroy(d.ev_chunk[k]);
+        if (d.ev_copied) cudaEventDestroy(d.ev_copied);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
     }
     cudaGetLastError();
@@ -291,8 +342,8 @@ static m2s_status grid_host(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, c
     for (int i = 0; i < nd; ++i) {
         Device& d = ctx->dev[i];
         GridParams g = ga.g;
-        g.x0 = (uint32_t)(xa + span * i / nd);
-        g.x1 = (uint32_t)(xa + span * (i + 1) / nd);
+        g.x0 = g.xa = (uint32_t)(xa + span * i / nd);
+        g.x1 = g.xb = (uint32_t)(xa + span * (i + 1) / nd);
         const uint64_t cells = (uint64_t)(g.x1 - g.x0) * plane;
         CU(ctx, cudaSetDevice(d.ordinal));
         const bool timed = i == 0;
@@ -305,10 +356,11 @@ static m2s_status grid_host(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, c
         }
         CU(ctx, d.out.ensure(cells * 4));
         if (timed) cudaEventRecord(d.ev[1], d.stream);
+        float* host_dst = out + (uint64_t)(g.x0 - xa) * plane;
         CU(ctx, enqueue_grid(ctx, d, d.verts.as<float>(), nv, d.tris.as<uint32_t>(), nt, g, sign_method,
-                             d.out.as<float>(), true, timed));
-        CU(ctx, cudaMemcpyAsync(out + (uint64_t)(g.x0 - xa) * plane, d.out.p, cells * 4, cudaMemcpyDeviceToHost,
-                                d.stream));
+                             d.out.as<float>(), true, timed, host_dst));
+        if (!grid_copied_by_chunks(d, g, nt))
+            CU(ctx, cudaMemcpyAsync(host_dst, d.out.p, cells * 4, cudaMemcpyDeviceToHost, d.stream));
         CU(ctx, cudaMemcpyAsync(d.h_status, d.status.p, sizeof(BuildStatus), cudaMemcpyDeviceToHost, d.stream));
         if (timed) cudaEventRecord(d.ev[5], d.stream);
     }
@@ -426,8 +478,8 @@ m2s_status m2s_generate_grid_sdf_device(m2s_ctx* ctx, const float* d_verts_xyz, 
     Device& d = ctx->dev[0];
     CU(ctx, cudaSetDevice(d.ordinal));
     GridParams g = ga.g;
-    g.x0 = (uint32_t)x_begin;
-    g.x1 = (uint32_t)x_end;
+    g.x0 = g.xa = (uint32_t)x_begin;
+    g.x1 = g.xb = (uint32_t)x_end;
     cudaEventRecord(d.ev[0], d.stream);
     cudaEventRecord(d.ev[1], d.stream);
     CU(ctx, enqueue_grid(ctx, d, d_verts_xyz, nv, d_tri_idx, nt, g, sign_method, d_out_slab, false, true));

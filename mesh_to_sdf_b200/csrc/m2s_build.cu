@@ -207,48 +207,96 @@ k_point_gather(const float* __restrict__ q, const uint32_t* __restrict__ perm, u
     q_sorted[i] = make_float4(q[3 * s], q[3 * s + 1], q[3 * s + 2], __uint_as_float(s));
 }
 
-// K4a: permute the records into leaf (sorted) order.
-// Pillbox (flat cylinder) around a vertex set: centre c, unit axis u, radius rho, half-height h such
-// that every point x of the convex hull has |dot(x-c,u)| <= h and |x - c - dot(x-c,u)u| <= rho. The
-// distance from a query p to anything inside is then >= hypot(max(0,|a|-h), max(0,l-rho)) with a, l
-// the axial / lateral offsets of p. For a (nearly) flat patch seen from far away this bound is tight
-// to first order where an axis-aligned box of a tilted patch is loose by about a third of its size,
-// which is what makes far-field searches cheap. u = 0 degrades gracefully to a bounding sphere.
-struct PillAcc {
-    float cx, cy, cz, ux, uy, uz, h, rho;
-    __device__ __forceinline__ void start(float3 c, float3 nsum) {
-        cx = c.x; cy = c.y; cz = c.z;
-        const float len2 = nsum.x * nsum.x + nsum.y * nsum.y + nsum.z * nsum.z;
-        if (len2 > 1e-30f && isfinite(len2)) {
-            const float inv = rsqrtf(len2);
-            ux = nsum.x * inv; uy = nsum.y * inv; uz = nsum.z * inv;
-        } else {
-            ux = uy = uz = 0.0f;
-        }
-        h = 0.0f;
-        rho = 0.0f;
+// ---------------------------------------------------------------------------------------------------
+// Oriented bounds. With axis-aligned boxes alone a far-field query visits hundreds of nodes: the box of
+// a tilted, nearly flat patch is loose by about a third of its size TOWARDS the query (first order)
+// while the distance to neighbouring patches only grows like x^2 / 2D. An oriented box whose first
+// axis is the patch's mean normal is tight to within the patch's sag in that direction, and fits an
+// elongated patch laterally (a disc / cylinder does not: measured 99 -> see DESIGN.md). The distance
+// from p to anything inside {c + a u + b v + g w : |a|<=eu, |b|<=ev, |g|<=ew} is at least
+// hypot(max(0,|(p-c).u|-eu), max(0,|(p-c).v|-ev), max(0,|(p-c).w|-ew)) for orthonormal (u, v, w).
+// ---------------------------------------------------------------------------------------------------
+struct Frame {
+    float3 u, v, w;
+};
+
+__device__ __forceinline__ float3 f3sub(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float f3dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 f3cross(float3 a, float3 b) {
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ bool f3normalize(float3& a) {
+    const float l2 = f3dot(a, a);
+    if (!(l2 > 1e-30f) || !isfinite(l2)) return false;
+    const float inv = rsqrtf(l2);
+    a = make_float3(a.x * inv, a.y * inv, a.z * inv);
+    return true;
+}
+
+// Orthonormal frame whose first axis is n (normalised here); false if n is degenerate.
+__device__ __forceinline__ bool frame_from_normal(float3 n, Frame* F) {
+    if (!f3normalize(n)) return false;
+    const float ax = fabsf(n.x), ay = fabsf(n.y), az = fabsf(n.z);
+    const float3 e = ax <= ay && ax <= az ? make_float3(1.f, 0.f, 0.f)
+                                          : (ay <= az ? make_float3(0.f, 1.f, 0.f) : make_float3(0.f, 0.f, 1.f));
+    float3 t1 = f3cross(n, e);
+    if (!f3normalize(t1)) return false;
+    float3 t2 = f3cross(n, t1);
+    f3normalize(t2);
+    F->u = n; F->v = t1; F->w = t2;
+    return true;
+}
+
+// Rotate (v, w) about u to the principal axes of the 2-D covariance (saa, sab, sbb already centred).
+__device__ __forceinline__ void frame_align(Frame* F, float caa, float cab, float cbb) {
+    const float theta = 0.5f * atan2f(2.0f * cab, caa - cbb);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    float3 v = make_float3(cs * F->v.x + sn * F->w.x, cs * F->v.y + sn * F->w.y, cs * F->v.z + sn * F->w.z);
+    f3normalize(v);
+    float3 w = f3cross(F->u, v);
+    f3normalize(w);
+    F->v = f3cross(w, F->u);  // re-orthogonalise
+    f3normalize(F->v);
+    F->w = w;
+}
+
+struct Extent {
+    float lo[3], hi[3];
+    __device__ __forceinline__ void reset() {
+        for (int i = 0; i < 3; ++i) { lo[i] = INFINITY; hi[i] = -INFINITY; }
     }
-    __device__ __forceinline__ void add(float x, float y, float z) {
-        const float dx = x - cx, dy = y - cy, dz = z - cz;
-        const float a = dx * ux + dy * uy + dz * uz;
-        const float lx = dx - a * ux, ly = dy - a * uy, lz = dz - a * uz;
-        h = fmaxf(h, fabsf(a));
-        rho = fmaxf(rho, sqrtf(lx * lx + ly * ly + lz * lz));
-    }
-    // inflate for the rounding of this computation and of the query-side evaluation
-    __device__ __forceinline__ void finish(float mag) {
-        const float slack = 4.0e-6f * mag;
-        h = h * 1.0001f + slack;
-        rho = rho * 1.0001f + slack;
+    __device__ __forceinline__ void add(const Frame& F, float3 d) {
+        const float a = f3dot(d, F.u), b = f3dot(d, F.v), g = f3dot(d, F.w);
+        lo[0] = fminf(lo[0], a); hi[0] = fmaxf(hi[0], a);
+        lo[1] = fminf(lo[1], b); hi[1] = fmaxf(hi[1], b);
+        lo[2] = fminf(lo[2], g); hi[2] = fmaxf(hi[2], g);
     }
 };
 
-// K4a: permute the records into leaf (sorted) order; per-triangle pillbox = the triangle's plane
-// disc (centroid, unit normal, circumscribing radius).
+// Writes the 4 x float4 oriented-box record: (centre.xyz, w0) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew).
+// Extents are inflated for the rounding of this computation and of the query-side evaluation.
+__device__ __forceinline__ void write_obb(float4* out, float3 origin, const Frame& F, const Extent& E, float mag,
+                                          float w0) {
+    const float ma = 0.5f * (E.lo[0] + E.hi[0]), mb = 0.5f * (E.lo[1] + E.hi[1]), mg = 0.5f * (E.lo[2] + E.hi[2]);
+    const float3 c = make_float3(origin.x + ma * F.u.x + mb * F.v.x + mg * F.w.x,
+                                 origin.y + ma * F.u.y + mb * F.v.y + mg * F.w.y,
+                                 origin.z + ma * F.u.z + mb * F.v.z + mg * F.w.z);
+    const float slack = 6.0e-6f * mag;
+    const float eu = 0.5f * (E.hi[0] - E.lo[0]) * 1.0001f + slack;
+    const float ev = 0.5f * (E.hi[1] - E.lo[1]) * 1.0001f + slack;
+    const float ew = 0.5f * (E.hi[2] - E.lo[2]) * 1.0001f + slack;
+    out[0] = make_float4(c.x, c.y, c.z, w0);
+    out[1] = make_float4(F.u.x, F.u.y, F.u.z, eu);
+    out[2] = make_float4(F.v.x, F.v.y, F.v.z, ev);
+    out[3] = make_float4(F.w.x, F.w.y, F.w.z, ew);
+}
+
+// K4a: permute the records into leaf (sorted) order; per-triangle oriented box (normal, longest edge).
 __global__ void __launch_bounds__(256)
 k_tri_permute(const float4* __restrict__ rec, const float4* __restrict__ tri_lo,
               const uint32_t* __restrict__ order, uint32_t nt, const BuildStatus* __restrict__ st,
-              float4* __restrict__ rec_sorted, float4* __restrict__ pill, uint32_t* __restrict__ tri_id_sorted) {
+              float4* __restrict__ rec_sorted, float4* __restrict__ tobb, uint32_t* __restrict__ tri_id_sorted) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nt) return;
     const uint32_t t = order[j];
@@ -257,31 +305,50 @@ k_tri_permute(const float4* __restrict__ rec, const float4* __restrict__ tri_lo,
     rec_sorted[3 * j + 1] = r1;
     rec_sorted[3 * j + 2] = r2;
     tri_id_sorted[j] = t | (tri_lo[t].w != 0.0f ? TRI_DEGEN_BIT : 0u);
-    PillAcc P;
-    const float third = 1.0f / 3.0f;
-    P.start(make_float3((r0.x + r0.w + r1.z) * third, (r0.y + r1.x + r1.w) * third, (r0.z + r1.y + r2.x) * third),
-            make_float3(r2.y, r2.z, r2.w));
-    P.add(r0.x, r0.y, r0.z);
-    P.add(r0.w, r1.x, r1.y);
-    P.add(r1.z, r1.w, r2.x);
-    P.finish(scene_mag(st));
-    pill[2 * j + 0] = make_float4(P.cx, P.cy, P.cz, P.rho);
-    pill[2 * j + 1] = make_float4(P.ux, P.uy, P.uz, P.h);
+    const float3 a = make_float3(r0.x, r0.y, r0.z), b = make_float3(r0.w, r1.x, r1.y), c = make_float3(r1.z, r1.w, r2.x);
+    const float mag = scene_mag(st);
+    Frame F;
+    Extent E;
+    E.reset();
+    const float3 ab = f3sub(b, a), bc = f3sub(c, b), ca = f3sub(a, c);
+    bool ok = frame_from_normal(make_float3(r2.y, r2.z, r2.w), &F);
+    if (ok) {
+        // second axis along the longest edge
+        const float lab = f3dot(ab, ab), lbc = f3dot(bc, bc), lca = f3dot(ca, ca);
+        float3 e = lab >= lbc && lab >= lca ? ab : (lbc >= lca ? bc : ca);
+        // project on the plane, normalise, rebuild w
+        const float k = f3dot(e, F.u);
+        e = make_float3(e.x - k * F.u.x, e.y - k * F.u.y, e.z - k * F.u.z);
+        if (f3normalize(e)) {
+            F.v = e;
+            F.w = f3cross(F.u, F.v);
+            f3normalize(F.w);
+        }
+    } else {
+        // degenerate triangle: axis-aligned frame (still a valid box around the three points)
+        F.u = make_float3(1.f, 0.f, 0.f); F.v = make_float3(0.f, 1.f, 0.f); F.w = make_float3(0.f, 0.f, 1.f);
+    }
+    E.add(F, make_float3(0.f, 0.f, 0.f));
+    E.add(F, ab);
+    E.add(F, f3sub(c, a));
+    write_obb(tobb + 4 * (size_t)j, a, F, E, mag, 0.0f);
 }
 
-// K4d: pillbox of every child slot of every internal node: one warp per slot strides over the
-// slot's (contiguous, leaf-order) triangles twice — normal sum, then extents. Slots covering more
-// than PILL_MAX_TRIS triangles keep a bounding sphere (u = 0): large curved regions do not profit.
-constexpr uint32_t PILL_MAX_TRIS = 2048;
+// K4d: search node of every internal node: per child either the padded box (for big / strongly curved
+// subtrees) or an oriented box fitted to the child's contiguous leaf-order triangle range. One warp
+// per child slot, three strided passes: normal sum -> lateral covariance -> extents.
+constexpr uint32_t OBB_MAX_TRIS = 4096;
 
 __global__ void __launch_bounds__(256)
-k_pillbox(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nleaf, float4* __restrict__ nodes,
-          const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st, float flat_thresh) {
+k_search_nodes(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nleaf,
+               const float4* __restrict__ boxes, float4* __restrict__ nodes, const uint2* __restrict__ node_range,
+               const BuildStatus* __restrict__ st, float obb_bias) {
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (slot >= 2u * (uint32_t)(nleaf - 1)) return;
+    const float4* bx = boxes + BOX_F4 * (size_t)(slot >> 1) + 2 * (slot & 1u);
     float4* ch = nodes + NODE_F4 * (size_t)(slot >> 1) + CHILD_F4 * (slot & 1u);
-    const float4 c0 = ch[0], c1 = ch[1];
+    const float4 c0 = bx[0], c1 = bx[1];
     const uint32_t ref = __float_as_uint(c0.w);
     uint32_t l0, l1;
     if (ref & LEAF_BIT) {
@@ -292,53 +359,74 @@ k_pillbox(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nl
         l1 = r.y;
     }
     const uint32_t b = l0 * K, e = min(nt, (l1 + 1) * K);
-    const float3 centre = make_float3(0.5f * (c0.x + c1.x), 0.5f * (c0.y + c1.y), 0.5f * (c0.z + c1.z));
-    PillAcc P;
-    float kind = CHILD_BOTH;
-    if (e - b > PILL_MAX_TRIS) {
-        kind = CHILD_BOX_ONLY;  // the sphere below never beats the box
-        P.start(centre, make_float3(0.f, 0.f, 0.f));
-        P.h = 0.0f;
-        const float dx = c1.x - centre.x, dy = c1.y - centre.y, dz = c1.z - centre.z;
-        P.rho = sqrtf(dx * dx + dy * dy + dz * dz);
-    } else {
+    const float3 origin = make_float3(0.5f * (c0.x + c1.x), 0.5f * (c0.y + c1.y), 0.5f * (c0.z + c1.z));
+    const unsigned full = 0xffffffffu;
+    bool use_obb = (e - b) <= OBB_MAX_TRIS;
+    Frame F;
+    Extent E;
+    if (use_obb) {
         float3 ns = make_float3(0.f, 0.f, 0.f);
         for (uint32_t j = b + lane; j < e; j += 32) {
             const float4 r2 = rec_sorted[3 * (size_t)j + 2];
             ns.x += r2.y; ns.y += r2.z; ns.z += r2.w;
         }
         for (int o = 16; o; o >>= 1) {
-            ns.x += __shfl_xor_sync(0xffffffffu, ns.x, o);
-            ns.y += __shfl_xor_sync(0xffffffffu, ns.y, o);
-            ns.z += __shfl_xor_sync(0xffffffffu, ns.z, o);
+            ns.x += __shfl_xor_sync(full, ns.x, o);
+            ns.y += __shfl_xor_sync(full, ns.y, o);
+            ns.z += __shfl_xor_sync(full, ns.z, o);
         }
-        P.start(centre, ns);  // identical on all lanes (xor-butterfly sums are bitwise equal)
+        use_obb = frame_from_normal(ns, &F);  // identical on all lanes (xor-butterfly sums are bitwise equal)
+    }
+    if (use_obb) {
+        // lateral covariance of the vertices in the (v, w) plane
+        float sa = 0.f, sb = 0.f, saa = 0.f, sab = 0.f, sbb = 0.f, cnt = 0.f;
         for (uint32_t j = b + lane; j < e; j += 32) {
             const float4 r0 = rec_sorted[3 * (size_t)j], r1 = rec_sorted[3 * (size_t)j + 1],
                          r2 = rec_sorted[3 * (size_t)j + 2];
-            P.add(r0.x, r0.y, r0.z);
-            P.add(r0.w, r1.x, r1.y);
-            P.add(r1.z, r1.w, r2.x);
+            const float3 p3[3] = {make_float3(r0.x, r0.y, r0.z), make_float3(r0.w, r1.x, r1.y),
+                                  make_float3(r1.z, r1.w, r2.x)};
+            for (int k = 0; k < 3; ++k) {
+                const float3 d = f3sub(p3[k], origin);
+                const float pa = f3dot(d, F.v), pb = f3dot(d, F.w);
+                sa += pa; sb += pb; saa += pa * pa; sab += pa * pb; sbb += pb * pb; cnt += 1.0f;
+            }
         }
         for (int o = 16; o; o >>= 1) {
-            P.h = fmaxf(P.h, __shfl_xor_sync(0xffffffffu, P.h, o));
-            P.rho = fmaxf(P.rho, __shfl_xor_sync(0xffffffffu, P.rho, o));
+            sa += __shfl_xor_sync(full, sa, o); sb += __shfl_xor_sync(full, sb, o);
+            saa += __shfl_xor_sync(full, saa, o); sab += __shfl_xor_sync(full, sab, o);
+            sbb += __shfl_xor_sync(full, sbb, o); cnt += __shfl_xor_sync(full, cnt, o);
         }
-    }
-    P.finish(scene_mag(st));
-    if (kind == CHILD_BOTH) {
-        if (P.ux == 0.0f && P.uy == 0.0f && P.uz == 0.0f) {
-            kind = CHILD_BOX_ONLY;
-        } else {
-            // a patch that is flat compared with its box: the pillbox alone prunes as well as both
-            const float he = 0.5f * fminf(fminf(c1.x - c0.x, c1.y - c0.y), c1.z - c0.z);
-            if (P.h <= flat_thresh * he) kind = CHILD_PILL_ONLY;
+        const float inv = 1.0f / fmaxf(cnt, 1.0f);
+        const float ma = sa * inv, mb = sb * inv;
+        frame_align(&F, saa * inv - ma * ma, sab * inv - ma * mb, sbb * inv - mb * mb);
+        E.reset();
+        for (uint32_t j = b + lane; j < e; j += 32) {
+            const float4 r0 = rec_sorted[3 * (size_t)j], r1 = rec_sorted[3 * (size_t)j + 1],
+                         r2 = rec_sorted[3 * (size_t)j + 2];
+            E.add(F, f3sub(make_float3(r0.x, r0.y, r0.z), origin));
+            E.add(F, f3sub(make_float3(r0.w, r1.x, r1.y), origin));
+            E.add(F, f3sub(make_float3(r1.z, r1.w, r2.x), origin));
         }
+        for (int o = 16; o; o >>= 1)
+            for (int k = 0; k < 3; ++k) {
+                E.lo[k] = fminf(E.lo[k], __shfl_xor_sync(full, E.lo[k], o));
+                E.hi[k] = fmaxf(E.hi[k], __shfl_xor_sync(full, E.hi[k], o));
+            }
+        // keep the oriented box only where it is the smaller volume (top-level, curved subtrees are
+        // better served by the axis-aligned box, which is also cheaper to test)
+        const float vo = (E.hi[0] - E.lo[0] + 1e-4f) * (E.hi[1] - E.lo[1] + 1e-4f) * (E.hi[2] - E.lo[2] + 1e-4f);
+        const float va = (c1.x - c0.x) * (c1.y - c0.y) * (c1.z - c0.z);
+        use_obb = vo <= obb_bias * va;
     }
     if (lane == 0) {
-        ch[1].w = P.rho;
-        ch[2] = make_float4(P.cx, P.cy, P.cz, P.h);
-        ch[3] = make_float4(P.ux, P.uy, P.uz, kind);
+        if (use_obb) {
+            write_obb(ch, origin, F, E, scene_mag(st), __uint_as_float(ref | REF_OBB_BIT));
+        } else {
+            ch[0] = c0;  // (min.xyz, ref)
+            ch[1] = c1;  // (max.xyz, 0)
+            ch[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ch[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -390,8 +478,8 @@ k_hierarchy(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, float4* __
         node_parent[gamma + 1] = ((uint32_t)i << 1) | 1u;
     }
     // boxes are filled by the refit; store the refs now (degenerate bits are OR-ed in by the refit).
-    nodes[NODE_F4 * (size_t)i + 0].w = __uint_as_float(left);
-    nodes[NODE_F4 * (size_t)i + CHILD_F4].w = __uint_as_float(right);
+    nodes[BOX_F4 * (size_t)i + 0].w = __uint_as_float(left);
+    nodes[BOX_F4 * (size_t)i + 2].w = __uint_as_float(right);
     node_range[i] = make_uint2((uint32_t)lo, (uint32_t)hi);  // leaves covered by node i (inclusive)
     if (i == 0) node_parent[0] = 0xffffffffu;
 }
@@ -419,10 +507,10 @@ k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
     bool first_level = true;
     for (;;) {
         const uint32_t p = link >> 1, side = link & 1u;
-        float4* nd = nodes + NODE_F4 * (size_t)p;
+        float4* nd = nodes + BOX_F4 * (size_t)p;
         // write my box into my side of the parent (the child ref lives in .w of the side's first
         // float4, each written only by its own side)
-        float4* mine = nd + CHILD_F4 * side;
+        float4* mine = nd + 2 * side;
         uint32_t ref = __float_as_uint(mine[0].w);
         if (first_level && degen) ref |= LEAF_DEGEN_BIT;
         mine[0] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(ref));
@@ -434,8 +522,7 @@ k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
         // both children present: union and go up
         const volatile float4* vn = nd;
         float4 a0 = make_float4(vn[0].x, vn[0].y, vn[0].z, 0.f), a1 = make_float4(vn[1].x, vn[1].y, vn[1].z, 0.f);
-        float4 b0 = make_float4(vn[CHILD_F4].x, vn[CHILD_F4].y, vn[CHILD_F4].z, 0.f),
-               b1 = make_float4(vn[CHILD_F4 + 1].x, vn[CHILD_F4 + 1].y, vn[CHILD_F4 + 1].z, 0.f);
+        float4 b0 = make_float4(vn[2].x, vn[2].y, vn[2].z, 0.f), b1 = make_float4(vn[3].x, vn[3].y, vn[3].z, 0.f);
         lo[0] = fminf(a0.x, b0.x); lo[1] = fminf(a0.y, b0.y); lo[2] = fminf(a0.z, b0.z);
         hi[0] = fmaxf(a1.x, b1.x); hi[1] = fmaxf(a1.y, b1.y); hi[2] = fmaxf(a1.z, b1.z);
         link = node_parent[p];
@@ -485,8 +572,9 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     CK(d.vals_out.ensure(nt * 4));
     CK(d.tri_id_sorted.ensure(nt * 4));
     CK(d.nodes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * NODE_F4 * 16));
+    CK(d.boxes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * BOX_F4 * 16));
     CK(d.node_range.ensure((size_t)nleaf * 8));
-    CK(d.pill.ensure(nt * 32));
+    CK(d.tobb.ensure(nt * 64));
     CK(d.leaf_parent.ensure((size_t)nleaf * 4));
     CK(d.node_parent.ensure((size_t)nleaf * 4));
     CK(d.node_flag.ensure((size_t)nleaf * 4));
@@ -507,25 +595,26 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     d.launches += 8;  // CUB onesweep: histogram + 8 digit passes (counted approximately)
     k_tri_permute<<<blocks_for(nt, bs), bs, 0, s>>>(d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
                                                     d.vals_out.as<uint32_t>(), (uint32_t)nt, st,
-                                                    d.rec_sorted.as<float4>(), d.pill.as<float4>(),
+                                                    d.rec_sorted.as<float4>(), d.tobb.as<float4>(),
                                                     d.tri_id_sorted.as<uint32_t>());
     d.launches++;
     if (nleaf > 1) {
         CK(cudaMemsetAsync(d.node_flag.p, 0, (size_t)nleaf * 4, s));
         k_hierarchy<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.keys_out.as<uint64_t>(), K, (int)nleaf,
-                                                             d.nodes.as<float4>(), d.leaf_parent.as<uint32_t>(),
+                                                             d.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                              d.node_parent.as<uint32_t>(), d.node_range.as<uint2>());
         k_refit<<<blocks_for(nleaf, bs), bs, 0, s>>>(d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),
                                                      d.vals_out.as<uint32_t>(), (uint32_t)nt, K, (int)nleaf,
-                                                     d.nodes.as<float4>(), d.leaf_parent.as<uint32_t>(),
+                                                     d.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                      d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
-        k_pillbox<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
-            d.rec_sorted.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.nodes.as<float4>(), d.node_range.as<uint2>(), st,
-            d.flat_thresh);
+        k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
+            d.rec_sorted.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.boxes.as<float4>(), d.nodes.as<float4>(),
+            d.node_range.as<uint2>(), st, d.obb_bias);
         d.launches += 3;
     }
     d.bvh.rec = d.rec_sorted.as<float4>();
-    d.bvh.pill = d.pill.as<float4>();
+    d.bvh.tobb = d.tobb.as<float4>();
+    d.bvh.boxes = d.boxes.as<float4>();
     d.bvh.tri_id = d.tri_id_sorted.as<uint32_t>();
     d.bvh.nodes = d.nodes.as<float4>();
     d.bvh.nleaf = nleaf;

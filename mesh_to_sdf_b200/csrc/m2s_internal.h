@@ -17,22 +17,24 @@ namespace m2s {
 //   brute-force / row kernels, leaf (Morton) order for the LBVH kernels):
 //       r0 = (a.x, a.y, a.z, b.x)   r1 = (b.y, b.z, c.x, c.y)   r2 = (c.z, n.x, n.y, n.z)
 //       n = cross(b - a, c - a), un-normalised, un-fused (geo.rs:60-64)
-//   triangle pillbox, 32 B = 2 x float4 (leaf order): (centroid.xyz, rho) (unit normal.xyz, h)
-//   LBVH internal node, 128 B = 8 x float4: per child 4 x float4, box (padded -/+1e-4, geo.rs:18-21)
-//   plus pillbox (flat cylinder: centre, axis, radius, half height; see m2s_build.cu):
-//       c0 = (min.xyz, bits(child ref))  c1 = (max.xyz, rho)  c2 = (centre.xyz, h)  c3 = (axis.xyz, kind)
-//       kind: which of the two bounds a traversal needs to evaluate (CHILD_BOTH / _PILL_ONLY / _BOX_ONLY)
-//       left child at float4 0..3, right child at 4..7
+//   triangle oriented box, 64 B = 4 x float4 (leaf order): (centre.xyz, 0) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew)
+//   with u = unit normal, v along the longest edge: the cheap pretest in front of the exact arithmetic
+//   box node, 64 B = 4 x float4 (`boxes`): per child (min.xyz, bits(child ref)) (max.xyz, 0), padded
+//   -/+1e-4 like geo.rs:18-21. Written by the refit; read by the ray walks.
+//   search node, 128 B = 8 x float4 (`nodes`): per child 4 x float4, EITHER the same padded box
+//   (min.xyz, ref) (max.xyz, 0) 0 0 OR, when ref has REF_OBB_BIT, an oriented box fitted to the child's
+//   triangles (centre.xyz, ref) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew); see m2s_build.cu.
 //   child ref: >= 0 internal node index; < 0 leaf: bit31 set, bit30 = "leaf holds a degenerate
 //   triangle" (slow path with the geo.rs:73-88 guards), bits 0..29 = leaf index. Leaf l owns the
 //   sorted triangles [l*K, min((l+1)*K, nt)).
 // ---------------------------------------------------------------------------------------------------
 constexpr int NODE_F4 = 8;   // float4 per node
 constexpr int CHILD_F4 = 4;  // float4 per child slot
-constexpr float CHILD_BOTH = 0.0f, CHILD_PILL_ONLY = 1.0f, CHILD_BOX_ONLY = 2.0f;
+constexpr int BOX_F4 = 4;    // float4 per box node
+constexpr uint32_t REF_OBB_BIT = 0x20000000u;  // search-node child slot holds an oriented box
 constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr uint32_t LEAF_DEGEN_BIT = 0x40000000u;
-constexpr uint32_t LEAF_INDEX_MASK = 0x3fffffffu;
+constexpr uint32_t LEAF_INDEX_MASK = 0x1fffffffu;
 constexpr uint32_t TRI_DEGEN_BIT = 0x80000000u;  // in tri_id_sorted
 
 // Written by the build kernels, read back once per call (64 B).
@@ -51,7 +53,8 @@ static_assert(sizeof(BuildStatus) == 64, "BuildStatus must be 64 bytes");
 
 struct Bvh {
     const float4* rec;        // leaf-order triangle records
-    const float4* pill;       // leaf-order triangle pillboxes
+    const float4* tobb;       // leaf-order triangle oriented boxes (pretest)
+    const float4* boxes;      // box nodes (ray walks)
     const uint32_t* tri_id;   // leaf-order -> original triangle id (| TRI_DEGEN_BIT)
     const float4* nodes;      // internal nodes
     uint32_t nt;              // triangles
@@ -66,7 +69,8 @@ struct GridParams {
     float fx, fy, fz;     // Grid::first_cell
     float sx, sy, sz;     // Grid::cell_size
     uint32_t nx, ny, nz;  // Grid::cell_count
-    uint32_t x0, x1;      // slab [x0, x1) computed by this launch
+    uint32_t x0, x1;      // slab [x0, x1): origin of the output / seed indexing
+    uint32_t xa, xb;      // planes [xa, xb) of the slab computed by this launch (chunked host copies)
 };
 
 // Row parity bitmaps for the grid Raycast sign (generate/grid.rs:568-642). For axis A the rows are
@@ -105,18 +109,22 @@ struct Device {
     // mesh + LBVH
     DevBuf verts, tris;  // staging for the host entry points
     DevBuf rec_orig, rec_sorted, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
-    DevBuf tri_id_sorted, nodes, leaf_parent, node_parent, node_flag, node_range, pill, status;
+    DevBuf tri_id_sorted, nodes, leaf_parent, node_parent, node_flag, node_range, tobb, boxes, status;
     DevBuf rows[3], big_list, big_count;
     DevBuf stats;             // traversal counters, only with M2S_STATS=1
     bool want_stats = false;
     int stats_mode = 0;
-    float flat_thresh = 0.3f;  // pillbox-only children when h <= flat_thresh * min box half extent (M2S_FLAT)
+    float obb_bias = 1.0f;     // oriented box kept when its volume <= obb_bias * padded box volume (M2S_OBB_BIAS)
     bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
     DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
     int seed_levels = 1;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
     BuildStatus* h_status = nullptr;  // pinned
     cudaEvent_t ev[8] = {};
+    cudaStream_t copy_stream = nullptr;  // D2H of finished x-chunks overlaps the next chunk's kernel
+    cudaEvent_t ev_chunk[8] = {};
+    cudaEvent_t ev_copied = nullptr;
+    int host_chunks = 2;                 // M2S_HOST_CHUNKS
 
     Bvh bvh{};
 };
@@ -129,6 +137,14 @@ cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
 
 cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb);
 
+struct SeedLevel {
+    const uint32_t* parent;  // nearest-triangle slots of the parent level (nullptr: start unbounded)
+    uint32_t px, py, pz;     // parent level dims
+    uint32_t pstride;        // parent level stride in voxels
+};
+cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* L);
+cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L, int mode, const RowBits* rb,
+                              float* d_out);
 cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,
                                 cudaEvent_t after_seeds = nullptr);
 

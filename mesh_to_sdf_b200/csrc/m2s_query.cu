@@ -39,26 +39,23 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
-// squared lower bound of the distance from p to anything inside the pillbox (centre c, unit axis u,
-// radius rho, half height h); see m2s_build.cu. Plain fp32: a pruning bound, never a result.
-__device__ __forceinline__ float pill_dist2(const f3 p, float cx, float cy, float cz, float ux, float uy, float uz,
-                                            float rho, float h) {
-    const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
-    const float a = dx * ux + dy * uy + dz * uz;
-    const float lx = dx - a * ux, ly = dy - a * uy, lz = dz - a * uz;
-    const float l = sqrt_approx(lx * lx + ly * ly + lz * lz);  // 1 MUFU; its 1-2 ulp are inside the slack
-    const float da = fmaxf(fabsf(a) - h, 0.0f), dl = fmaxf(l - rho, 0.0f);
-    return da * da + dl * dl;
+// squared lower bound of the distance from p to anything inside the oriented box
+// (centre.xyz, *) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew); see m2s_build.cu. Plain fp32: a pruning bound,
+// never a result (the extents carry the slack for its rounding).
+__device__ __forceinline__ float obb_dist2(const f3 p, const float4 c, const float4 u, const float4 v, const float4 w) {
+    const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+    const float a = fmaxf(fabsf(dx * u.x + dy * u.y + dz * u.z) - u.w, 0.0f);
+    const float b = fmaxf(fabsf(dx * v.x + dy * v.y + dz * v.z) - v.w, 0.0f);
+    const float g = fmaxf(fabsf(dx * w.x + dy * w.y + dz * w.z) - w.w, 0.0f);
+    return a * a + b * b + g * g;
 }
 
-// lower bound for one child slot (4 x float4): max(box, pillbox)
+// lower bound for one child slot of a search node (4 x float4): oriented box or padded box, as the
+// build decided (REF_OBB_BIT; warp-uniform in the packet kernel)
 __device__ __forceinline__ float child_dist2(const f3 p, const float4 c0, const float4 c1, const float4 c2,
                                              const float4 c3) {
-    // c3.w says which bound is worth evaluating (decided at build time; warp-uniform in the packet kernel)
-    float b = 0.0f, q = 0.0f;
-    if (c3.w != CHILD_PILL_ONLY) b = box_dist2(p.x, p.y, p.z, c0.x, c0.y, c0.z, c1.x, c1.y, c1.z);
-    if (c3.w != CHILD_BOX_ONLY) q = pill_dist2(p, c2.x, c2.y, c2.z, c3.x, c3.y, c3.z, c1.w, c2.w);
-    return fmaxf(b, q);
+    if (__float_as_uint(c0.w) & REF_OBB_BIT) return obb_dist2(p, c0, c1, c2, c3);
+    return box_dist2(p.x, p.y, p.z, c0.x, c0.y, c0.z, c1.x, c1.y, c1.z);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -145,8 +142,8 @@ __device__ __forceinline__ void visit_leaf(const Bvh& bvh, uint32_t ref, const f
     for (uint32_t j = b; j < e; ++j) {
         // plane-disc pretest: skips the exact (un-fused, ~10x costlier) leaf arithmetic for triangles
         // that provably cannot change the result
-        const float4 q0 = ldg4(bvh.pill + 2 * (size_t)j), q1 = ldg4(bvh.pill + 2 * (size_t)j + 1);
-        if (pill_dist2(p, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q0.w, q1.w) > s.bound2) continue;
+        const float4* tb = bvh.tobb + 4 * (size_t)j;
+        if (obb_dist2(p, ldg4(tb), ldg4(tb + 1), ldg4(tb + 2), ldg4(tb + 3)) > s.bound2) continue;
         visit_tri<MODE>(bvh, j, degen, p, s);
     }
 }
@@ -181,7 +178,7 @@ __device__ __forceinline__ uint32_t node_step(const Bvh& bvh, uint32_t cur, cons
     const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
     const float dl = child_dist2(p, l0, l1, l2, l3);
     const float dr = child_dist2(p, r0, r1, r2, r3);
-    const uint32_t lref = __float_as_uint(l0.w), rref = __float_as_uint(r0.w);
+    const uint32_t lref = __float_as_uint(l0.w) & ~REF_OBB_BIT, rref = __float_as_uint(r0.w) & ~REF_OBB_BIT;
     const bool hl = dl <= s.bound2, hr = dr <= s.bound2;
     if (hl && hr) {
         const bool left_first = dl <= dr;
@@ -240,8 +237,8 @@ __device__ __forceinline__ void nearest(const Bvh& bvh, const f3 p, Near<MODE>& 
             const uint32_t b = leaf * bvh.leaf_size;
             const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
             for (uint32_t j = b; j < e; ++j) {
-                const float4 q0 = ldg4(bvh.pill + 2 * (size_t)j), q1 = ldg4(bvh.pill + 2 * (size_t)j + 1);
-                if (pill_dist2(p, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q0.w, q1.w) > s.bound2) continue;
+                const float4* tb = bvh.tobb + 4 * (size_t)j;
+                if (obb_dist2(p, ldg4(tb), ldg4(tb + 1), ldg4(tb + 2), ldg4(tb + 3)) > s.bound2) continue;
                 if (ntri == TRI_BATCH) {  // rare: flush
                     for (int t = 0; t < ntri; ++t)
                         visit_tri<MODE>(bvh, tribuf[t] & ~TRI_DEGEN_BIT, (tribuf[t] & TRI_DEGEN_BIT) != 0u, p, s);
@@ -289,8 +286,8 @@ __device__ __forceinline__ uint32_t ray_parity(const Bvh& bvh, const f3 o, int* 
                 if (ray_aligned<AXIS>(o, a, bb, c, &t)) ++count;
             }
         } else {
-            const float4* nd = bvh.nodes + NODE_F4 * (size_t)cur;
-            const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + CHILD_F4), n3 = ldg4(nd + CHILD_F4 + 1);
+            const float4* nd = bvh.boxes + BOX_F4 * (size_t)cur;
+            const float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
             const float llo[3] = {n0.x, n0.y, n0.z}, lhi[3] = {n1.x, n1.y, n1.z};
             const float rlo[3] = {n2.x, n2.y, n2.z}, rhi[3] = {n3.x, n3.y, n3.z};
             const bool hl = oy >= llo[IY] && oy <= lhi[IY] && oz >= llo[IZ] && oz <= lhi[IZ] && ox <= lhi[AXIS];
@@ -342,12 +339,6 @@ __device__ __forceinline__ float finish(const Bvh& bvh, const f3 p, const Near<M
 constexpr int BX = 4, BY = 8, BZ = 8;
 constexpr uint32_t SEED_STRIDE = 4;  // ratio between consecutive levels
 
-struct SeedLevel {
-    const uint32_t* parent;  // nearest-triangle slots of the parent level (nullptr: start unbounded)
-    uint32_t px, py, pz;     // parent level dims
-    uint32_t pstride;        // parent level stride in voxels
-};
-
 __device__ __forceinline__ void brick_coords(uint32_t nby, uint32_t nbz, uint32_t* x, uint32_t* y, uint32_t* z) {
     uint32_t bid = blockIdx.x;
     const uint32_t bz = bid % nbz;
@@ -397,8 +388,9 @@ k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const Se
                float* __restrict__ out, BuildStatus* __restrict__ st) {
     uint32_t xr, y, z;
     brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
+    xr += g.xa - g.x0;
     const uint32_t x = g.x0 + xr;
-    if (x >= g.x1 || y >= g.ny || z >= g.nz) return;
+    if (x >= g.xb || y >= g.ny || z >= g.nz) return;
 
     const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
     Near<MODE> s;
@@ -470,7 +462,8 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
         z = min(bzs * stride + stride / 2, g.nz - 1);
     } else {
         brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
-        valid = g.x0 + xr < g.x1 && y < g.ny && z < g.nz;
+        xr += g.xa - g.x0;  // this launch covers planes [xa, xb) of the slab
+        valid = g.x0 + xr < g.xb && y < g.ny && z < g.nz;
     }
     const uint32_t x = g.x0 + xr;
     if (!__any_sync(full, valid)) return;  // warp-uniform
@@ -519,7 +512,7 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
             const float dr = child_dist2(p, r0, r1, r2, r3);
             const bool hl = valid && dl <= s.bound2, hr = valid && dr <= s.bound2;
             const unsigned bl = __ballot_sync(full, hl), br = __ballot_sync(full, hr);
-            const uint32_t lref = __float_as_uint(l0.w), rref = __float_as_uint(r0.w);
+            const uint32_t lref = __float_as_uint(l0.w) & ~REF_OBB_BIT, rref = __float_as_uint(r0.w) & ~REF_OBB_BIT;
             if (bl && br) {
                 // warp-min lower bounds over the lanes that want the child
                 const unsigned ml = __reduce_min_sync(full, hl ? __float_as_uint(dl) : 0x7f800000u);
@@ -547,8 +540,8 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
             const uint32_t b = leaf * bvh.leaf_size;
             const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
             for (uint32_t j = b; j < e; ++j) {  // warp-uniform loop, uniform loads
-                const float4 q0 = ldg4(bvh.pill + 2 * (size_t)j), q1 = ldg4(bvh.pill + 2 * (size_t)j + 1);
-                const bool want = valid && pill_dist2(p, q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q0.w, q1.w) <= s.bound2;
+                const float4* tb = bvh.tobb + 4 * (size_t)j;
+                const bool want = valid && obb_dist2(p, ldg4(tb), ldg4(tb + 1), ldg4(tb + 2), ldg4(tb + 3)) <= s.bound2;
                 if (want) tribuf[ntri++] = j | dg;
                 // a full queue anywhere forces a flush before the next triangle (only leaves with
                 // more triangles than the queue has room for after the per-leaf flush can get here)
@@ -864,18 +857,14 @@ static float grid_magnitude(const GridParams& g) {
 
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
-cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,
-                                cudaEvent_t after_seeds) {
+// Coarse seeding pass(es) over the whole slab [g.x0, g.x1).
+cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* out) {
     cudaStream_t s = d.stream;
     const uint32_t sx = g.x1 - g.x0;
-    const uint64_t nblocks = (uint64_t)cdiv(sx, BX) * cdiv(g.ny, BY) * cdiv(g.nz, BZ);
-    if (nblocks == 0) return cudaSuccess;
-    if (nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     const float mag = grid_magnitude(g);
     BuildStatus* st = d.status.as<BuildStatus>();
-
-    // coarse-to-fine seeding: strides 16 and 4 (skipped for grids that are too small to profit)
     SeedLevel L{nullptr, 0, 0, 0, 0};
+    // strides 4 (and 16 with M2S_SEED_LEVELS=2); skipped for grids that are too small to profit
     if (d.seed_levels > 0 && (uint64_t)sx * g.ny * g.nz >= 4096) {
         const int nlev = d.seed_levels > 2 ? 2 : d.seed_levels;
         for (int lev = nlev; lev >= 1; --lev) {
@@ -894,7 +883,19 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
             L = SeedLevel{buf.as<uint32_t>(), cx, cy, cz, stride};
         }
     }
-    if (after_seeds) cudaEventRecord(after_seeds, s);
+    *out = L;
+    return cudaGetLastError();
+}
+
+// The distance kernel over planes [g.xa, g.xb) of the slab.
+cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L, int mode, const RowBits* rb,
+                              float* d_out) {
+    cudaStream_t s = d.stream;
+    const uint64_t nblocks = (uint64_t)cdiv(g.xb - g.xa, BX) * cdiv(g.ny, BY) * cdiv(g.nz, BZ);
+    if (nblocks == 0) return cudaSuccess;
+    if (nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    const float mag = grid_magnitude(g);
+    BuildStatus* st = d.status.as<BuildStatus>();
     const unsigned nb = (unsigned)nblocks;
     if (d.packet) {
         if (rb) {
@@ -907,10 +908,7 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
             k_grid_nearest_pkt<MODE_UNSIGNED, false, false><<<nb, 256, 0, s>>>(
                 d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st, 1u, make_uint3(0, 0, 0));
         }
-        d.launches++;
-        return cudaGetLastError();
-    }
-    if (rb) {
+    } else if (rb) {
         k_grid_nearest<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2],
                                                                d_out, st);
     } else if (mode == MODE_NORMAL) {
@@ -920,6 +918,14 @@ cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const 
     }
     d.launches++;
     return cudaGetLastError();
+}
+
+cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,
+                                cudaEvent_t after_seeds) {
+    SeedLevel L{};
+    CK(launch_grid_seeds(d, g, &L));
+    if (after_seeds) cudaEventRecord(after_seeds, d.stream);
+    return launch_grid_final(d, g, L, mode, rb, d_out);
 }
 
 // sign_rule: 0 none, 1 = +X parity, 3 = best of three axes

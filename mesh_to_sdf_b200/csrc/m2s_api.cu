@@ -251,8 +251,10 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         }
         std::memset(d.h_status, 0, sizeof(BuildStatus));
         if (const char* e = std::getenv("M2S_PACKET")) d.packet = std::atoi(e) != 0;
+        if (const char* e = std::getenv("M2S_SEED_PACKET")) d.seed_packet = std::atoi(e) != 0;
         if (const char* e = std::getenv("M2S_OBB_BIAS")) d.obb_bias = (float)std::atof(e);
         if (const char* e = std::getenv("M2S_STATS")) { d.want_stats = std::atoi(e) != 0; d.stats_mode = std::atoi(e); }
+        if (const char* e = std::getenv("M2S_SEED_STRIDE")) d.seed_stride = (uint32_t)std::max(2, std::min(64, std::atoi(e)));
         if (const char* e = std::getenv("M2S_SEED_LEVELS")) d.seed_levels = std::max(0, std::min(2, std::atoi(e)));
     }
     if (const char* e = std::getenv("M2S_LEAF_SIZE")) ctx->leaf_size = (uint32_t)std::max(1, std::min(32, std::atoi(e)));

@@ -115,8 +115,10 @@ struct Device {
     bool want_stats = false;
     int stats_mode = 0;
     float obb_bias = 1.0f;     // oriented box kept when its volume <= obb_bias * padded box volume (M2S_OBB_BIAS)
+    bool seed_packet = false;  // M2S_SEED_PACKET=0: per-lane traversal for the seed pass
     bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
     DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
+    uint32_t seed_stride = 4;  // voxels per seed block edge (M2S_SEED_STRIDE)
     int seed_levels = 1;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
     BuildStatus* h_status = nullptr;  // pinned
@@ -162,6 +164,6 @@ struct m2s_ctx {
     m2s::Device* dev = nullptr;
     std::string last_error;
     m2s_timings timings{};
-    uint32_t leaf_size = 2;
+    uint32_t leaf_size = 1;
     std::mutex mu;  // a context serves one call at a time
 };

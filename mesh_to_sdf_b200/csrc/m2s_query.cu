@@ -90,6 +90,17 @@ struct Near {
     }
 };
 
+// Exact squared distance from p to triangle slot j: geo.rs:70-138 + Point::dist2, un-fused.
+__device__ __forceinline__ float exact_d2(const Bvh& bvh, uint32_t j, bool degen, const f3 p) {
+    const float4 r0 = ldg4(bvh.rec + 3 * (size_t)j);
+    const float4 r1 = ldg4(bvh.rec + 3 * (size_t)j + 1);
+    const float4 r2 = ldg4(bvh.rec + 3 * (size_t)j + 2);
+    const f3 a = {r0.x, r0.y, r0.z}, bb = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
+    const f3 q = degen ? closest_point_triangle_any(p, a, bb, c) : closest_point_triangle(p, a, bb, c);
+    const f3 dir = v_sub(p, q);
+    return v_dot(dir, dir);
+}
+
 // One triangle (leaf-order slot j) against the query: the leaf arithmetic of geo.rs:26-56.
 template <int MODE>
 __device__ __forceinline__ void visit_tri(const Bvh& bvh, uint32_t j, bool degen, const f3 p, Near<MODE>& s) {
@@ -154,6 +165,27 @@ template <int MODE>
 __device__ __forceinline__ void seed_tri(const Bvh& bvh, uint32_t j, const f3 p, Near<MODE>& s) {
     if (j >= bvh.nt) return;
     visit_tri<MODE>(bvh, j, (bvh.tri_id[j] & TRI_DEGEN_BIT) != 0u, p, s);
+}
+
+// Greedy descent (no backtracking): follows the child with the smaller lower bound down to one leaf and
+// evaluates its triangles. ~depth node visits; gives a search that has no seed a finite radius to
+// start with (a from-infinity packet walk over 32 spread-out voxels visits thousands of nodes).
+template <int MODE>
+__device__ __forceinline__ void greedy_seed(const Bvh& bvh, const f3 p, Near<MODE>& s) {
+    if (bvh.nt == 0) return;
+    uint32_t cur = bvh.root;
+    for (int guard = 0; guard < 256 && !(cur & LEAF_BIT); ++guard) {
+        const float4* nd = bvh.nodes + NODE_F4 * (size_t)cur;
+        const float4 l0 = ldg4(nd), l1 = ldg4(nd + 1), l2 = ldg4(nd + 2), l3 = ldg4(nd + 3);
+        const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
+        const float dl = child_dist2(p, l0, l1, l2, l3), dr = child_dist2(p, r0, r1, r2, r3);
+        cur = (dl <= dr ? __float_as_uint(l0.w) : __float_as_uint(r0.w)) & ~REF_OBB_BIT;
+    }
+    if (!(cur & LEAF_BIT)) return;
+    const uint32_t leaf = cur & LEAF_INDEX_MASK;
+    const bool degen = (cur & LEAF_DEGEN_BIT) != 0u;
+    const uint32_t b = leaf * bvh.leaf_size, e = min(bvh.nt, b + bvh.leaf_size);
+    for (uint32_t j = b; j < e; ++j) visit_tri<MODE>(bvh, j, degen, p, s);
 }
 
 constexpr uint32_t TRAVERSAL_DONE = 0xffffffffu;  // has LEAF_BIT set; never a real leaf ref (nt < 2^30)
@@ -375,6 +407,7 @@ k_grid_seed(const Bvh bvh, const GridParams g, const float grid_mag, const uint3
     Near<MODE_UNSIGNED> s;
     s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
     if (L.parent) seed_tri<MODE_UNSIGNED>(bvh, parent_seed(L, xr, y, z), p, s);
+    else greedy_seed<MODE_UNSIGNED>(bvh, p, s);
     int overflow = 0;
     nearest<MODE_UNSIGNED>(bvh, p, s, &overflow);
     seeds[((size_t)bx * cy + by) * cz + bz] = s.slot;
@@ -433,6 +466,7 @@ k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const Se
 constexpr int PKT_STACK = 128;
 constexpr int PKT_TRI_BATCH = 16;   // per-lane queue of surviving triangles
 constexpr int PKT_FLUSH_AT = 6;     // flush all lanes' queues once any lane holds this many
+constexpr int PKT_QCAP = 96;        // warp-shared work queue (UNSIGNED): < 32 left over + 2 x 32 appended per node
 
 template <int MODE>
 __device__ __forceinline__ float warp_max_bound(const Near<MODE>& s, bool valid) {
@@ -443,14 +477,17 @@ __device__ __forceinline__ float warp_max_bound(const Near<MODE>& s, bool valid)
 // SEEDPASS: the same walk over the representative voxels of the stride^3 blocks (cdim = block counts),
 // storing the nearest triangle's slot instead of a distance.
 template <int MODE, bool RAYSIGN, bool SEEDPASS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
                    const uint32_t* __restrict__ px, const uint32_t* __restrict__ py,
                    const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st,
                    const uint32_t stride, const uint3 cdim) {
     __shared__ uint2 s_stack[8][PKT_STACK];
+    __shared__ uint2 s_queue[8][MODE == MODE_UNSIGNED ? PKT_QCAP : 1];       // (triangle slot | degen, owner lane)
+    __shared__ unsigned long long s_best[8][MODE == MODE_UNSIGNED ? 32 : 1];  // per owner: (d2 bits << 32) | slot
     const unsigned full = 0xffffffffu;
-    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t xr, y, z;
     uint32_t bxs = 0, bys = 0, bzs = 0;
     bool valid;
@@ -471,11 +508,22 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
     Near<MODE> s;
     s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
-    if (valid && L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
+    if (valid) {
+        if (L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
+        else greedy_seed<MODE>(bvh, p, s);
+    }
     float max_b = warp_max_bound<MODE>(s, valid);
 
-    uint32_t tribuf[PKT_TRI_BATCH];
+    // Exact-arithmetic work. NORMAL: per-lane queue (the compare_distances fold is order dependent and
+    // stays with its voxel). UNSIGNED: one warp-shared queue of (triangle, owner) items processed 32 at a
+    // time, any lane working for any voxel of the tile (the owner's position comes by shuffle, the
+    // minimum goes back through a shared-memory atomicMin) - the expensive un-fused code then runs with
+    // all lanes busy instead of ~10 of 32.
+    uint32_t tribuf[MODE == MODE_UNSIGNED ? 1 : PKT_TRI_BATCH];
     int ntri = 0;
+    int qn = 0;  // warp-uniform
+    uint2* queue = s_queue[warp];
+    unsigned long long* best = s_best[warp];
     int sp = 0;
     int overflow = 0;
     uint32_t n_nodes = 0, n_leaves = 0;
@@ -494,11 +542,55 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
         __syncwarp();  // every lane has read its entry before lane 0 may overwrite the slot
         return r;
     };
-    auto flush = [&]() {
-        const int most = __reduce_max_sync(full, ntri);
-        for (int t = 0; t < most; ++t)
-            if (t < ntri) visit_tri<MODE>(bvh, tribuf[t] & ~TRI_DEGEN_BIT, (tribuf[t] & TRI_DEGEN_BIT) != 0u, p, s);
-        ntri = 0;
+    // every lane calls enqueue (uniform); `want` says whether this lane's voxel needs triangle `item`
+    auto enqueue = [&](bool want, uint32_t item) {
+        if (MODE == MODE_UNSIGNED) {
+            const unsigned m = __ballot_sync(full, want);
+            if (want) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane);
+            qn += __popc(m);
+        } else if (want) {
+            tribuf[ntri++] = item;
+        }
+    };
+    // everything == false: only full batches of 32 (UNSIGNED) / only when a lane's queue is filling (NORMAL)
+    auto flush = [&](bool everything) {
+        if (MODE == MODE_UNSIGNED) {
+            const int nb = everything ? (qn + 31) >> 5 : qn >> 5;
+            if (nb == 0) return;
+            best[lane] = ((unsigned long long)__float_as_uint(s.best2) << 32) | s.slot;
+            __syncwarp();
+            for (int b = 0; b < nb; ++b) {
+                const int idx = b * 32 + (int)lane;
+                const bool act = idx < qn;
+                const uint2 it = act ? queue[idx] : make_uint2(0u, lane);
+                const f3 po = {__shfl_sync(full, p.x, it.y), __shfl_sync(full, p.y, it.y), __shfl_sync(full, p.z, it.y)};
+                if (act) {
+                    const uint32_t j = it.x & ~TRI_DEGEN_BIT;
+                    const float d2 = exact_d2(bvh, j, (it.x & TRI_DEGEN_BIT) != 0u, po);
+                    atomicMin(best + it.y, ((unsigned long long)__float_as_uint(d2) << 32) | j);
+                }
+            }
+            __syncwarp();
+            const int done = min(nb * 32, qn), rem = qn - done;
+            const uint2 keep = (int)lane < rem ? queue[done + lane] : make_uint2(0u, 0u);
+            const unsigned long long v = best[lane];
+            __syncwarp();
+            if ((int)lane < rem) queue[lane] = keep;
+            qn = rem;
+            const float nb2 = __uint_as_float((unsigned)(v >> 32));
+            if (nb2 < s.best2) {
+                s.best2 = nb2;
+                s.slot = (uint32_t)v;
+                s.set_bound(sqrt_approx(nb2));
+            }
+            __syncwarp();
+        } else {
+            const int most = __reduce_max_sync(full, ntri);
+            if (!everything && most < PKT_FLUSH_AT) return;
+            for (int t = 0; t < most; ++t)
+                if (t < ntri) visit_tri<MODE>(bvh, tribuf[t] & ~TRI_DEGEN_BIT, (tribuf[t] & TRI_DEGEN_BIT) != 0u, p, s);
+            ntri = 0;
+        }
         max_b = warp_max_bound<MODE>(s, valid);
     };
 
@@ -511,8 +603,26 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
             const float dl = child_dist2(p, l0, l1, l2, l3);
             const float dr = child_dist2(p, r0, r1, r2, r3);
             const bool hl = valid && dl <= s.bound2, hr = valid && dr <= s.bound2;
-            const unsigned bl = __ballot_sync(full, hl), br = __ballot_sync(full, hr);
+            unsigned bl = __ballot_sync(full, hl), br = __ballot_sync(full, hr);
             const uint32_t lref = __float_as_uint(l0.w) & ~REF_OBB_BIT, rref = __float_as_uint(r0.w) & ~REF_OBB_BIT;
+            if (bvh.leaf_size == 1u) {
+                // single-triangle leaves: the child's box IS the triangle's box, so the lanes that want it
+                // queue the triangle right here and the leaf is never pushed / popped / re-tested
+                bool queued = false;
+                if ((lref & LEAF_BIT) && bl) {
+                    enqueue(hl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    bl = 0u;
+                    queued = true;
+                    ++n_leaves;
+                }
+                if ((rref & LEAF_BIT) && br) {
+                    enqueue(hr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    br = 0u;
+                    queued = true;
+                    ++n_leaves;
+                }
+                if (queued) flush(false);
+            }
             if (bl && br) {
                 // warp-min lower bounds over the lanes that want the child
                 const unsigned ml = __reduce_min_sync(full, hl ? __float_as_uint(dl) : 0x7f800000u);
@@ -542,16 +652,17 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
             for (uint32_t j = b; j < e; ++j) {  // warp-uniform loop, uniform loads
                 const float4* tb = bvh.tobb + 4 * (size_t)j;
                 const bool want = valid && obb_dist2(p, ldg4(tb), ldg4(tb + 1), ldg4(tb + 2), ldg4(tb + 3)) <= s.bound2;
-                if (want) tribuf[ntri++] = j | dg;
-                // a full queue anywhere forces a flush before the next triangle (only leaves with
-                // more triangles than the queue has room for after the per-leaf flush can get here)
-                if (bvh.leaf_size > PKT_TRI_BATCH - PKT_FLUSH_AT && __any_sync(full, ntri == PKT_TRI_BATCH)) flush();
+                enqueue(want, j | dg);
+                // UNSIGNED: at most 31 + 32 items are queued here, below PKT_QCAP. NORMAL: a lane's queue holds
+                // PKT_TRI_BATCH; drain it when a big leaf (K > batch - flush level) could overflow it
+                if (MODE == MODE_UNSIGNED) flush(false);
+                else if (bvh.leaf_size > PKT_TRI_BATCH - PKT_FLUSH_AT && __any_sync(full, ntri == PKT_TRI_BATCH)) flush(true);
             }
-            if (__any_sync(full, ntri >= PKT_FLUSH_AT)) flush();
+            flush(false);
             cur = pop();
         }
     }
-    flush();
+    flush(true);
 
     if (SEEDPASS) {
         if (valid) reinterpret_cast<uint32_t*>(out)[((size_t)bxs * cdim.y + bys) * cdim.z + bzs] = s.slot;
@@ -869,12 +980,12 @@ cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* out) {
         const int nlev = d.seed_levels > 2 ? 2 : d.seed_levels;
         for (int lev = nlev; lev >= 1; --lev) {
             uint32_t stride = 1;
-            for (int k = 0; k < lev; ++k) stride *= SEED_STRIDE;
+            for (int k = 0; k < lev; ++k) stride *= d.seed_stride;
             const uint32_t cx = cdiv(sx, stride), cy = cdiv(g.ny, stride), cz = cdiv(g.nz, stride);
             DevBuf& buf = d.seeds[lev - 1];
             CK(buf.ensure((size_t)cx * cy * cz * 4));
             const unsigned nb = cdiv(cx, BX) * cdiv(cy, BY) * cdiv(cz, BZ);
-            if (d.packet)
+            if (d.packet && d.seed_packet)
                 k_grid_nearest_pkt<MODE_UNSIGNED, false, true><<<nb, 256, 0, s>>>(
                     d.bvh, g, mag, L, nullptr, nullptr, nullptr, buf.as<float>(), st, stride, make_uint3(cx, cy, cz));
             else

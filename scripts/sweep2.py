@@ -10,7 +10,8 @@ def case(nu, nv, n):
     return verts, tris, m2s.Grid.from_bounding_box(mn, mx, [n, n, n])
 cases = {"C2": case(64, 40, 128) + (1,), "C3": case(256, 196, 256) + (0,)}
 ref = {}
-knobs = [dict(zip(("M2S_SEED_LEVELS", "M2S_LEAF_SIZE", "M2S_OBB_BIAS"), k)) for k in itertools.product(("1",), ("1", "2", "4"), ("0.7", "1.0", "1.4"))]
+knobs = [dict(zip(("M2S_SEED_PACKET", "M2S_SEED_STRIDE", "M2S_LEAF_SIZE"), k)) for k in itertools.product(("0",), ("4",), ("1", "2"))]
+os.environ["M2S_HOST_CHUNKS"] = "1"
 for kn in knobs:
     os.environ.update(kn)
     with m2s.Context() as ctx:

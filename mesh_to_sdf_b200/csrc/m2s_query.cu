@@ -474,44 +474,22 @@ __device__ __forceinline__ float warp_max_bound(const Near<MODE>& s, bool valid)
     return __uint_as_float(__reduce_max_sync(0xffffffffu, b));
 }
 
-// SEEDPASS: the same walk over the representative voxels of the stride^3 blocks (cdim = block counts),
-// storing the nearest triangle's slot instead of a distance.
-template <int MODE, bool RAYSIGN, bool SEEDPASS>
-__global__ void __launch_bounds__(256, 4)
-k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
-                   const uint32_t* __restrict__ px, const uint32_t* __restrict__ py,
-                   const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st,
-                   const uint32_t stride, const uint3 cdim) {
-    __shared__ uint2 s_stack[8][PKT_STACK];
-    __shared__ uint2 s_queue[8][MODE == MODE_UNSIGNED ? PKT_QCAP : 1];       // (triangle slot | degen, owner lane)
-    __shared__ unsigned long long s_best[8][MODE == MODE_UNSIGNED ? 32 : 1];  // per owner: (d2 bits << 32) | slot
-    const unsigned full = 0xffffffffu;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    uint32_t xr, y, z;
-    uint32_t bxs = 0, bys = 0, bzs = 0;
-    bool valid;
-    if (SEEDPASS) {
-        brick_coords((cdim.y + BY - 1) / BY, (cdim.z + BZ - 1) / BZ, &bxs, &bys, &bzs);
-        valid = bxs < cdim.x && bys < cdim.y && bzs < cdim.z;
-        xr = min(bxs * stride + stride / 2, g.x1 - g.x0 - 1);
-        y = min(bys * stride + stride / 2, g.ny - 1);
-        z = min(bzs * stride + stride / 2, g.nz - 1);
-    } else {
-        brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
-        xr += g.xa - g.x0;  // this launch covers planes [xa, xb) of the slab
-        valid = g.x0 + xr < g.xb && y < g.ny && z < g.nz;
-    }
-    const uint32_t x = g.x0 + xr;
-    if (!__any_sync(full, valid)) return;  // warp-uniform
+// The packet walk itself: all 32 lanes call it together (valid == false lanes only help). On return every
+// valid lane's state `s` holds its own exact result. stack / queue / best are this warp's shared arrays.
+struct PacketCounters {
+    uint32_t nodes, leaves;
+    int overflow;
+};
 
-    const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
-    Near<MODE> s;
-    s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
-    if (valid) {
-        if (L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
-        else greedy_seed<MODE>(bvh, p, s);
-    }
+template <int MODE>
+__device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const bool valid, Near<MODE>& s,
+                                              uint2* stack, uint2* queue, unsigned long long* best,
+                                              PacketCounters* ctr) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int overflow = 0;
+    uint32_t n_nodes = 0, n_leaves = 0;
     float max_b = warp_max_bound<MODE>(s, valid);
 
     // Exact-arithmetic work. NORMAL: per-lane queue (the compare_distances fold is order dependent and
@@ -522,12 +500,7 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
     uint32_t tribuf[MODE == MODE_UNSIGNED ? 1 : PKT_TRI_BATCH];
     int ntri = 0;
     int qn = 0;  // warp-uniform
-    uint2* queue = s_queue[warp];
-    unsigned long long* best = s_best[warp];
     int sp = 0;
-    int overflow = 0;
-    uint32_t n_nodes = 0, n_leaves = 0;
-    uint2* stack = s_stack[warp];
     uint32_t cur = bvh.nt ? bvh.root : TRAVERSAL_DONE;
 
     auto pop = [&]() -> uint32_t {
@@ -663,6 +636,52 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
         }
     }
     flush(true);
+    ctr->nodes = n_nodes;
+    ctr->leaves = n_leaves;
+    ctr->overflow = overflow;
+}
+
+// SEEDPASS: the same walk over the representative voxels of the stride^3 blocks (cdim = block counts),
+// storing the nearest triangle's slot instead of a distance.
+template <int MODE, bool RAYSIGN, bool SEEDPASS>
+__global__ void __launch_bounds__(256, 4)
+k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
+                   const uint32_t* __restrict__ px, const uint32_t* __restrict__ py,
+                   const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st,
+                   const uint32_t stride, const uint3 cdim) {
+    __shared__ uint2 s_stack[8][PKT_STACK];
+    __shared__ uint2 s_queue[8][MODE == MODE_UNSIGNED ? PKT_QCAP : 1];       // (triangle slot | degen, owner lane)
+    __shared__ unsigned long long s_best[8][MODE == MODE_UNSIGNED ? 32 : 1];  // per owner: (d2 bits << 32) | slot
+    const unsigned full = 0xffffffffu;
+    const uint32_t warp = threadIdx.x >> 5;
+    uint32_t xr, y, z;
+    uint32_t bxs = 0, bys = 0, bzs = 0;
+    bool valid;
+    if (SEEDPASS) {
+        brick_coords((cdim.y + BY - 1) / BY, (cdim.z + BZ - 1) / BZ, &bxs, &bys, &bzs);
+        valid = bxs < cdim.x && bys < cdim.y && bzs < cdim.z;
+        xr = min(bxs * stride + stride / 2, g.x1 - g.x0 - 1);
+        y = min(bys * stride + stride / 2, g.ny - 1);
+        z = min(bzs * stride + stride / 2, g.nz - 1);
+    } else {
+        brick_coords((g.ny + BY - 1) / BY, (g.nz + BZ - 1) / BZ, &xr, &y, &z);
+        xr += g.xa - g.x0;  // this launch covers planes [xa, xb) of the slab
+        valid = g.x0 + xr < g.xb && y < g.ny && z < g.nz;
+    }
+    const uint32_t x = g.x0 + xr;
+    if (!__any_sync(full, valid)) return;  // warp-uniform
+
+    const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
+    Near<MODE> s;
+    s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
+    if (valid) {
+        if (L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
+        else greedy_seed<MODE>(bvh, p, s);
+    }
+    PacketCounters ctr;
+    packet_search<MODE>(bvh, p, valid, s, s_stack[warp], s_queue[warp], s_best[warp], &ctr);
+    const int overflow = ctr.overflow;
+    const uint32_t n_nodes = ctr.nodes, n_leaves = ctr.leaves;
 
     if (SEEDPASS) {
         if (valid) reinterpret_cast<uint32_t*>(out)[((size_t)bxs * cdim.y + bys) * cdim.z + bzs] = s.slot;
@@ -901,6 +920,47 @@ k_points(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, const 
     if (MODE == MODE_NORMAL && s.nan) atomicExch(&st->nan_distance, 1);
 }
 
+// Packet variant for scattered queries: 32 consecutive Morton-sorted queries are close together, so they
+// share one tree walk exactly like a voxel tile. No seed pass: every lane starts from a greedy descent.
+template <int MODE, int SIGN>
+__global__ void __launch_bounds__(256, 4)
+k_points_pkt(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, float* __restrict__ out,
+             BuildStatus* __restrict__ st) {
+    __shared__ uint2 s_stack[8][PKT_STACK];
+    __shared__ uint2 s_queue[8][MODE == MODE_UNSIGNED ? PKT_QCAP : 1];
+    __shared__ unsigned long long s_best[8][MODE == MODE_UNSIGNED ? 32 : 1];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < nq;
+    if (!__any_sync(0xffffffffu, valid)) return;  // warp-uniform
+    const float4 q = valid ? q_sorted[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const f3 p = {q.x, q.y, q.z};
+    Near<MODE> s;
+    s.init(4.0e-6f * scene_magnitude(st));
+    if (valid) greedy_seed<MODE>(bvh, p, s);
+    PacketCounters ctr;
+    packet_search<MODE>(bvh, p, valid, s, s_stack[warp], s_queue[warp], s_best[warp], &ctr);
+    int overflow = ctr.overflow;
+    if (valid) {
+        float d = finish<MODE>(bvh, p, s);
+        if (SIGN == 1) {
+            if (ray_parity<0>(bvh, p, &overflow)) d = -d;
+        } else if (SIGN == 3) {
+            const uint32_t insides = ray_parity<0>(bvh, p, &overflow) + ray_parity<1>(bvh, p, &overflow) +
+                                     ray_parity<2>(bvh, p, &overflow);
+            if (insides > 1u) d = -d;
+        }
+        out[__float_as_uint(q.w)] = d;
+        if (MODE == MODE_NORMAL && s.nan) atomicExch(&st->nan_distance, 1);
+    }
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+    if (bvh.stats && (threadIdx.x & 31) == 0) {
+        atomicAdd(bvh.stats + 0, (unsigned long long)ctr.nodes);
+        atomicAdd(bvh.stats + 1, (unsigned long long)ctr.leaves);
+        atomicAdd(bvh.stats + 2, 1ull);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_fill(float* __restrict__ out, uint64_t n, float v) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
         out[i] = v;
@@ -1047,6 +1107,17 @@ cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float
     BuildStatus* st = d.status.as<BuildStatus>();
     const uint32_t n = (uint32_t)nq;
 
+    if (d.packet) {
+        if (after_seeds) cudaEventRecord(after_seeds, s);
+        const unsigned nbp = blocks_for(nq, 256);
+        if (mode == MODE_NORMAL) k_points_pkt<MODE_NORMAL, 0><<<nbp, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+        else if (mode == MODE_ARGMIN) k_points_pkt<MODE_ARGMIN, 0><<<nbp, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+        else if (sign_rule == 1) k_points_pkt<MODE_UNSIGNED, 1><<<nbp, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+        else if (sign_rule == 3) k_points_pkt<MODE_UNSIGNED, 3><<<nbp, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+        else k_points_pkt<MODE_UNSIGNED, 0><<<nbp, 256, 0, s>>>(d.bvh, q, n, d_out, st);
+        d.launches++;
+        return cudaGetLastError();
+    }
     const uint32_t* parent = nullptr;
     uint32_t parent_count = 0;
     if (d.seed_levels > 0 && n >= 4096) {

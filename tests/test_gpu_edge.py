@@ -1,0 +1,138 @@
+"""GPU edge cases through the C ABI, each against the exact oracle: the reference's own fixture meshes
+(suzanne, ferris3d), grids that do not contain the mesh (generate/grid.rs:810-843), negative and anisotropic
+cell sizes (grid.rs:25 allows them), meshes far from the origin (pruning slack scales with the coordinates),
+triangles much larger than a cell (the k_rows_big path), tiny grids, multi-device contexts."""
+import os
+
+import numpy as np
+import pytest
+
+from mesh_to_sdf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+RAYCAST, NORMAL = 0, 1
+
+
+def load_mesh(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    return z["vertices"].astype(np.float32), z["indices"].astype(np.uint32).reshape(-1, 3)
+
+
+def assert_grid_matches(m2s, oracle, verts, tris, grid, sign):
+    got = m2s.default_context().grid_sdf(verts, tris, grid, sign)
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, sign)
+    if sign == RAYCAST:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    else:
+        assert np.max(np.abs(np.abs(got) - np.abs(want))) <= 4e-6 * max(1.0, float(np.abs(verts).max()))
+        assert np.array_equal(np.signbit(got), np.signbit(want))
+    return got
+
+
+@pytest.mark.parametrize("sign", [RAYCAST, NORMAL])
+def test_suzanne_grid_32(m2s, oracle, sign):
+    # generic/bvh.rs:192-310 use this fixture at 32^3 / 16^3 (bbox of the mesh itself: cells touch the surface)
+    verts, tris = load_mesh("suzanne")
+    grid = m2s.Grid.from_bounding_box(verts.min(axis=0), verts.max(axis=0), [32, 32, 32])
+    assert_grid_matches(m2s, oracle, verts, tris, grid, sign)
+
+
+def test_ferris_continuity_and_out_of_bounds(m2s, oracle):
+    verts, tris = load_mesh("ferris3d")
+    mn, mx = verts.min(axis=0), verts.max(axis=0)
+    ext = mx - mn
+    grid = m2s.Grid.from_bounding_box(mn - 0.2 * ext, mx + 0.23 * ext, [32, 32, 32])  # grid.rs:728-807
+    sdf = assert_grid_matches(m2s, oracle, verts, tris, grid, RAYCAST).reshape(32, 32, 32)
+    for axis in range(3):
+        assert np.all(np.abs(np.diff(np.abs(sdf), axis=axis)) <= float(grid.cell_size[axis]) * (1 + 1e-4))
+    small = m2s.Grid.from_bounding_box(mn, mx * 0.5, [32, 32, 32])  # grid.rs:810-843: grid does not contain the mesh
+    assert_grid_matches(m2s, oracle, verts, tris, small, RAYCAST)
+
+
+def test_negative_and_anisotropic_cell_size(m2s, oracle):
+    verts, tris = synth.bumpy_torus(20, 12)
+    mn, mx = synth.padded_grid_box(verts)
+    # walk the x axis backwards: first cell at the max side, negative step
+    n = [14, 9, 21]
+    size = (mx - mn) / np.array(n, np.float32)
+    first = mn + 0.5 * size
+    first[0] = mx[0] - 0.5 * size[0]
+    size[0] = -size[0]
+    grid = m2s.Grid(first, size, n)
+    for sign in (RAYCAST, NORMAL):
+        assert_grid_matches(m2s, oracle, verts, tris, grid, sign)
+
+
+@pytest.mark.parametrize("offset", [[1000.0, -2000.0, 500.0], [0.0, 0.0, 30000.0]])
+def test_far_from_origin(m2s, oracle, offset):
+    verts, tris = synth.bumpy_torus(24, 16)
+    verts = (verts + np.array(offset, np.float32)).astype(np.float32)
+    mn, mx = synth.padded_grid_box(verts)
+    grid = m2s.Grid.from_bounding_box(mn, mx, [20, 18, 16])
+    for sign in (RAYCAST, NORMAL):
+        assert_grid_matches(m2s, oracle, verts, tris, grid, sign)
+    q = synth.splitmix64_points(3000, mn, mx, seed=5)
+    got = m2s.default_context().sdf(verts, tris, q, 3, 0)
+    want = oracle.generate_sdf(verts, tris, q, 3)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_tiny_scale(m2s, oracle):
+    # knight.glb is 0.1 tall: absolute slacks must not swamp a small mesh
+    verts, tris = synth.bumpy_torus(24, 16)
+    verts = (verts * np.float32(0.01)).astype(np.float32)
+    mn, mx = synth.padded_grid_box(verts)
+    grid = m2s.Grid.from_bounding_box(mn, mx, [24, 24, 12])
+    for sign in (RAYCAST, NORMAL):
+        assert_grid_matches(m2s, oracle, verts, tris, grid, sign)
+
+
+def test_large_triangles_many_rows(m2s, oracle):
+    # two triangles spanning the whole grid: every row is covered by one triangle (k_rows_big)
+    verts = np.array([[-1, -1, 0.13], [1, -1, 0.07], [1, 1, 0.21], [-1, 1, 0.02]], np.float32)
+    tris = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    grid = m2s.Grid.from_bounding_box([-0.9, -0.8, -0.5], [0.95, 0.85, 0.6], [40, 33, 24])
+    assert_grid_matches(m2s, oracle, verts, tris, grid, RAYCAST)
+    assert_grid_matches(m2s, oracle, verts, tris, grid, NORMAL)
+
+
+@pytest.mark.parametrize("n", [[1, 1, 1], [1, 7, 2], [3, 1, 65], [33, 2, 1]])
+def test_tiny_grids(m2s, oracle, n):
+    verts, tris = synth.bumpy_torus(12, 8)
+    mn, mx = synth.padded_grid_box(verts)
+    grid = m2s.Grid.from_bounding_box(mn, mx, n)
+    assert_grid_matches(m2s, oracle, verts, tris, grid, RAYCAST)
+    assert_grid_matches(m2s, oracle, verts, tris, grid, NORMAL)
+
+
+def test_single_triangle_and_two_triangles(m2s, oracle):
+    verts = np.array([[0.5, 1.5, 0.5], [1., 2., 3.], [1., 3., 7.], [2., 0., 0.]], np.float32)
+    for tris in (np.array([[0, 1, 2]], np.uint32), np.array([[0, 1, 2], [1, 2, 3]], np.uint32)):
+        grid = m2s.Grid.from_bounding_box([0., 0., 0.], [10., 10., 10.], [9, 10, 11])
+        assert_grid_matches(m2s, oracle, verts, tris, grid, RAYCAST)
+        assert_grid_matches(m2s, oracle, verts, tris, grid, NORMAL)
+
+
+def test_zero_cell_count_returns_empty(m2s):
+    verts, tris = synth.bumpy_torus(8, 6)
+    out = m2s.default_context().grid_sdf(verts, tris, m2s.Grid([0, 0, 0], [1, 1, 1], [0, 4, 4]), RAYCAST)
+    assert out.shape == (0,)
+
+
+def test_multi_device_context_matches_single(m2s):
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    verts, tris = synth.bumpy_torus(32, 20)
+    mn, mx = synth.padded_grid_box(verts)
+    grid = m2s.Grid.from_bounding_box(mn, mx, [37, 20, 24])
+    q = synth.splitmix64_points(10001, mn, mx)
+    one = m2s.default_context().grid_sdf(verts, tris, grid, RAYCAST)
+    qa = m2s.default_context().sdf(verts, tris, q, 3, 0)
+    with m2s.Context([0, 1]) as c2:
+        assert c2.device_count == 2
+        two = c2.grid_sdf(verts, tris, grid, RAYCAST)
+        qb = c2.sdf(verts, tris, q, 3, 0)
+    assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
+    assert np.array_equal(qa.view(np.uint32), qb.view(np.uint32))

@@ -63,8 +63,9 @@ wr = num("dram__bytes_write.sum") * scale.get(m["dram__bytes_write.sum"][1], 1)
 lines = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_lines.py"), rep, kern, "30"], capture_output=True, text=True).stdout
 with open(os.path.join(prof, f"{tag}_{kern.split('IL')[0]}_ncu_full.md"), "w") as f:
     f.write(f"# ncu --set full: {r[2][h.index('Kernel Name')][:160] if 'Kernel Name' in h else kern} ({tag})\n\n"
-            f"Captured with `ncu --set full --clock-control none --import-source on -k regex:k_grid_nearest` around "
-            f"`python bench.py` (workload C3). One launch. Numbers under a profiler are not bench values.\n\n| metric | value | unit |\n|---|---:|---|\n")
+            f"Captured with `ncu --set full --clock-control none --import-source on -k regex:k_grid_nearest -c 1` around "
+            f"`{os.environ.get('PROFILE_CMD', 'python bench.py')}` (workload C3, the whole 256^3 grid in one launch). "
+            f"Numbers under a profiler are not bench values.\n\n| metric | value | unit |\n|---|---:|---|\n")
     for k in keys:
         if k in m:
             f.write(f"| `{k}` | {m[k][0]} | {m[k][1]} |\n")

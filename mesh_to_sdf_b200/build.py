@@ -46,7 +46,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("M2S_NVCC_EXTRA", "").split()  # development: e.g. -DPKT_MIN_BLOCKS=5
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

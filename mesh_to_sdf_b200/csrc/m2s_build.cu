@@ -340,9 +340,9 @@ k_tri_permute(const float4* __restrict__ rec, const float4* __restrict__ tri_lo,
 constexpr uint32_t OBB_MAX_TRIS = 4096;
 
 __global__ void __launch_bounds__(256)
-k_search_nodes(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, int nleaf,
-               const float4* __restrict__ boxes, float4* __restrict__ nodes, const uint2* __restrict__ node_range,
-               const BuildStatus* __restrict__ st, float obb_bias) {
+k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__ tobb, uint32_t nt, uint32_t K,
+               int nleaf, const float4* __restrict__ boxes, float4* __restrict__ nodes,
+               const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st, float obb_bias) {
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (slot >= 2u * (uint32_t)(nleaf - 1)) return;
@@ -353,6 +353,15 @@ k_search_nodes(const float4* __restrict__ rec_sorted, uint32_t nt, uint32_t K, i
     uint32_t l0, l1;
     if (ref & LEAF_BIT) {
         l0 = l1 = ref & LEAF_INDEX_MASK;
+        if (K == 1u) {
+            // single-triangle leaf: its oriented box was already fitted by k_tri_permute
+            if (lane < 4) {
+                float4 v = tobb[4 * (size_t)l0 + lane];
+                if (lane == 0) v.w = __uint_as_float(ref | REF_OBB_BIT);
+                ch[lane] = v;
+            }
+            return;
+        }
     } else {
         const uint2 r = node_range[ref];
         l0 = r.x;
@@ -608,8 +617,8 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
                                                      d.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                      d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
         k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
-            d.rec_sorted.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.boxes.as<float4>(), d.nodes.as<float4>(),
-            d.node_range.as<uint2>(), st, d.obb_bias);
+            d.rec_sorted.as<float4>(), d.tobb.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.boxes.as<float4>(),
+            d.nodes.as<float4>(), d.node_range.as<uint2>(), st, d.obb_bias);
         d.launches += 3;
     }
     d.bvh.rec = d.rec_sorted.as<float4>();

@@ -463,6 +463,15 @@ k_grid_nearest(const Bvh bvh, const GridParams g, const float grid_mag, const Se
 // is dropped when its warp-min bound exceeds the warp-max radius. Triangles that survive a lane's
 // plane-disc pretest are queued per lane and evaluated with the exact arithmetic in batches.
 // ---------------------------------------------------------------------------------------------------
+// traversal counters of the packet walk (m2s_debug_stats) cost ~2 % of the kernel: only with -DM2S_STATS_BUILD
+#ifdef M2S_STATS_BUILD
+#define PKT_COUNT(x) ++(x)
+#else
+#define PKT_COUNT(x) ((void)0)
+#endif
+#ifndef PKT_MIN_BLOCKS
+#define PKT_MIN_BLOCKS 4
+#endif
 constexpr int PKT_STACK = 128;
 constexpr int PKT_TRI_BATCH = 16;   // per-lane queue of surviving triangles
 constexpr int PKT_FLUSH_AT = 6;     // flush all lanes' queues once any lane holds this many
@@ -569,7 +578,7 @@ __device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const 
 
     while (cur != TRAVERSAL_DONE) {
         if (!(cur & LEAF_BIT)) {
-            ++n_nodes;
+            PKT_COUNT(n_nodes);
             const float4* nd = bvh.nodes + NODE_F4 * (size_t)cur;  // warp-uniform address
             const float4 l0 = ldg4(nd), l1 = ldg4(nd + 1), l2 = ldg4(nd + 2), l3 = ldg4(nd + 3);
             const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
@@ -586,13 +595,13 @@ __device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const 
                     enqueue(hl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
                     bl = 0u;
                     queued = true;
-                    ++n_leaves;
+                    PKT_COUNT(n_leaves);
                 }
                 if ((rref & LEAF_BIT) && br) {
                     enqueue(hr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
                     br = 0u;
                     queued = true;
-                    ++n_leaves;
+                    PKT_COUNT(n_leaves);
                 }
                 if (queued) flush(false);
             }
@@ -617,7 +626,7 @@ __device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const 
                 cur = pop();
             }
         } else {
-            ++n_leaves;
+            PKT_COUNT(n_leaves);
             const uint32_t leaf = cur & LEAF_INDEX_MASK;
             const uint32_t dg = (cur & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u;
             const uint32_t b = leaf * bvh.leaf_size;
@@ -644,7 +653,7 @@ __device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const 
 // SEEDPASS: the same walk over the representative voxels of the stride^3 blocks (cdim = block counts),
 // storing the nearest triangle's slot instead of a distance.
 template <int MODE, bool RAYSIGN, bool SEEDPASS>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, PKT_MIN_BLOCKS)
 k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
                    const uint32_t* __restrict__ px, const uint32_t* __restrict__ py,
                    const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st,

@@ -44,7 +44,7 @@ struct GridArgs {
 m2s_status check_mesh(m2s_ctx* ctx, const void* verts, uint64_t nv, const void* tris, uint64_t nt) {
     if (nt > 0 && (!tris || !verts)) return fail(ctx, M2S_EINVAL, "null vertex / index pointer");
     if (nt > 0 && nv == 0) return fail(ctx, M2S_EINDEX, "triangles reference an empty vertex array");
-    if (nt >= (1ull << 29)) return fail(ctx, M2S_EINVAL, "more than 2^29 triangles");
+    if (nt >= (1ull << 30)) return fail(ctx, M2S_EINVAL, "more than 2^30 triangles");
     if (nv > 0xffffffffull) return fail(ctx, M2S_EINVAL, "more than 2^32 vertices");
     return M2S_OK;
 }

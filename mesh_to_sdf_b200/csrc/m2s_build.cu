@@ -357,7 +357,7 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
             // single-triangle leaf: its oriented box was already fitted by k_tri_permute
             if (lane < 4) {
                 float4 v = tobb[4 * (size_t)l0 + lane];
-                if (lane == 0) v.w = __uint_as_float(ref | REF_OBB_BIT);
+                if (lane == 0) v.w = __uint_as_float(ref);
                 ch[lane] = v;
             }
             return;
@@ -429,12 +429,15 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
     }
     if (lane == 0) {
         if (use_obb) {
-            write_obb(ch, origin, F, E, scene_mag(st), __uint_as_float(ref | REF_OBB_BIT));
+            write_obb(ch, origin, F, E, scene_mag(st), __uint_as_float(ref));
         } else {
-            ch[0] = c0;  // (min.xyz, ref)
-            ch[1] = c1;  // (max.xyz, 0)
-            ch[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ch[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // the padded axis-aligned box in the same format (identity frame): one code path, no
+            // per-child branch in the traversal
+            const float slack = 6.0e-6f * scene_mag(st);  // rounding of the centre and of the query side
+            ch[0] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(ref));
+            ch[1] = make_float4(1.f, 0.f, 0.f, fmaxf(c1.x - origin.x, origin.x - c0.x) + slack);
+            ch[2] = make_float4(0.f, 1.f, 0.f, fmaxf(c1.y - origin.y, origin.y - c0.y) + slack);
+            ch[3] = make_float4(0.f, 0.f, 1.f, fmaxf(c1.z - origin.z, origin.z - c0.z) + slack);
         }
     }
 }

@@ -21,9 +21,9 @@ namespace m2s {
 //   with u = unit normal, v along the longest edge: the cheap pretest in front of the exact arithmetic
 //   box node, 64 B = 4 x float4 (`boxes`): per child (min.xyz, bits(child ref)) (max.xyz, 0), padded
 //   -/+1e-4 like geo.rs:18-21. Written by the refit; read by the ray walks.
-//   search node, 128 B = 8 x float4 (`nodes`): per child 4 x float4, EITHER the same padded box
-//   (min.xyz, ref) (max.xyz, 0) 0 0 OR, when ref has REF_OBB_BIT, an oriented box fitted to the child's
-//   triangles (centre.xyz, ref) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew); see m2s_build.cu.
+//   search node, 128 B = 8 x float4 (`nodes`): per child 4 x float4 = an oriented box
+//   (centre.xyz, ref) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew), either fitted to the child's triangles or,
+//   where that is not smaller, the padded axis-aligned box written with the identity frame; m2s_build.cu.
 //   child ref: >= 0 internal node index; < 0 leaf: bit31 set, bit30 = "leaf holds a degenerate
 //   triangle" (slow path with the geo.rs:73-88 guards), bits 0..29 = leaf index. Leaf l owns the
 //   sorted triangles [l*K, min((l+1)*K, nt)).
@@ -31,10 +31,9 @@ namespace m2s {
 constexpr int NODE_F4 = 8;   // float4 per node
 constexpr int CHILD_F4 = 4;  // float4 per child slot
 constexpr int BOX_F4 = 4;    // float4 per box node
-constexpr uint32_t REF_OBB_BIT = 0x20000000u;  // search-node child slot holds an oriented box
 constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr uint32_t LEAF_DEGEN_BIT = 0x40000000u;
-constexpr uint32_t LEAF_INDEX_MASK = 0x1fffffffu;
+constexpr uint32_t LEAF_INDEX_MASK = 0x3fffffffu;
 constexpr uint32_t TRI_DEGEN_BIT = 0x80000000u;  // in tri_id_sorted
 
 // Written by the build kernels, read back once per call (64 B).

@@ -50,12 +50,11 @@ __device__ __forceinline__ float obb_dist2(const f3 p, const float4 c, const flo
     return a * a + b * b + g * g;
 }
 
-// lower bound for one child slot of a search node (4 x float4): oriented box or padded box, as the
-// build decided (REF_OBB_BIT; warp-uniform in the packet kernel)
+// lower bound for one child slot of a search node (4 x float4). Every slot is stored as an oriented box
+// (a padded axis-aligned box is the same record with the identity frame), so there is one code path.
 __device__ __forceinline__ float child_dist2(const f3 p, const float4 c0, const float4 c1, const float4 c2,
                                              const float4 c3) {
-    if (__float_as_uint(c0.w) & REF_OBB_BIT) return obb_dist2(p, c0, c1, c2, c3);
-    return box_dist2(p.x, p.y, p.z, c0.x, c0.y, c0.z, c1.x, c1.y, c1.z);
+    return obb_dist2(p, c0, c1, c2, c3);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -179,7 +178,7 @@ __device__ __forceinline__ void greedy_seed(const Bvh& bvh, const f3 p, Near<MOD
         const float4 l0 = ldg4(nd), l1 = ldg4(nd + 1), l2 = ldg4(nd + 2), l3 = ldg4(nd + 3);
         const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
         const float dl = child_dist2(p, l0, l1, l2, l3), dr = child_dist2(p, r0, r1, r2, r3);
-        cur = (dl <= dr ? __float_as_uint(l0.w) : __float_as_uint(r0.w)) & ~REF_OBB_BIT;
+        cur = (dl <= dr ? __float_as_uint(l0.w) : __float_as_uint(r0.w));
     }
     if (!(cur & LEAF_BIT)) return;
     const uint32_t leaf = cur & LEAF_INDEX_MASK;
@@ -210,7 +209,7 @@ __device__ __forceinline__ uint32_t node_step(const Bvh& bvh, uint32_t cur, cons
     const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
     const float dl = child_dist2(p, l0, l1, l2, l3);
     const float dr = child_dist2(p, r0, r1, r2, r3);
-    const uint32_t lref = __float_as_uint(l0.w) & ~REF_OBB_BIT, rref = __float_as_uint(r0.w) & ~REF_OBB_BIT;
+    const uint32_t lref = __float_as_uint(l0.w), rref = __float_as_uint(r0.w);
     const bool hl = dl <= s.bound2, hr = dr <= s.bound2;
     if (hl && hr) {
         const bool left_first = dl <= dr;
@@ -499,6 +498,7 @@ __device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const 
     const unsigned lt_mask = (1u << lane) - 1u;
     int overflow = 0;
     uint32_t n_nodes = 0, n_leaves = 0;
+    if (!valid) s.bound2 = -1.0f;  // never wants a child or a triangle; its state is never updated
     float max_b = warp_max_bound<MODE>(s, valid);
 
     // Exact-arithmetic work. NORMAL: per-lane queue (the compare_distances fold is order dependent and
@@ -584,9 +584,9 @@ __device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const 
             const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
             const float dl = child_dist2(p, l0, l1, l2, l3);
             const float dr = child_dist2(p, r0, r1, r2, r3);
-            const bool hl = valid && dl <= s.bound2, hr = valid && dr <= s.bound2;
+            const bool hl = dl <= s.bound2, hr = dr <= s.bound2;  // lanes without a voxel carry bound2 = -1
             unsigned bl = __ballot_sync(full, hl), br = __ballot_sync(full, hr);
-            const uint32_t lref = __float_as_uint(l0.w) & ~REF_OBB_BIT, rref = __float_as_uint(r0.w) & ~REF_OBB_BIT;
+            const uint32_t lref = __float_as_uint(l0.w), rref = __float_as_uint(r0.w);
             if (bvh.leaf_size == 1u) {
                 // single-triangle leaves: the child's box IS the triangle's box, so the lanes that want it
                 // queue the triangle right here and the leaf is never pushed / popped / re-tested
@@ -633,7 +633,7 @@ __device__ __forceinline__ void packet_search(const Bvh& bvh, const f3 p, const 
             const uint32_t e = min(bvh.nt, b + bvh.leaf_size);
             for (uint32_t j = b; j < e; ++j) {  // warp-uniform loop, uniform loads
                 const float4* tb = bvh.tobb + 4 * (size_t)j;
-                const bool want = valid && obb_dist2(p, ldg4(tb), ldg4(tb + 1), ldg4(tb + 2), ldg4(tb + 3)) <= s.bound2;
+                const bool want = obb_dist2(p, ldg4(tb), ldg4(tb + 1), ldg4(tb + 2), ldg4(tb + 3)) <= s.bound2;
                 enqueue(want, j | dg);
                 // UNSIGNED: at most 31 + 32 items are queued here, below PKT_QCAP. NORMAL: a lane's queue holds
                 // PKT_TRI_BATCH; drain it when a big leaf (K > batch - flush level) could overflow it

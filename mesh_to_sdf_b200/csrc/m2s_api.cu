@@ -69,8 +69,16 @@ m2s_status check_grid(m2s_ctx* ctx, const float first[3], const float size[3], c
 }
 
 // Enqueue: records + LBVH + (row parities) + nearest kernel for one slab, all on d.stream.
-// host_out != nullptr: the slab is computed in x-chunks and every finished chunk is copied to
-// host_out on the device's copy stream while the next chunk's kernel runs.
+// host-destined slabs of at least 4 Mi cells and 64 planes are computed as two half-slabs (see enqueue_grid)
+static bool grid_is_split(const Device& d, const GridParams& g, uint64_t nt, const float* host_out) {
+    const uint64_t slab_cells = (uint64_t)(g.x1 - g.x0) * g.ny * g.nz;
+    // device-resident output: measured slower when split (8.39 vs 8.11 ms; the seed pass is bound by the
+    // latency of its longest search, not by its size) — only the host path, which hides a copy, splits
+    return host_out != nullptr && nt > 0 && d.split_halves && d.seed_levels == 1 && slab_cells >= (4u << 20) && (g.x1 - g.x0) >= 64u;
+}
+
+// host_out != nullptr: every finished half is copied to host_out on the device's copy stream while the
+// next half's kernel runs.
 cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris,
                          uint64_t nt, const GridParams& g, int sign, float* d_out, bool clear_errors,
                          bool timed, float* host_out = nullptr) {
@@ -91,50 +99,50 @@ cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t
     if (raycast && (e = launch_grid_rows(d, g, &rb)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev[3], d.stream);
     const int mode = raycast ? MODE_UNSIGNED : MODE_NORMAL;
+    const RowBits* rbp = raycast ? &rb : nullptr;
     const uint32_t span = g.x1 - g.x0;
     const uint64_t plane = (uint64_t)g.ny * g.nz;
-    int chunks = host_out ? d.host_chunks : 1;
-    if (slab_cells < (4u << 20) || span < 32u * (uint32_t)chunks) chunks = 1;  // small slabs: one kernel, one copy
-    if (chunks > 8) chunks = 8;
-    if (chunks == 1) {
-        e = launch_grid_nearest(d, g, mode, raycast ? &rb : nullptr, d_out, timed ? d.ev[6] : nullptr);
+    d.last_split = false;
+    if (!grid_is_split(d, g, nt, host_out)) {
+        e = launch_grid_nearest(d, g, mode, rbp, d_out, timed ? d.ev[6] : nullptr);
         if (timed) cudaEventRecord(d.ev[4], d.stream);
         return e;
     }
-    // one seeding pass for the slab, then the distance kernel chunk by chunk. Every chunk's kernel is
-    // enqueued before the copies: a D2H into pageable memory blocks the calling thread, which must not
-    // delay the launch of the following chunks.
-    SeedLevel L{};
-    if ((e = launch_grid_seeds(d, g, &L)) != cudaSuccess) return e;
+    // Big slabs run as two half-slabs. The seed pass is latency bound (few, long, divergent searches) and
+    // the distance kernel issue bound, so the second half's seed pass runs on a high-priority side stream
+    // underneath the first half's distance kernel. With a host destination the first half's D2H overlaps
+    // the second half's kernel as well; only the last copy is exposed, hence the uneven cut.
+    d.last_split = true;
+    const uint32_t cut = g.x0 + (uint32_t)(span * 0.72) / 4u * 4u;
+    GridParams g1 = g, g2 = g;
+    g1.x1 = g1.xb = cut;
+    g2.x0 = g2.xa = cut;
+    float* out2 = d_out + (uint64_t)(cut - g.x0) * plane;
+    SeedLevel L1{}, L2{};
+    if ((e = cudaEventRecord(d.ev_fork, d.stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(d.aux_stream, d.ev_fork, 0)) != cudaSuccess) return e;
+    if ((e = launch_grid_seeds(d, g2, &L2, 1, d.aux_stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(d.ev_join, d.aux_stream)) != cudaSuccess) return e;
+    if ((e = launch_grid_seeds(d, g1, &L1, 0)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev[6], d.stream);
-    uint32_t cx0[8], cx1[8];
-    for (int c = 0; c < chunks; ++c) {
-        GridParams gc = g;
-        gc.xa = cx0[c] = g.x0 + (uint32_t)((uint64_t)span * c / chunks) / 4u * 4u;
-        gc.xb = cx1[c] = c + 1 == chunks ? g.x1 : g.x0 + (uint32_t)((uint64_t)span * (c + 1) / chunks) / 4u * 4u;
-        if (gc.xb > gc.xa && (e = launch_grid_final(d, gc, L, mode, raycast ? &rb : nullptr, d_out)) != cudaSuccess)
-            return e;
-        if ((e = cudaEventRecord(d.ev_chunk[c], d.stream)) != cudaSuccess) return e;
-    }
-    for (int c = 0; c < chunks; ++c) {
-        if (cx1[c] <= cx0[c]) continue;
-        if ((e = cudaStreamWaitEvent(d.copy_stream, d.ev_chunk[c], 0)) != cudaSuccess) return e;
-        const uint64_t off = (uint64_t)(cx0[c] - g.x0) * plane;
-        if ((e = cudaMemcpyAsync(host_out + off, d_out + off, (uint64_t)(cx1[c] - cx0[c]) * plane * 4,
-                                 cudaMemcpyDeviceToHost, d.copy_stream)) != cudaSuccess)
-            return e;
-    }
+    if ((e = launch_grid_final(d, g1, L1, mode, rbp, d_out)) != cudaSuccess) return e;
+    if (timed) cudaEventRecord(d.ev_half[0], d.stream);
+    if (host_out && (e = cudaEventRecord(d.ev_chunk[0], d.stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(d.stream, d.ev_join, 0)) != cudaSuccess) return e;
+    if (timed) cudaEventRecord(d.ev_half[1], d.stream);
+    if ((e = launch_grid_final(d, g2, L2, mode, rbp, out2)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev[4], d.stream);
+    if (!host_out) return cudaSuccess;
+    // both kernels are enqueued before the copies: a D2H into pageable memory blocks the calling thread
+    if ((e = cudaEventRecord(d.ev_chunk[1], d.stream)) != cudaSuccess) return e;
+    const uint64_t n1 = (uint64_t)(cut - g.x0) * plane, n2 = (uint64_t)(g.x1 - cut) * plane;
+    if ((e = cudaStreamWaitEvent(d.copy_stream, d.ev_chunk[0], 0)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(host_out, d_out, n1 * 4, cudaMemcpyDeviceToHost, d.copy_stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(d.copy_stream, d.ev_chunk[1], 0)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(host_out + n1, out2, n2 * 4, cudaMemcpyDeviceToHost, d.copy_stream)) != cudaSuccess) return e;
     // the caller's stream continues only after the last chunk has landed
     if ((e = cudaEventRecord(d.ev_copied, d.copy_stream)) != cudaSuccess) return e;
     return cudaStreamWaitEvent(d.stream, d.ev_copied, 0);
-}
-
-// true when enqueue_grid(host_out) already copied the slab to the host
-static bool grid_copied_by_chunks(const Device& d, const GridParams& g, uint64_t nt) {
-    const uint64_t slab_cells = (uint64_t)(g.x1 - g.x0) * g.ny * g.nz;
-    int chunks = d.host_chunks > 8 ? 8 : d.host_chunks;
-    return nt > 0 && chunks > 1 && slab_cells >= (4u << 20) && (g.x1 - g.x0) >= 32u * (uint32_t)chunks;
 }
 
 struct PointPlan {
@@ -197,7 +205,14 @@ void collect_timings(m2s_ctx* ctx, Device& d) {
     cudaEventElapsedTime(&t.build_ms, d.ev[1], d.ev[2]);
     cudaEventElapsedTime(&t.sign_ms, d.ev[2], d.ev[3]);
     cudaEventElapsedTime(&t.seed_ms, d.ev[3], d.ev[6]);
-    cudaEventElapsedTime(&t.dist_ms, d.ev[6], d.ev[4]);
+    if (d.last_split) {  // two launches of the distance kernel; the second half's seed pass ran beside the first
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, d.ev[6], d.ev_half[0]);
+        cudaEventElapsedTime(&b, d.ev_half[1], d.ev[4]);
+        t.dist_ms = a + b;
+    } else {
+        cudaEventElapsedTime(&t.dist_ms, d.ev[6], d.ev[4]);
+    }
     cudaEventElapsedTime(&t.d2h_ms, d.ev[4], d.ev[5]);
     cudaEventElapsedTime(&t.total_ms, d.ev[0], d.ev[5]);
     ctx->timings = t;
@@ -243,7 +258,15 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&d.ev_chunk[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_copied, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
-        if (const char* c = std::getenv("M2S_HOST_CHUNKS")) d.host_chunks = std::max(1, std::min(8, std::atoi(c)));
+        if (e == cudaSuccess) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+            e = cudaStreamCreateWithPriority(&d.aux_stream, cudaStreamNonBlocking, hi);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreate(&d.ev_half[k]);
+        if (const char* c = std::getenv("M2S_SPLIT")) d.split_halves = std::atoi(c) != 0;
         if (e != cudaSuccess) {
             cudaGetLastError();
             m2s_destroy(ctx);
@@ -294,6 +317,11 @@ void m2s_destroy(m2s_ctx* ctx) {
         for (int k = 0; k < 8; ++k)
             if (d.ev_chunk[k]) cudaEventDestroy(d.ev_chunk[k]);
         if (d.ev_copied) cudaEventDestroy(d.ev_copied);
+        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.ev_join) cudaEventDestroy(d.ev_join);
+        for (int k = 0; k < 2; ++k)
+            if (d.ev_half[k]) cudaEventDestroy(d.ev_half[k]);
+        if (d.aux_stream) cudaStreamDestroy(d.aux_stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
     }
@@ -361,7 +389,7 @@ static m2s_status grid_host(m2s_ctx* ctx, const float* verts_xyz, uint64_t nv, c
         float* host_dst = out + (uint64_t)(g.x0 - xa) * plane;
         CU(ctx, enqueue_grid(ctx, d, d.verts.as<float>(), nv, d.tris.as<uint32_t>(), nt, g, sign_method,
                              d.out.as<float>(), true, timed, host_dst));
-        if (!grid_copied_by_chunks(d, g, nt))
+        if (!grid_is_split(d, g, nt, host_dst))
             CU(ctx, cudaMemcpyAsync(host_dst, d.out.p, cells * 4, cudaMemcpyDeviceToHost, d.stream));
         CU(ctx, cudaMemcpyAsync(d.h_status, d.status.p, sizeof(BuildStatus), cudaMemcpyDeviceToHost, d.stream));
         if (timed) cudaEventRecord(d.ev[5], d.stream);

@@ -122,10 +122,13 @@ struct Device {
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
     BuildStatus* h_status = nullptr;  // pinned
     cudaEvent_t ev[8] = {};
+    cudaStream_t aux_stream = nullptr;   // high priority: the second half's seed pass hides under the first half's kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_half[2] = {};
+    bool split_halves = true;            // M2S_SPLIT=0: one seed pass + one distance launch per slab
+    bool last_split = false;
     cudaStream_t copy_stream = nullptr;  // D2H of finished x-chunks overlaps the next chunk's kernel
     cudaEvent_t ev_chunk[8] = {};
     cudaEvent_t ev_copied = nullptr;
-    int host_chunks = 2;                 // M2S_HOST_CHUNKS
 
     Bvh bvh{};
 };
@@ -143,7 +146,7 @@ struct SeedLevel {
     uint32_t px, py, pz;     // parent level dims
     uint32_t pstride;        // parent level stride in voxels
 };
-cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* L);
+cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* L, int slot = 0, cudaStream_t stream = nullptr);
 cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L, int mode, const RowBits* rb,
                               float* d_out);
 cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,

@@ -1038,8 +1038,9 @@ static float grid_magnitude(const GridParams& g) {
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 // Coarse seeding pass(es) over the whole slab [g.x0, g.x1).
-cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* out) {
-    cudaStream_t s = d.stream;
+// slot selects the seed buffer (two half-slabs may be in flight); stream defaults to the device's.
+cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* out, int slot, cudaStream_t stream) {
+    cudaStream_t s = stream ? stream : d.stream;
     const uint32_t sx = g.x1 - g.x0;
     const float mag = grid_magnitude(g);
     BuildStatus* st = d.status.as<BuildStatus>();
@@ -1051,7 +1052,7 @@ cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* out) {
             uint32_t stride = 1;
             for (int k = 0; k < lev; ++k) stride *= d.seed_stride;
             const uint32_t cx = cdiv(sx, stride), cy = cdiv(g.ny, stride), cz = cdiv(g.nz, stride);
-            DevBuf& buf = d.seeds[lev - 1];
+            DevBuf& buf = d.seeds[(lev - 1 + slot) & 1];
             CK(buf.ensure((size_t)cx * cy * cz * 4));
             const unsigned nb = cdiv(cx, BX) * cdiv(cy, BY) * cdiv(cz, BZ);
             if (d.packet && d.seed_packet)

@@ -392,7 +392,10 @@ __device__ __forceinline__ uint32_t parent_seed(const SeedLevel& L, uint32_t xr,
 
 // Coarse level: one thread per S^3 block of the slab; searches the block's representative voxel and
 // stores the nearest triangle's slot.
-__global__ void __launch_bounds__(256)
+#ifndef SEED_MIN_BLOCKS
+#define SEED_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, SEED_MIN_BLOCKS)
 k_grid_seed(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t stride, const uint32_t cx,
             const uint32_t cy, const uint32_t cz, const SeedLevel L, uint32_t* __restrict__ seeds,
             BuildStatus* __restrict__ st) {

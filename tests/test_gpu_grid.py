@@ -108,3 +108,30 @@ def test_slab_invariance_device_entry(m2s, oracle):
             c.synchronize()
             parts.append(out.cpu().numpy())
     assert np.array_equal(np.concatenate(parts).view(np.uint32), whole.view(np.uint32))
+
+
+def test_device_entry_defers_data_errors(m2s):
+    # device-buffer calls only enqueue; a bad index surfaces at the next m2s_synchronize (M2S_EINDEX)
+    torch = pytest.importorskip("torch")
+    verts, tris = synth.bumpy_torus(8, 6)
+    bad = tris.copy()
+    bad[5, 1] = 10_000
+    grid = _grid_for(m2s, verts, [8, 8, 8])
+    dv = torch.from_numpy(verts).cuda()
+    out = torch.empty(512, dtype=torch.float32, device="cuda")
+    with m2s.Context() as c:
+        dt = torch.from_numpy(bad.view(np.int32)).cuda()
+        torch.cuda.synchronize()
+        c.grid_sdf_device(dv.data_ptr(), len(verts), dt.data_ptr(), len(bad), grid, RAYCAST, 0, 8, out.data_ptr())
+        with pytest.raises(m2s.M2SError) as e:
+            c.synchronize()
+        assert e.value.status == m2s.M2S_EINDEX
+        # the flags were cleared: a good call afterwards synchronises cleanly and is correct
+        dt = torch.from_numpy(tris.view(np.int32)).cuda()
+        torch.cuda.synchronize()
+        c.grid_sdf_device(dv.data_ptr(), len(verts), dt.data_ptr(), len(tris), grid, RAYCAST, 0, 8, out.data_ptr())
+        c.synchronize()
+        want = c.grid_sdf(verts, tris, grid, RAYCAST)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        t = c.timings()
+        assert t["total_ms"] > 0 and c.launch_count > 0

@@ -119,16 +119,19 @@ cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t
     g2.x0 = g2.xa = cut;
     float* out2 = d_out + (uint64_t)(cut - g.x0) * plane;
     SeedLevel L1{}, L2{};
-    if ((e = cudaEventRecord(d.ev_fork, d.stream)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(d.aux_stream, d.ev_fork, 0)) != cudaSuccess) return e;
-    if ((e = launch_grid_seeds(d, g2, &L2, 1, d.aux_stream)) != cudaSuccess) return e;
-    if ((e = cudaEventRecord(d.ev_join, d.aux_stream)) != cudaSuccess) return e;
-    if ((e = launch_grid_seeds(d, g1, &L1, 0)) != cudaSuccess) return e;
+    const bool coarse_pass = !grid_uses_neighbour_seeds(d, mode);
+    if (coarse_pass) {
+        if ((e = cudaEventRecord(d.ev_fork, d.stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(d.aux_stream, d.ev_fork, 0)) != cudaSuccess) return e;
+        if ((e = launch_grid_seeds(d, g2, &L2, 1, d.aux_stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(d.ev_join, d.aux_stream)) != cudaSuccess) return e;
+        if ((e = launch_grid_seeds(d, g1, &L1, 0)) != cudaSuccess) return e;
+    }
     if (timed) cudaEventRecord(d.ev[6], d.stream);
     if ((e = launch_grid_final(d, g1, L1, mode, rbp, d_out)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev_half[0], d.stream);
     if (host_out && (e = cudaEventRecord(d.ev_chunk[0], d.stream)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(d.stream, d.ev_join, 0)) != cudaSuccess) return e;
+    if (coarse_pass && (e = cudaStreamWaitEvent(d.stream, d.ev_join, 0)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev_half[1], d.stream);
     if ((e = launch_grid_final(d, g2, L2, mode, rbp, out2)) != cudaSuccess) return e;
     if (timed) cudaEventRecord(d.ev[4], d.stream);
@@ -267,6 +270,7 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming);
         for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreate(&d.ev_half[k]);
         if (const char* c = std::getenv("M2S_SPLIT")) d.split_halves = std::atoi(c) != 0;
+        if (const char* c = std::getenv("M2S_NSEED")) { d.neighbour_seeds = std::atoi(c) != 0; d.neighbour_and_coarse = std::atoi(c) == 2; }
         if (e != cudaSuccess) {
             cudaGetLastError();
             m2s_destroy(ctx);
@@ -309,7 +313,7 @@ void m2s_destroy(m2s_ctx* ctx) {
                           &d.keys_out, &d.vals_in, &d.vals_out, &d.cub_tmp, &d.tri_id_sorted, &d.nodes,
                           &d.leaf_parent, &d.node_parent, &d.node_flag, &d.status, &d.rows[0], &d.rows[1],
                           &d.rows[2], &d.big_list, &d.big_count, &d.queries, &d.q_sorted, &d.q_perm,
-                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.tobb, &d.boxes};
+                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.tobb, &d.boxes, &d.tile_slot};
         for (DevBuf* b : bufs) b->release();
         if (d.h_status) cudaFreeHost(d.h_status);
         for (int k = 0; k < 8; ++k)
@@ -356,6 +360,7 @@ m2s_status m2s_debug_stats(m2s_ctx* ctx, uint64_t out[4]) {
     CU(ctx, cudaSetDevice(d.ordinal));
     CU(ctx, cudaStreamSynchronize(d.stream));
     CU(ctx, cudaMemcpy(out, d.stats.p, 32, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(out + 3, (char*)d.stats.p + 32, 8, cudaMemcpyDeviceToHost));  // [3] = tiles that found no neighbour seed
     return M2S_OK;
 }
 

@@ -116,6 +116,9 @@ struct Device {
     float obb_bias = 1.0f;     // oriented box kept when its volume <= obb_bias * padded box volume (M2S_OBB_BIAS)
     bool seed_packet = false;  // M2S_SEED_PACKET=0: per-lane traversal for the seed pass
     bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
+    DevBuf tile_slot;         // per-tile nearest-triangle slots published by the distance kernel
+    bool neighbour_and_coarse = false;  // experiment (M2S_NSEED=2): coarse pass as the fallback of neighbour seeds
+    bool neighbour_seeds = true;  // M2S_NSEED=0: separate coarse seed pass for every grid
     DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
     uint32_t seed_stride = 4;  // voxels per seed block edge (M2S_SEED_STRIDE)
     int seed_levels = 1;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
@@ -146,6 +149,7 @@ struct SeedLevel {
     uint32_t px, py, pz;     // parent level dims
     uint32_t pstride;        // parent level stride in voxels
 };
+bool grid_uses_neighbour_seeds(const Device& d, int mode);
 cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* L, int slot = 0, cudaStream_t stream = nullptr);
 cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L, int mode, const RowBits* rb,
                               float* d_out);

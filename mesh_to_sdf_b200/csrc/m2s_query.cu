@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(256, PKT_MIN_BLOCKS)
 k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, const SeedLevel L,
                    const uint32_t* __restrict__ px, const uint32_t* __restrict__ py,
                    const uint32_t* __restrict__ pz, float* __restrict__ out, BuildStatus* __restrict__ st,
-                   const uint32_t stride, const uint3 cdim) {
+                   const uint32_t stride, const uint3 cdim, uint32_t* tile_slot) {
     __shared__ uint2 s_stack[8][PKT_STACK];
     __shared__ uint2 s_queue[8][MODE == MODE_UNSIGNED ? PKT_QCAP : 1];       // (triangle slot | degen, owner lane)
     __shared__ unsigned long long s_best[8][MODE == MODE_UNSIGNED ? 32 : 1];  // per owner: (d2 bits << 32) | slot
@@ -686,14 +686,43 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const f3 p = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
     Near<MODE> s;
     s.init(4.0e-6f * fmaxf(scene_magnitude(st), grid_mag));
+    // Seed = one known-near triangle that gives the search a tight radius from its first node on.
+    //   tile_slot (Raycast / unsigned grids): the nearest triangle of the tile four (two) cells back in x,
+    //     published by the warp that computed it (four representatives per tile, one per (y, z) quadrant).
+    //     Bricks are dispatched in x-major order and ~600 are resident, so the brick 1024 dispatches back
+    //     has practically always finished; if its entry is still empty (first brick plane of a launch, or
+    //     a straggler) the lane falls back to a greedy descent. The seed only initialises the radius - the
+    //     result is the same exact minimum either way, so this benign race cannot change a bit of output.
+    //   L.parent: slots from a separate coarse pass (Normal sign: its compare_distances fold depends on
+    //     the visiting order, so it keeps the deterministic seed source).
+    uint32_t nseed = 0xffffffffu;
+    if (!SEEDPASS && tile_slot) {
+        const uint32_t plane_bricks = ((g.ny + BY - 1) / BY) * ((g.nz + BZ - 1) / BZ);
+        const uint32_t lane = threadIdx.x & 31u, quad = ((lane >> 3) & 1u) * 2u + ((lane >> 1) & 1u);
+        if (blockIdx.x >= plane_bricks)
+            nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - plane_bricks) * 8u + (warp | 4u)) * 4u + quad);
+    }
+#ifdef M2S_STATS_BUILD
+    if (!SEEDPASS && tile_slot && bvh.stats && (threadIdx.x & 31u) == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 4, 1ull);
+#endif
     if (valid) {
-        if (L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
+        if (nseed != 0xffffffffu) seed_tri<MODE>(bvh, nseed, p, s);
+        else if (L.parent) seed_tri<MODE>(bvh, parent_seed(L, xr, y, z), p, s);
         else greedy_seed<MODE>(bvh, p, s);
     }
     PacketCounters ctr;
     packet_search<MODE>(bvh, p, valid, s, s_stack[warp], s_queue[warp], s_best[warp], &ctr);
     const int overflow = ctr.overflow;
     const uint32_t n_nodes = ctr.nodes, n_leaves = ctr.leaves;
+    if (!SEEDPASS && tile_slot) {
+        // publish this tile's representatives: the x-far lanes next to the centre of each (y, z) quadrant
+        // (lanes 21, 22, 25, 26 = lx 1, ly 1|2, lz 1|2); an entry stays empty if that lane has no voxel
+        const uint32_t lane = threadIdx.x & 31u;
+        if (valid && (lane == 21u || lane == 22u || lane == 25u || lane == 26u)) {
+            const uint32_t quad = ((lane >> 3) & 1u) * 2u + ((lane >> 1) & 1u);
+            __stcg(tile_slot + ((size_t)blockIdx.x * 8u + warp) * 4u + quad, s.slot);
+        }
+    }
 
     if (SEEDPASS) {
         if (valid) reinterpret_cast<uint32_t*>(out)[((size_t)bxs * cdim.y + bys) * cdim.z + bzs] = s.slot;
@@ -1040,6 +1069,12 @@ static float grid_magnitude(const GridParams& g) {
 
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+// Raycast / unsigned grids take their seeds from finished neighbour tiles inside the distance kernel
+// (k_grid_nearest_pkt); everything else runs the separate coarse pass below.
+bool grid_uses_neighbour_seeds(const Device& d, int mode) {
+    return d.packet && d.neighbour_seeds && mode != MODE_NORMAL;
+}
+
 // Coarse seeding pass(es) over the whole slab [g.x0, g.x1).
 // slot selects the seed buffer (two half-slabs may be in flight); stream defaults to the device's.
 cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* out, int slot, cudaStream_t stream) {
@@ -1060,7 +1095,8 @@ cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* out, in
             const unsigned nb = cdiv(cx, BX) * cdiv(cy, BY) * cdiv(cz, BZ);
             if (d.packet && d.seed_packet)
                 k_grid_nearest_pkt<MODE_UNSIGNED, false, true><<<nb, 256, 0, s>>>(
-                    d.bvh, g, mag, L, nullptr, nullptr, nullptr, buf.as<float>(), st, stride, make_uint3(cx, cy, cz));
+                    d.bvh, g, mag, L, nullptr, nullptr, nullptr, buf.as<float>(), st, stride, make_uint3(cx, cy, cz),
+                    nullptr);
             else
                 k_grid_seed<<<nb, 256, 0, s>>>(d.bvh, g, mag, stride, cx, cy, cz, L, buf.as<uint32_t>(), st);
             d.launches++;
@@ -1082,15 +1118,21 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
     BuildStatus* st = d.status.as<BuildStatus>();
     const unsigned nb = (unsigned)nblocks;
     if (d.packet) {
+        uint32_t* tile_slot = nullptr;
+        if (grid_uses_neighbour_seeds(d, mode)) {
+            CK(d.tile_slot.ensure((size_t)nb * 8 * 4 * 4));
+            CK(cudaMemsetAsync(d.tile_slot.p, 0xff, (size_t)nb * 8 * 4 * 4, s));
+            tile_slot = d.tile_slot.as<uint32_t>();
+        }
         if (rb) {
             k_grid_nearest_pkt<MODE_UNSIGNED, true, false><<<nb, 256, 0, s>>>(
-                d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2], d_out, st, 1u, make_uint3(0, 0, 0));
+                d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2], d_out, st, 1u, make_uint3(0, 0, 0), tile_slot);
         } else if (mode == MODE_NORMAL) {
             k_grid_nearest_pkt<MODE_NORMAL, false, false><<<nb, 256, 0, s>>>(
-                d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st, 1u, make_uint3(0, 0, 0));
+                d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st, 1u, make_uint3(0, 0, 0), nullptr);
         } else {
             k_grid_nearest_pkt<MODE_UNSIGNED, false, false><<<nb, 256, 0, s>>>(
-                d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st, 1u, make_uint3(0, 0, 0));
+                d.bvh, g, mag, L, nullptr, nullptr, nullptr, d_out, st, 1u, make_uint3(0, 0, 0), tile_slot);
         }
     } else if (rb) {
         k_grid_nearest<MODE_UNSIGNED, true><<<nb, 256, 0, s>>>(d.bvh, g, mag, L, rb->bits[0], rb->bits[1], rb->bits[2],
@@ -1107,7 +1149,7 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
 cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,
                                 cudaEvent_t after_seeds) {
     SeedLevel L{};
-    CK(launch_grid_seeds(d, g, &L));
+    if (!grid_uses_neighbour_seeds(d, mode) || d.neighbour_and_coarse) CK(launch_grid_seeds(d, g, &L));
     if (after_seeds) cudaEventRecord(after_seeds, d.stream);
     return launch_grid_final(d, g, L, mode, rb, d_out);
 }

@@ -278,6 +278,7 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         }
         std::memset(d.h_status, 0, sizeof(BuildStatus));
         if (const char* e = std::getenv("M2S_PACKET")) d.packet = std::atoi(e) != 0;
+        if (const char* e = std::getenv("M2S_PAIR")) d.pair = std::max(0, std::min(3, std::atoi(e)));
         if (const char* e = std::getenv("M2S_SEED_PACKET")) d.seed_packet = std::atoi(e) != 0;
         if (const char* e = std::getenv("M2S_OBB_BIAS")) d.obb_bias = (float)std::atof(e);
         if (const char* e = std::getenv("M2S_STATS")) { d.want_stats = std::atoi(e) != 0; d.stats_mode = std::atoi(e); }
@@ -310,7 +311,7 @@ void m2s_destroy(m2s_ctx* ctx) {
         cudaSetDevice(d.ordinal);
         if (d.stream || !d.own_stream) cudaStreamSynchronize(d.stream);
         DevBuf* bufs[] = {&d.verts, &d.tris, &d.rec_orig, &d.rec_sorted, &d.tri_lo, &d.tri_hi, &d.keys_in,
-                          &d.keys_out, &d.vals_in, &d.vals_out, &d.cub_tmp, &d.tri_id_sorted, &d.nodes,
+                          &d.keys_out, &d.vals_in, &d.vals_out, &d.cub_tmp, &d.tri_id_sorted, &d.nodes, &d.nodes_il,
                           &d.leaf_parent, &d.node_parent, &d.node_flag, &d.status, &d.rows[0], &d.rows[1],
                           &d.rows[2], &d.big_list, &d.big_count, &d.queries, &d.q_sorted, &d.q_perm,
                           &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.tobb, &d.boxes, &d.tile_slot};

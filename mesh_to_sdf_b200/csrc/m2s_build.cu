@@ -442,6 +442,25 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
     }
 }
 
+// K4e: the same search nodes with the two children interleaved component by component, so that one
+// packed-fp32 instruction (FFMA2 / FMUL2 / FADD2, sm_100a) evaluates the left child in its low half and
+// the right child in its high half:
+//   q0 = (cL.x, cR.x, cL.y, cR.y)  q1 = (cL.z, cR.z, refL, refR)
+//   q2 = (uL.x, uR.x, uL.y, uR.y)  q3 = (uL.z, uR.z, euL, euR)     q4, q5: v     q6, q7: w
+__global__ void __launch_bounds__(256)
+k_nodes_interleave(const float4* __restrict__ nodes, uint32_t n_nodes, float4* __restrict__ il) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4* nd = nodes + NODE_F4 * (size_t)i;
+    float4* o = il + NODE_F4 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 l = nd[k], r = nd[CHILD_F4 + k];
+        o[2 * k] = make_float4(l.x, r.x, l.y, r.y);
+        o[2 * k + 1] = make_float4(l.z, r.z, l.w, r.w);
+    }
+}
+
 // Karras 2012 delta over the leaf keys (leaf l's key = key of its first sorted triangle).
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, int i, int j) {
     if (j < 0 || j >= nleaf) return -1;
@@ -584,6 +603,7 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     CK(d.vals_out.ensure(nt * 4));
     CK(d.tri_id_sorted.ensure(nt * 4));
     CK(d.nodes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * NODE_F4 * 16));
+    CK(d.nodes_il.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * NODE_F4 * 16));
     CK(d.boxes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * BOX_F4 * 16));
     CK(d.node_range.ensure((size_t)nleaf * 8));
     CK(d.tobb.ensure(nt * 64));
@@ -622,13 +642,16 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
         k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
             d.rec_sorted.as<float4>(), d.tobb.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.boxes.as<float4>(),
             d.nodes.as<float4>(), d.node_range.as<uint2>(), st, d.obb_bias);
-        d.launches += 3;
+        k_nodes_interleave<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.nodes.as<float4>(), nleaf - 1,
+                                                                    d.nodes_il.as<float4>());
+        d.launches += 4;
     }
     d.bvh.rec = d.rec_sorted.as<float4>();
     d.bvh.tobb = d.tobb.as<float4>();
     d.bvh.boxes = d.boxes.as<float4>();
     d.bvh.tri_id = d.tri_id_sorted.as<uint32_t>();
     d.bvh.nodes = d.nodes.as<float4>();
+    d.bvh.nodes_il = d.nodes_il.as<float4>();
     d.bvh.nleaf = nleaf;
     if (d.want_stats) {
         CK(d.stats.ensure(64));

@@ -56,6 +56,7 @@ struct Bvh {
     const float4* boxes;      // box nodes (ray walks)
     const uint32_t* tri_id;   // leaf-order -> original triangle id (| TRI_DEGEN_BIT)
     const float4* nodes;      // internal nodes
+    const float4* nodes_il;   // the same nodes, children interleaved for packed-fp32 tests (m2s_build.cu, K4e)
     uint32_t nt;              // triangles
     uint32_t nleaf;           // leaves
     uint32_t leaf_size;       // K
@@ -108,7 +109,7 @@ struct Device {
     // mesh + LBVH
     DevBuf verts, tris;  // staging for the host entry points
     DevBuf rec_orig, rec_sorted, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
-    DevBuf tri_id_sorted, nodes, leaf_parent, node_parent, node_flag, node_range, tobb, boxes, status;
+    DevBuf tri_id_sorted, nodes, nodes_il, leaf_parent, node_parent, node_flag, node_range, tobb, boxes, status;
     DevBuf rows[3], big_list, big_count;
     DevBuf stats;             // traversal counters, only with M2S_STATS=1
     bool want_stats = false;
@@ -116,6 +117,8 @@ struct Device {
     float obb_bias = 1.0f;     // oriented box kept when its volume <= obb_bias * padded box volume (M2S_OBB_BIAS)
     bool seed_packet = false;  // M2S_SEED_PACKET=0: per-lane traversal for the seed pass
     bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
+    int pair = 1;              // M2S_PAIR: 0 = one voxel per lane (k_grid_nearest_pkt); 1 = two voxels per lane, tile
+                               // shape picked from the cell sizes; 2 / 3 force the x-extended / z-extended tile
     DevBuf tile_slot;         // per-tile nearest-triangle slots published by the distance kernel
     bool neighbour_and_coarse = false;  // experiment (M2S_NSEED=2): coarse pass as the fallback of neighbour seeds
     bool neighbour_seeds = true;  // M2S_NSEED=0: separate coarse seed pass for every grid

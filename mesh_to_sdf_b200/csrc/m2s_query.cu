@@ -749,6 +749,278 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Pair kernel: the packet walk with TWO voxels per lane and both children of a node evaluated by one
+// packed-fp32 instruction stream (FFMA2 / FMUL2, sm_100a). Default for Raycast / unsigned grids.
+//
+// ncu on k_grid_nearest_pkt (profiles/r1e) showed two co-limiters at ~76 %: issue slots and the L1 -> register
+// write-back of the warp-uniform node loads (8 x LDG.128 broadcast = 4 KB of register writes per node visit).
+// Here a warp owns 64 voxels - a 4x4x4 tile (EXT = 0: the lane's second voxel is two cells further in x) or a
+// 2x4x8 tile (EXT = 2: the next cell in z; picked when the cells are flat in z) - so one node load and one
+// round of votes / stack traffic serve twice the voxels, and the bound arithmetic shrinks from 4 x 22 scalar
+// instructions to 45 per (2 voxels x 2 children):
+//   * the node is stored with its children interleaved (Bvh::nodes_il), the low half of every packed
+//     operation is the left child and the high half the right child;
+//   * the second voxel differs from the first by a constant step d along one grid axis, so its projections
+//     are one FFMA2 each: (pB - c).u = (pA - c).u + d * u[axis].
+// Only the pruning bounds are computed this way (plain fp32, conservative: the extents carry the slack);
+// results still come from the reference-order un-fused arithmetic of exact_d2, so the output is the same
+// exact minimum, bit for bit. Requires single-triangle leaves (K = 1) and at least one internal node.
+// ---------------------------------------------------------------------------------------------------
+#ifndef PK2_MIN_BLOCKS
+#define PK2_MIN_BLOCKS 5
+#endif
+constexpr int PK2_QCAP = 160;  // < 32 items left over + at most 2 leaves x 64 voxels appended by one node
+
+__device__ __forceinline__ float2 f2lo(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 f2hi(const float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 excess2(const float2 t, const float2 e) {  // max(|t| - e, 0) per half
+    return make_float2(fmaxf(fabsf(t.x) - e.x, 0.0f), fmaxf(fabsf(t.y) - e.y, 0.0f));
+}
+__device__ __forceinline__ float2 sumsq2(const float2 a, const float2 b, const float2 c) {
+    return __ffma2_rn(c, c, __ffma2_rn(b, b, __fmul2_rn(a, a)));
+}
+__device__ __forceinline__ unsigned long long pack_best(float d2, uint32_t slot) {
+    return ((unsigned long long)__float_as_uint(d2) << 32) | slot;
+}
+
+template <bool RAYSIGN, int EXT>
+__global__ void __launch_bounds__(128, PK2_MIN_BLOCKS)
+k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
+                   const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
+                   BuildStatus* __restrict__ st, uint32_t* tile_slot) {
+    __shared__ uint2 s_stack[4][PKT_STACK];
+    __shared__ uint2 s_queue[4][PK2_QCAP];          // (triangle slot | degen, owner voxel 0..63)
+    __shared__ unsigned long long s_best[4][64];    // per owner voxel: (d2 bits << 32) | slot
+    const unsigned full = 0xffffffffu;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint2* const stack = s_stack[warp];
+    uint2* const queue = s_queue[warp];
+    unsigned long long* const best = s_best[warp];
+
+    // brick numbering as in brick_coords (z fastest): consecutive blocks share tree nodes in L1 / L2
+    const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZ - 1) / BZ;
+    uint32_t bid = blockIdx.x;
+    const uint32_t bz = bid % nbz;
+    bid /= nbz;
+    const uint32_t by = bid % nby, bx = bid / nby;
+    uint32_t xr, y, z;  // voxel A of this lane (x relative to the slab start)
+    if (EXT == 0) {     // warp (wy, wz), lane (lx, ly, lz): tile 4 x 4 x 4, voxel B = A + 2 cells in x
+        xr = bx * BX + (lane >> 4);
+        y = by * BY + ((warp >> 1) & 1u) * 4u + ((lane >> 2) & 3u);
+        z = bz * BZ + (warp & 1u) * 4u + (lane & 3u);
+    } else {            // warp (wx, wy), lane (lx, ly, lz'): tile 2 x 4 x 8, voxel B = A + 1 cell in z
+        xr = bx * BX + ((warp >> 1) & 1u) * 2u + (lane >> 4);
+        y = by * BY + (warp & 1u) * 4u + ((lane >> 2) & 3u);
+        z = bz * BZ + (lane & 3u) * 2u;
+    }
+    xr += g.xa - g.x0;  // this launch covers planes [xa, xb) of the slab
+    const uint32_t x = g.x0 + xr;
+    const uint32_t xB = EXT == 0 ? x + 2u : x, zB = EXT == 0 ? z : z + 1u;
+    const bool validA = x < g.xb && y < g.ny && z < g.nz;
+    const bool validB = xB < g.xb && y < g.ny && zB < g.nz;
+    if (!__any_sync(full, validA || validB)) return;  // warp-uniform
+
+    const f3 pA = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
+    const float pBe = EXT == 0 ? cell_center(g.fx, g.sx, xB) : cell_center(g.fz, g.sz, zB);  // B's differing coordinate
+    const f3 pB = {EXT == 0 ? pBe : pA.x, pA.y, EXT == 0 ? pA.z : pBe};
+    const float delta = pBe - (EXT == 0 ? pA.x : pA.z);
+
+    const float eps = 4.0e-6f * fmaxf(scene_magnitude(st), grid_mag);
+    auto bound_of = [&](float d2) {  // (dist + slack)^2, rounded up a little (Near::set_bound)
+        const float r = sqrt_approx(d2) + eps;
+        return r * r * 1.000001f;
+    };
+    float bestA = INFINITY, bestB = INFINITY;
+    uint32_t slotA = 0u, slotB = 0u;
+
+    // Seed: the nearest triangle of the voxel with the same (y, z) on the x-far face of the brick one step back in
+    // x (1..4 cells away), published by the warp that computed it; see k_grid_nearest_pkt for why this benign
+    // race cannot change the output. Without one (first brick plane of a launch, stragglers): greedy descent.
+    uint32_t nseed = 0xffffffffu;
+    const uint32_t plane_bricks = nby * nbz;
+    if (tile_slot && blockIdx.x >= plane_bricks) {
+        const uint32_t src_warp = EXT == 0 ? warp : (warp | 2u);
+        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - plane_bricks) * 4u + src_warp) * 16u + (lane & 15u));
+    }
+#ifdef M2S_STATS_BUILD
+    if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 4, 1ull);
+#endif
+    if (nseed >= bvh.nt && (validA || validB)) {
+        Near<MODE_UNSIGNED> s;
+        s.init(eps);
+        greedy_seed<MODE_UNSIGNED>(bvh, validA ? pA : pB, s);
+        nseed = s.best2 < INFINITY ? s.slot : 0u;
+    }
+    if (nseed < bvh.nt) {
+        const bool degen = (bvh.tri_id[nseed] & TRI_DEGEN_BIT) != 0u;
+        if (validA) { bestA = exact_d2(bvh, nseed, degen, pA); slotA = nseed; }
+        if (validB) { bestB = exact_d2(bvh, nseed, degen, pB); slotB = nseed; }
+    }
+    // voxels outside the grid never want a child or a triangle
+    float bndA = validA ? bound_of(bestA) : -1.0f, bndB = validB ? bound_of(bestB) : -1.0f;
+    auto warp_max_b = [&]() {
+        return __uint_as_float(__reduce_max_sync(full, __float_as_uint(fmaxf(fmaxf(bndA, bndB), 0.0f))));
+    };
+    float max_b = warp_max_b();
+
+    int qn = 0, sp = 0;  // warp-uniform
+    int overflow = 0;
+    uint32_t n_nodes = 0, n_leaves = 0;
+
+    // every lane calls it; hA / hB: this lane's voxel A / B needs triangle `item`
+    auto enqueue2 = [&](bool hA, bool hB, uint32_t item) {
+        const unsigned mA = __ballot_sync(full, hA), mB = __ballot_sync(full, hB);
+        const int nA = __popc(mA);
+        if (hA) queue[qn + __popc(mA & lt_mask)] = make_uint2(item, lane);
+        if (hB) queue[qn + nA + __popc(mB & lt_mask)] = make_uint2(item, lane + 32u);
+        qn += nA + __popc(mB);
+    };
+    // exact arithmetic on the queued (triangle, voxel) items, 32 at a time, any lane for any voxel of the tile
+    auto flush = [&](bool everything) {
+        const int nb = everything ? (qn + 31) >> 5 : qn >> 5;
+        if (nb == 0) return;
+        best[lane] = pack_best(bestA, slotA);
+        best[lane + 32u] = pack_best(bestB, slotB);
+        __syncwarp();
+        for (int b = 0; b < nb; ++b) {
+            const int idx = b * 32 + (int)lane;
+            const bool act = idx < qn;
+            const uint2 it = act ? queue[idx] : make_uint2(0u, lane);
+            const int ow = (int)(it.y & 31u);
+            f3 po = {__shfl_sync(full, pA.x, ow), __shfl_sync(full, pA.y, ow), __shfl_sync(full, pA.z, ow)};
+            const float oe = __shfl_sync(full, pBe, ow);
+            if (it.y & 32u) {
+                if (EXT == 0) po.x = oe;
+                else po.z = oe;
+            }
+            if (act) {
+                const uint32_t j = it.x & ~TRI_DEGEN_BIT;
+                const float d2 = exact_d2(bvh, j, (it.x & TRI_DEGEN_BIT) != 0u, po);
+                atomicMin(best + it.y, pack_best(d2, j));
+            }
+        }
+        __syncwarp();
+        const int done = min(nb * 32, qn), rem = qn - done;
+        const uint2 keep = (int)lane < rem ? queue[done + lane] : make_uint2(0u, 0u);
+        const unsigned long long vA = best[lane], vB = best[lane + 32u];
+        __syncwarp();
+        if ((int)lane < rem) queue[lane] = keep;
+        qn = rem;
+        const float nA2 = __uint_as_float((unsigned)(vA >> 32)), nB2 = __uint_as_float((unsigned)(vB >> 32));
+        if (nA2 < bestA) { bestA = nA2; slotA = (uint32_t)vA; bndA = bound_of(nA2); }
+        if (nB2 < bestB) { bestB = nB2; slotB = (uint32_t)vB; bndB = bound_of(nB2); }
+        __syncwarp();
+        max_b = warp_max_b();
+    };
+
+    uint32_t cur = bvh.root;  // always an internal node: leaves are consumed at their parent
+    for (;;) {
+        PKT_COUNT(n_nodes);
+        const float4* nd = bvh.nodes_il + NODE_F4 * (size_t)cur;  // warp-uniform address
+        const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+        const float4 q4 = ldg4(nd + 4), q5 = ldg4(nd + 5), q6 = ldg4(nd + 6), q7 = ldg4(nd + 7);
+        const float2 m1 = make_float2(-1.0f, -1.0f);
+        // low half: left child, high half: right child
+        const float2 dx = __ffma2_rn(f2lo(q0), m1, make_float2(pA.x, pA.x));
+        const float2 dy = __ffma2_rn(f2hi(q0), m1, make_float2(pA.y, pA.y));
+        const float2 dz = __ffma2_rn(f2lo(q1), m1, make_float2(pA.z, pA.z));
+        const float2 tu = __ffma2_rn(dz, f2lo(q3), __ffma2_rn(dy, f2hi(q2), __fmul2_rn(dx, f2lo(q2))));
+        const float2 tv = __ffma2_rn(dz, f2lo(q5), __ffma2_rn(dy, f2hi(q4), __fmul2_rn(dx, f2lo(q4))));
+        const float2 tw = __ffma2_rn(dz, f2lo(q7), __ffma2_rn(dy, f2hi(q6), __fmul2_rn(dx, f2lo(q6))));
+        const float2 dl2 = make_float2(delta, delta);
+        const float2 tuB = __ffma2_rn(dl2, EXT == 0 ? f2lo(q2) : f2lo(q3), tu);
+        const float2 tvB = __ffma2_rn(dl2, EXT == 0 ? f2lo(q4) : f2lo(q5), tv);
+        const float2 twB = __ffma2_rn(dl2, EXT == 0 ? f2lo(q6) : f2lo(q7), tw);
+        const float2 eu = f2hi(q3), ev = f2hi(q5), ew = f2hi(q7);
+        const float2 dA = sumsq2(excess2(tu, eu), excess2(tv, ev), excess2(tw, ew));
+        const float2 dB = sumsq2(excess2(tuB, eu), excess2(tvB, ev), excess2(twB, ew));
+        const bool hAl = dA.x <= bndA, hAr = dA.y <= bndA, hBl = dB.x <= bndB, hBr = dB.y <= bndB;
+        unsigned bl = __ballot_sync(full, hAl || hBl), br = __ballot_sync(full, hAr || hBr);
+        const uint32_t lref = __float_as_uint(q1.z), rref = __float_as_uint(q1.w);
+        if (lref & LEAF_BIT) {
+            if (bl) {
+                enqueue2(hAl, hBl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                PKT_COUNT(n_leaves);
+            }
+            bl = 0u;
+        }
+        if (rref & LEAF_BIT) {
+            if (br) {
+                enqueue2(hAr, hBr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                PKT_COUNT(n_leaves);
+            }
+            br = 0u;
+        }
+        if (qn >= 32) flush(false);
+        if (bl && br) {
+            // children ordered by the warp-min lower bound over the voxels that want them
+            const unsigned kl = min(hAl ? __float_as_uint(dA.x) : 0x7f800000u, hBl ? __float_as_uint(dB.x) : 0x7f800000u);
+            const unsigned kr = min(hAr ? __float_as_uint(dA.y) : 0x7f800000u, hBr ? __float_as_uint(dB.y) : 0x7f800000u);
+            const unsigned ml = __reduce_min_sync(full, kl), mr = __reduce_min_sync(full, kr);
+            const bool left_first = ml <= mr;
+            if (sp < PKT_STACK) {
+                if (lane == 0) stack[sp] = left_first ? make_uint2(rref, mr) : make_uint2(lref, ml);
+                ++sp;
+                __syncwarp();
+            } else {
+                overflow = 1;
+            }
+            cur = left_first ? lref : rref;
+        } else if (bl) {
+            cur = lref;
+        } else if (br) {
+            cur = rref;
+        } else {
+            // pop: entries are re-checked against the current warp-max radius, so a subtree pushed early is
+            // dropped without touching memory
+            uint32_t r = TRAVERSAL_DONE;
+            while (sp > 0) {
+                const uint2 e = stack[--sp];
+                if (__uint_as_float(e.y) <= max_b) {
+                    r = e.x;
+                    break;
+                }
+            }
+            __syncwarp();  // every lane has read its entry before lane 0 may overwrite the slot
+            if (r == TRAVERSAL_DONE) break;
+            cur = r;
+        }
+    }
+    flush(true);
+
+    // publish the x-far voxels' nearest triangles for the brick one step further in x
+    if (tile_slot && lane >= 16u && (EXT == 0 || (warp & 2u))) {
+        if (EXT == 0 ? validB : validA)
+            __stcg(tile_slot + ((size_t)blockIdx.x * 4u + warp) * 16u + (lane & 15u), EXT == 0 ? slotB : slotA);
+    }
+
+    // sqrt is monotone: min sqrt = sqrt min (finish<MODE_UNSIGNED>)
+    float outA = __fsqrt_rn(bestA), outB = __fsqrt_rn(bestB);
+    if (RAYSIGN) {
+        // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd.
+        const uint32_t rows_x = g.ny * g.nz, rows_y = g.nx * g.nz, rows_z = g.nx * g.ny;
+        auto inside = [&](uint32_t vx, uint32_t vz) {
+            const uint32_t rowx = y * g.nz + vz, rowy = vx * g.nz + vz, rowz = vx * g.ny + y;
+            const uint32_t hx = (px[(size_t)(vx >> 5) * rows_x + rowx] >> (vx & 31)) & 1u;
+            const uint32_t hy = (py[(size_t)(y >> 5) * rows_y + rowy] >> (y & 31)) & 1u;
+            const uint32_t hz = (pz[(size_t)(vz >> 5) * rows_z + rowz] >> (vz & 31)) & 1u;
+            return hx + hy + hz >= 2u;
+        };
+        if (validA && inside(x, z)) outA = -outA;
+        if (validB && inside(xB, zB)) outB = -outB;
+    }
+    if (validA) out[((size_t)xr * g.ny + y) * g.nz + z] = outA;
+    if (validB) out[((size_t)(xB - g.x0) * g.ny + y) * g.nz + zB] = outB;
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+    if (bvh.stats && lane == 0) {
+        atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
+        atomicAdd(bvh.stats + 1, (unsigned long long)n_leaves);
+        atomicAdd(bvh.stats + 2, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Grid Raycast rows (generate/grid.rs:568-684). Instead of walking a tree per ray, every triangle
 // finds the few rows whose start-cell centre falls inside its padded, projected box (the box is
 // the bvh crate's filter, geo.rs:4-22), evaluates geo.rs:165-216 there and toggles bit k
@@ -1117,7 +1389,18 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
     const float mag = grid_magnitude(g);
     BuildStatus* st = d.status.as<BuildStatus>();
     const unsigned nb = (unsigned)nblocks;
-    if (d.packet) {
+    if (d.packet && d.pair && grid_uses_neighbour_seeds(d, mode) && d.bvh.leaf_size == 1u && d.bvh.nleaf >= 2u) {
+        // two voxels per lane; the tile is extended along z when the cells are flat in z, else along x
+        CK(d.tile_slot.ensure((size_t)nb * 4 * 16 * 4));
+        CK(cudaMemsetAsync(d.tile_slot.p, 0xff, (size_t)nb * 4 * 16 * 4, s));
+        uint32_t* tile_slot = d.tile_slot.as<uint32_t>();
+        const bool ext_z = d.pair == 3 || (d.pair == 1 && fabsf(g.sz) * 1.5f <= fabsf(g.sx));
+        const uint32_t *b0 = rb ? rb->bits[0] : nullptr, *b1 = rb ? rb->bits[1] : nullptr, *b2 = rb ? rb->bits[2] : nullptr;
+        if (rb && ext_z) k_grid_nearest_pk2<true, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
+        else if (rb) k_grid_nearest_pk2<true, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
+        else if (ext_z) k_grid_nearest_pk2<false, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
+        else k_grid_nearest_pk2<false, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
+    } else if (d.packet) {
         uint32_t* tile_slot = nullptr;
         if (grid_uses_neighbour_seeds(d, mode)) {
             CK(d.tile_slot.ensure((size_t)nb * 8 * 4 * 4));

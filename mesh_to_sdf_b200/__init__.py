@@ -21,7 +21,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm2s.so")
+# M2S_LIB: development override (A/B builds of the same library, e.g. with -DM2S_STATS_BUILD)
+LIB_PATH = os.environ.get("M2S_LIB") or os.path.join(_HERE, "libm2s.so")
 
 __all__ = [
     "generate_sdf", "generate_grid_sdf", "Grid", "SnapResult", "Topology", "SignMethod", "AccelerationMethod",

@@ -43,11 +43,12 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    """out: alternative output path for development A/B builds (loaded with M2S_LIB=<path>)."""
+    if out is None and not force and not is_stale():
         return SO
     extra = os.environ.get("M2S_NVCC_EXTRA", "").split()  # development: e.g. -DPKT_MIN_BLOCKS=5
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", out or SO] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
@@ -57,8 +58,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libm2s.so")
     if verbose:
         print(log)
-    return SO
+    return out or SO
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _out = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=_out[0] if _out else None))

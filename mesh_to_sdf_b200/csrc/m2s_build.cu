@@ -447,17 +447,28 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
 // the right child in its high half:
 //   q0 = (cL.x, cR.x, cL.y, cR.y)  q1 = (cL.z, cR.z, refL, refR)
 //   q2 = (uL.x, uR.x, uL.y, uR.y)  q3 = (uL.z, uR.z, euL, euR)     q4, q5: v     q6, q7: w
+// Frames and extents are multiplied by inv_s (a power of two: exact), so the projections come out in units
+// of S = 1 / inv_s >= 4 x the largest scene / grid coordinate and max(|t| - e, 0) is ONE saturating add
+// (FADD.SAT clamps to [0, 1]; 1 is never reached inside the scene, and clamping a lower bound from above
+// keeps it a lower bound).
 __global__ void __launch_bounds__(256)
-k_nodes_interleave(const float4* __restrict__ nodes, uint32_t n_nodes, float4* __restrict__ il) {
+k_nodes_interleave(const float4* __restrict__ nodes, uint32_t n_nodes, float4* __restrict__ il,
+                   const BuildStatus* __restrict__ st, float grid_mag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
+    const float inv_s = pair_inv_scale(fmaxf(scene_mag(st), grid_mag));
     const float4* nd = nodes + NODE_F4 * (size_t)i;
     float4* o = il + NODE_F4 * (size_t)i;
+    {
+        const float4 l = nd[0], r = nd[CHILD_F4];
+        o[0] = make_float4(l.x, r.x, l.y, r.y);
+        o[1] = make_float4(l.z, r.z, l.w, r.w);
+    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 1; k < 4; ++k) {
         const float4 l = nd[k], r = nd[CHILD_F4 + k];
-        o[2 * k] = make_float4(l.x, r.x, l.y, r.y);
-        o[2 * k + 1] = make_float4(l.z, r.z, l.w, r.w);
+        o[2 * k] = make_float4(l.x * inv_s, r.x * inv_s, l.y * inv_s, r.y * inv_s);
+        o[2 * k + 1] = make_float4(l.z * inv_s, r.z * inv_s, l.w * inv_s, r.w * inv_s);
     }
 }
 
@@ -642,9 +653,7 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
         k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
             d.rec_sorted.as<float4>(), d.tobb.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.boxes.as<float4>(),
             d.nodes.as<float4>(), d.node_range.as<uint2>(), st, d.obb_bias);
-        k_nodes_interleave<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.nodes.as<float4>(), nleaf - 1,
-                                                                    d.nodes_il.as<float4>());
-        d.launches += 4;
+        d.launches += 3;
     }
     d.bvh.rec = d.rec_sorted.as<float4>();
     d.bvh.tobb = d.tobb.as<float4>();
@@ -652,6 +661,7 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     d.bvh.tri_id = d.tri_id_sorted.as<uint32_t>();
     d.bvh.nodes = d.nodes.as<float4>();
     d.bvh.nodes_il = d.nodes_il.as<float4>();
+    d.nodes_il_mag = -1.0f;  // the interleaved copy is written by launch_nodes_interleave once the grid is known
     d.bvh.nleaf = nleaf;
     if (d.want_stats) {
         CK(d.stats.ensure(64));
@@ -660,6 +670,16 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
         d.bvh.stats = d.stats.as<unsigned long long>();
     }
     d.bvh.root = nleaf > 1 ? 0u : (LEAF_BIT | LEAF_DEGEN_BIT);  // single leaf: always take the guarded path
+    return cudaGetLastError();
+}
+
+// Writes Bvh::nodes_il for a grid of magnitude grid_mag (see k_nodes_interleave); a no-op if it is current.
+cudaError_t launch_nodes_interleave(Device& d, float grid_mag) {
+    if (d.bvh.nleaf < 2 || d.nodes_il_mag == grid_mag) return cudaSuccess;
+    k_nodes_interleave<<<blocks_for(d.bvh.nleaf - 1, 256), 256, 0, d.stream>>>(
+        d.nodes.as<float4>(), d.bvh.nleaf - 1, d.nodes_il.as<float4>(), d.status.as<BuildStatus>(), grid_mag);
+    d.launches++;
+    d.nodes_il_mag = grid_mag;
     return cudaGetLastError();
 }
 

@@ -73,6 +73,18 @@ struct GridParams {
     uint32_t xa, xb;      // planes [xa, xb) of the slab computed by this launch (chunked host copies)
 };
 
+#ifdef __CUDACC__
+// Scale of the interleaved nodes (k_nodes_interleave / k_grid_nearest_pk2): 1 / S with S the power of two
+// >= 4 x mag, mag = largest |coordinate| of mesh and grid. Both kernels derive it from the same device-side
+// inputs, so the host never has to know the mesh bounds.
+__device__ __forceinline__ float pair_inv_scale(float mag) {
+    if (!(mag > 0.0f) || !isfinite(mag)) return 1.0f;
+    int e;
+    frexpf(4.0f * mag, &e);  // 4 mag = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.0f, -e);
+}
+#endif
+
 // Row parity bitmaps for the grid Raycast sign (generate/grid.rs:568-642). For axis A the rows are
 // the nB*nC rays starting on the face cell A=0; bit i of a row = parity of the hits whose last
 // incremented cell k satisfies k >= i. Layout: [word][row] per axis so neighbouring rows are adjacent.
@@ -137,12 +149,14 @@ struct Device {
     cudaEvent_t ev_copied = nullptr;
 
     Bvh bvh{};
+    float nodes_il_mag = -1.0f;  // grid magnitude the interleaved nodes were last written for (< 0: stale)
 };
 
 // ---- launchers (each returns the CUDA error of its enqueue) ------------------------------------------
 cudaError_t launch_status_reset(Device& d, bool clear_errors);
 cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
                          uint32_t leaf_size);
+cudaError_t launch_nodes_interleave(Device& d, float grid_mag);
 cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
 
 cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb);

@@ -773,8 +773,10 @@ constexpr int PK2_QCAP = 160;  // < 32 items left over + at most 2 leaves x 64 v
 
 __device__ __forceinline__ float2 f2lo(const float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 f2hi(const float4 v) { return make_float2(v.z, v.w); }
-__device__ __forceinline__ float2 excess2(const float2 t, const float2 e) {  // max(|t| - e, 0) per half
-    return make_float2(fmaxf(fabsf(t.x) - e.x, 0.0f), fmaxf(fabsf(t.y) - e.y, 0.0f));
+// max(|t| - e, 0) per half as one saturating add each: projections and extents are pre-scaled so that 1 is
+// out of reach inside the scene (k_nodes_interleave)
+__device__ __forceinline__ float2 excess2(const float2 t, const float2 e) {
+    return make_float2(__saturatef(fabsf(t.x) - e.x), __saturatef(fabsf(t.y) - e.y));
 }
 __device__ __forceinline__ float2 sumsq2(const float2 a, const float2 b, const float2 c) {
     return __ffma2_rn(c, c, __ffma2_rn(b, b, __fmul2_rn(a, a)));
@@ -826,10 +828,13 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const f3 pB = {EXT == 0 ? pBe : pA.x, pA.y, EXT == 0 ? pA.z : pBe};
     const float delta = pBe - (EXT == 0 ? pA.x : pA.z);
 
-    const float eps = 4.0e-6f * fmaxf(scene_magnitude(st), grid_mag);
-    auto bound_of = [&](float d2) {  // (dist + slack)^2, rounded up a little (Near::set_bound)
+    const float mag = fmaxf(scene_magnitude(st), grid_mag);
+    const float eps = 4.0e-6f * mag;
+    const float inv_s = pair_inv_scale(mag), inv_s2 = inv_s * inv_s;
+    // (dist + slack)^2, rounded up a little (Near::set_bound), in the squared units of the scaled nodes
+    auto bound_of = [&](float d2) {
         const float r = sqrt_approx(d2) + eps;
-        return r * r * 1.000001f;
+        return r * r * 1.000001f * inv_s2;
     };
     float bestA = INFINITY, bestB = INFINITY;
     uint32_t slotA = 0u, slotB = 0u;
@@ -1396,6 +1401,7 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
         uint32_t* tile_slot = d.tile_slot.as<uint32_t>();
         const bool ext_z = d.pair == 3 || (d.pair == 1 && fabsf(g.sz) * 1.5f <= fabsf(g.sx));
         const uint32_t *b0 = rb ? rb->bits[0] : nullptr, *b1 = rb ? rb->bits[1] : nullptr, *b2 = rb ? rb->bits[2] : nullptr;
+        CK(launch_nodes_interleave(d, mag));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
         if (rb && ext_z) k_grid_nearest_pk2<true, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
         else if (rb) k_grid_nearest_pk2<true, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
         else if (ext_z) k_grid_nearest_pk2<false, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);

@@ -352,6 +352,19 @@ uint64_t m2s_launch_count(const m2s_ctx* ctx) {
 
 int m2s_device_count(const m2s_ctx* ctx) { return ctx ? ctx->n_devices : 0; }
 
+#ifdef M2S_STATS_BUILD
+// development builds only (not part of the ABI): visits per subtree size class, see Bvh::stats
+M2S_API m2s_status m2s_debug_hist(m2s_ctx* ctx, uint64_t out[32]) {
+    if (!ctx || !out) return M2S_EINVAL;
+    std::memset(out, 0, 32 * 8);
+    Device& d = ctx->dev[0];
+    if (!d.stats.p) return M2S_OK;
+    cudaSetDevice(d.ordinal);
+    cudaStreamSynchronize(d.stream);
+    return cudaMemcpy(out, (char*)d.stats.p + 64, 32 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? M2S_OK : M2S_ECUDA;
+}
+#endif
+
 m2s_status m2s_debug_stats(m2s_ctx* ctx, uint64_t out[4]) {
     if (!ctx || !out) return M2S_EINVAL;
     std::lock_guard<std::mutex> lock(ctx->mu);

@@ -663,9 +663,10 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     d.bvh.nodes_il = d.nodes_il.as<float4>();
     d.nodes_il_mag = -1.0f;  // the interleaved copy is written by launch_nodes_interleave once the grid is known
     d.bvh.nleaf = nleaf;
+    d.bvh.node_range = d.node_range.as<uint2>();
     if (d.want_stats) {
-        CK(d.stats.ensure(64));
-        CK(cudaMemsetAsync(d.stats.p, 0, 64, s));
+        CK(d.stats.ensure(64 + 32 * 8));
+        CK(cudaMemsetAsync(d.stats.p, 0, 64 + 32 * 8, s));
         if (d.stats_mode == 2) CK(cudaMemsetAsync((char*)d.stats.p + 24, 2, 1, s));
         d.bvh.stats = d.stats.as<unsigned long long>();
     }

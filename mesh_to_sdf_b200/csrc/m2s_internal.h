@@ -62,7 +62,9 @@ struct Bvh {
     uint32_t leaf_size;       // K
     uint32_t root;            // root ref (a leaf ref when nleaf == 1)
     const BuildStatus* st;    // device pointer: scene bounds (-> pruning slack) and error flags
-    unsigned long long* stats; // optional traversal counters (M2S_STATS=1): nodes, leaves, searches
+    unsigned long long* stats; // optional traversal counters (M2S_STATS=1): nodes, leaves, searches; with
+                               // -DM2S_STATS_BUILD also [8 + k]: visits of nodes spanning [2^k, 2^(k+1)) leaves
+    const uint2* node_range;   // per internal node: first / last leaf (diagnostics only)
 };
 
 struct GridParams {

@@ -789,7 +789,7 @@ template <bool RAYSIGN, int EXT>
 __global__ void __launch_bounds__(128, PK2_MIN_BLOCKS)
 k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
                    const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
-                   BuildStatus* __restrict__ st, uint32_t* tile_slot) {
+                   BuildStatus* __restrict__ st, uint32_t* tile_slot, const uint32_t seed_planes) {
     __shared__ uint2 s_stack[4][PKT_STACK];
     __shared__ uint2 s_queue[4][PK2_QCAP];          // (triangle slot | degen, owner voxel 0..63)
     __shared__ unsigned long long s_best[4][64];    // per owner voxel: (d2 bits << 32) | slot
@@ -843,19 +843,25 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     // x (1..4 cells away), published by the warp that computed it; see k_grid_nearest_pkt for why this benign
     // race cannot change the output. Without one (first brick plane of a launch, stragglers): greedy descent.
     uint32_t nseed = 0xffffffffu;
-    const uint32_t plane_bricks = nby * nbz;
-    if (tile_slot && blockIdx.x >= plane_bricks) {
+    const uint32_t back = seed_planes * nby * nbz;  // dispatch distance of the brick `seed_planes` steps back in x
+    if (tile_slot && blockIdx.x >= back) {
         const uint32_t src_warp = EXT == 0 ? warp : (warp | 2u);
-        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - plane_bricks) * 4u + src_warp) * 16u + (lane & 15u));
+        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - back) * 4u + src_warp) * 16u + (lane & 15u));
+        // a straggler: the brick twice as far back has certainly finished (still a good radius)
+        if (nseed == 0xffffffffu && blockIdx.x >= 2u * back)
+            nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - 2u * back) * 4u + src_warp) * 16u + (lane & 15u));
     }
 #ifdef M2S_STATS_BUILD
     if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 4, 1ull);
 #endif
-    if (nseed >= bvh.nt && (validA || validB)) {
+    if (__any_sync(full, nseed >= bvh.nt)) {
+        // no neighbour result (first brick planes of a launch): one greedy descent for a voxel in the middle of
+        // the tile, the same on every lane (uniform loads, no divergence); its triangle seeds the lanes without one
+        const f3 pc = {__shfl_sync(full, pA.x, 13), __shfl_sync(full, pA.y, 13), __shfl_sync(full, pA.z, 13)};
         Near<MODE_UNSIGNED> s;
         s.init(eps);
-        greedy_seed<MODE_UNSIGNED>(bvh, validA ? pA : pB, s);
-        nseed = s.best2 < INFINITY ? s.slot : 0u;
+        greedy_seed<MODE_UNSIGNED>(bvh, pc, s);
+        if (nseed >= bvh.nt) nseed = s.best2 < INFINITY ? s.slot : 0u;
     }
     if (nseed < bvh.nt) {
         const bool degen = (bvh.tri_id[nseed] & TRI_DEGEN_BIT) != 0u;
@@ -922,6 +928,12 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     uint32_t cur = bvh.root;  // always an internal node: leaves are consumed at their parent
     for (;;) {
         PKT_COUNT(n_nodes);
+#ifdef M2S_STATS_BUILD
+        if (bvh.stats && lane == 0) {
+            const uint2 nr = bvh.node_range[cur];
+            atomicAdd(bvh.stats + 8 + (31 - __clz(nr.y - nr.x + 1u)), 1ull);
+        }
+#endif
         const float4* nd = bvh.nodes_il + NODE_F4 * (size_t)cur;  // warp-uniform address
         const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
         const float4 q4 = ldg4(nd + 4), q5 = ldg4(nd + 5), q6 = ldg4(nd + 6), q7 = ldg4(nd + 7);
@@ -1401,11 +1413,15 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
         uint32_t* tile_slot = d.tile_slot.as<uint32_t>();
         const bool ext_z = d.pair == 3 || (d.pair == 1 && fabsf(g.sz) * 1.5f <= fabsf(g.sx));
         const uint32_t *b0 = rb ? rb->bits[0] : nullptr, *b1 = rb ? rb->bits[1] : nullptr, *b2 = rb ? rb->bits[2] : nullptr;
+        // seeds come from the brick `planes` steps back in x: far enough in dispatch order to have finished
+        // (about 1.25 x the resident blocks), at most 4 steps (16 cells)
+        const uint32_t plane_bricks = cdiv(g.ny, BY) * cdiv(g.nz, BZ);
+        const uint32_t planes = std::min(4u, std::max(1u, cdiv((uint32_t)d.sm_count * PK2_MIN_BLOCKS * 5u / 4u, plane_bricks)));
         CK(launch_nodes_interleave(d, mag));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
-        if (rb && ext_z) k_grid_nearest_pk2<true, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
-        else if (rb) k_grid_nearest_pk2<true, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
-        else if (ext_z) k_grid_nearest_pk2<false, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
-        else k_grid_nearest_pk2<false, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot);
+        if (rb && ext_z) k_grid_nearest_pk2<true, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
+        else if (rb) k_grid_nearest_pk2<true, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
+        else if (ext_z) k_grid_nearest_pk2<false, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
+        else k_grid_nearest_pk2<false, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
     } else if (d.packet) {
         uint32_t* tile_slot = nullptr;
         if (grid_uses_neighbour_seeds(d, mode)) {

@@ -17,5 +17,11 @@ for pair in sys.argv[1:] or ["0", "2", "3"]:
         a = (C.c_uint64 * 4)()
         L.m2s_debug_stats(ctx._h, a)
         s = [int(x) for x in a]
-        print(f"pair={pair}: tiles {s[2]} nodes/tile {s[0]/max(s[2],1):.1f} leaves/tile {s[1]/max(s[2],1):.1f} "
+        if hasattr(L, "m2s_debug_hist"):
+            h = (C.c_uint64 * 32)()
+            L.m2s_debug_hist(ctx._h, h)
+            h = [int(x) for x in h]
+            if sum(h):
+                print("   visits per tile by subtree size 2^k leaves:", " ".join(f"{k}:{v/max(s[2],1):.1f}" for k, v in enumerate(h) if v))
+        print(f"pair={pair}: no-seed tiles {s[3]} tiles {s[2]} nodes/tile {s[0]/max(s[2],1):.1f} leaves/tile {s[1]/max(s[2],1):.1f} "
               f"dist_ms {ctx.timings()['dist_ms']:.2f}", flush=True)

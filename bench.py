@@ -6,7 +6,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A step = one full pass of the hot path over one slab: triangle records + Morton sort + LBVH + pillboxes, the
+A step = one full pass of the hot path over one slab: triangle records + Morton sort + LBVH + oriented boxes, the
 Raycast row parities, the seeding passes and the nearest-triangle kernel with the sign epilogue.
   value : inputs already resident in HBM (m2s_generate_grid_sdf_device), timed with CUDA events on the stream
           the kernels are launched on; L2 is flushed between steps (256 MiB write, outside the event pairs).
@@ -177,7 +177,7 @@ def workload_config(name, verts, tris, grid, sign, world, scaling):
         "sign_method": "Raycast" if sign == 0 else "Normal",
         "partition": f"x-slabs, {world} rank(s), {scaling} scaling" if world > 1 else "single GPU, whole grid",
         "l2": "flushed between steps (256 MiB device write outside the per-step event pairs)",
-        "step": "records + Morton sort + LBVH + pillboxes + row parities + seeding + nearest kernel, per step",
+        "step": "records + Morton sort + LBVH + oriented boxes + row parities + nearest kernel (neighbour seeds), per step",
     }
 
 
@@ -279,13 +279,13 @@ def run_ours(args):
     e2e_phase = ctx.timings()
     checksum = float(np.abs(np_out[:: max(1, slab_cells // 4096)]).sum())
 
-    # ---- roofline of the dominant kernel (k_grid_nearest) ----
+    # ---- roofline of the dominant kernel (k_grid_nearest_run) ----
     b_alg = 4 * slab_cells + 12 * len(verts) + 12 * len(tris)  # output once + raw mesh once
     kern_ms = float(kern.item())
     peak, peak_src = measured_peak()
     achieved = b_alg / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "k_grid_nearest", "kernel_ms": kern_ms,
+                "traffic": ncu_traffic(), "kernel": "k_grid_nearest_run<Raycast, V=2>", "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": b_alg, "peak_source": peak_src,
                 "note": "exact nearest-triangle search is issue/L1-bound, not HBM-bound (see DESIGN.md, profiles/)"}
 

@@ -76,7 +76,7 @@ struct GridParams {
 };
 
 #ifdef __CUDACC__
-// Scale of the interleaved nodes (k_nodes_interleave / k_grid_nearest_pk2): 1 / S with S the power of two
+// Scale of the interleaved nodes (k_nodes_interleave / k_grid_nearest_run): 1 / S with S the power of two
 // >= 4 x mag, mag = largest |coordinate| of mesh and grid. Both kernels derive it from the same device-side
 // inputs, so the host never has to know the mesh bounds.
 __device__ __forceinline__ float pair_inv_scale(float mag) {
@@ -131,8 +131,8 @@ struct Device {
     float obb_bias = 1.0f;     // oriented box kept when its volume <= obb_bias * padded box volume (M2S_OBB_BIAS)
     bool seed_packet = false;  // M2S_SEED_PACKET=0: per-lane traversal for the seed pass
     bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
-    int pair = 1;              // M2S_PAIR: 0 = one voxel per lane (k_grid_nearest_pkt); 1 = two voxels per lane, tile
-                               // shape picked from the cell sizes; 2 / 3 force the x-extended / z-extended tile
+    int pair = 1;              // M2S_PAIR: 0 = one voxel per lane (k_grid_nearest_pkt); 1 = k_grid_nearest_run, V = 2 voxels
+                               // per lane; 4..7 = its (V, LAYOUT) variants for A/B runs
     DevBuf tile_slot;         // per-tile nearest-triangle slots published by the distance kernel
     bool neighbour_and_coarse = false;  // experiment (M2S_NSEED=2): coarse pass as the fallback of neighbour seeds
     bool neighbour_seeds = true;  // M2S_NSEED=0: separate coarse seed pass for every grid

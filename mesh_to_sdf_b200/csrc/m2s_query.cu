@@ -749,27 +749,30 @@ k_grid_nearest_pkt(const Bvh bvh, const GridParams g, const float grid_mag, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Pair kernel: the packet walk with TWO voxels per lane and both children of a node evaluated by one
-// packed-fp32 instruction stream (FFMA2 / FMUL2, sm_100a). Default for Raycast / unsigned grids.
+// Run kernel: the packet walk with a RUN of V consecutive voxels along z per lane (V = 2 by default) and both
+// children of a node evaluated by one packed-fp32 instruction stream (FFMA2 / FMUL2, sm_100a). Default for
+// Raycast / unsigned grids.
 //
 // ncu on k_grid_nearest_pkt (profiles/r1e) showed two co-limiters at ~76 %: issue slots and the L1 -> register
 // write-back of the warp-uniform node loads (8 x LDG.128 broadcast = 4 KB of register writes per node visit).
-// Here a warp owns 64 voxels - a 4x4x4 tile (EXT = 0: the lane's second voxel is two cells further in x) or a
-// 2x4x8 tile (EXT = 2: the next cell in z; picked when the cells are flat in z) - so one node load and one
-// round of votes / stack traffic serve twice the voxels, and the bound arithmetic shrinks from 4 x 22 scalar
-// instructions to 45 per (2 voxels x 2 children):
-//   * the node is stored with its children interleaved (Bvh::nodes_il), the low half of every packed
-//     operation is the left child and the high half the right child;
-//   * the second voxel differs from the first by a constant step d along one grid axis, so its projections
-//     are one FFMA2 each: (pB - c).u = (pA - c).u + d * u[axis].
+// Here a warp owns 32 V voxels, so one node load and one round of votes / stack traffic serve V times the
+// voxels, and the bound arithmetic shrinks from 4 x 22 scalar instructions to 33 per (2 voxels x 2 children):
+//   * the node is stored with its children interleaved (Bvh::nodes_il): the low half of every packed
+//     operation is the left child, the high half the right child;
+//   * voxel i of a lane differs from voxel 0 by the constant step z_i - z_0 along one grid axis, so its
+//     projections are one FFMA2 each: (p_i - c).u = (p_0 - c).u + (z_i - z_0) u.z;
+//   * frames and extents are pre-scaled (k_nodes_interleave) so that max(|t| - e, 0) is one FADD.SAT.
 // Only the pruning bounds are computed this way (plain fp32, conservative: the extents carry the slack);
 // results still come from the reference-order un-fused arithmetic of exact_d2, so the output is the same
 // exact minimum, bit for bit. Requires single-triangle leaves (K = 1) and at least one internal node.
+// LAYOUT 0: lanes 2 x 4 x 4 runs -> tile 2 x 4 x 4V;  LAYOUT 1: lanes 4 x 4 x 2 runs -> tile 4 x 4 x 2V.
+// A block of 4 warps covers a 4 x 8 x 4V brick either way. Measured on C3 (flat cells) and on a cubic-cell
+// grid: (V, LAYOUT) = (2, 0) is the best or within 1 % of it on both; V = 4 executes fewer instructions
+// but loses as much to its 96 registers (fewer resident warps); kept as M2S_PAIR = 5..7 for A/B runs.
 // ---------------------------------------------------------------------------------------------------
-#ifndef PK2_MIN_BLOCKS
-#define PK2_MIN_BLOCKS 5
+#ifndef RUN2_MIN_BLOCKS
+#define RUN2_MIN_BLOCKS 5
 #endif
-constexpr int PK2_QCAP = 160;  // < 32 items left over + at most 2 leaves x 64 voxels appended by one node
 
 __device__ __forceinline__ float2 f2lo(const float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 f2hi(const float4 v) { return make_float2(v.z, v.w); }
@@ -785,14 +788,21 @@ __device__ __forceinline__ unsigned long long pack_best(float d2, uint32_t slot)
     return ((unsigned long long)__float_as_uint(d2) << 32) | slot;
 }
 
-template <bool RAYSIGN, int EXT>
-__global__ void __launch_bounds__(128, PK2_MIN_BLOCKS)
-k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
+#ifndef RUN4_MIN_BLOCKS
+#define RUN4_MIN_BLOCKS 4
+#endif
+
+template <bool RAYSIGN, int V, int LAYOUT>
+__global__ void __launch_bounds__(128, V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS)
+k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
                    const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
                    BuildStatus* __restrict__ st, uint32_t* tile_slot, const uint32_t seed_planes) {
+    constexpr int NV = 32 * V;         // voxels per tile
+    constexpr int QCAP = 32 + 2 * NV;  // < 32 items left over + at most 2 leaves x NV voxels appended by one node
+    constexpr uint32_t BZR = 4u * V;   // brick extent in z
     __shared__ uint2 s_stack[4][PKT_STACK];
-    __shared__ uint2 s_queue[4][PK2_QCAP];          // (triangle slot | degen, owner voxel 0..63)
-    __shared__ unsigned long long s_best[4][64];    // per owner voxel: (d2 bits << 32) | slot
+    __shared__ uint2 s_queue[4][QCAP];            // (triangle slot | degen, owner voxel = i * 32 + lane)
+    __shared__ unsigned long long s_best[4][NV];  // per owner voxel: (d2 bits << 32) | slot
     const unsigned full = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -800,33 +810,34 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     uint2* const queue = s_queue[warp];
     unsigned long long* const best = s_best[warp];
 
-    // brick numbering as in brick_coords (z fastest): consecutive blocks share tree nodes in L1 / L2
-    const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZ - 1) / BZ;
+    // bricks numbered z fastest, x slowest: consecutive blocks share tree nodes in L1 / L2
+    const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZR - 1) / BZR;
     uint32_t bid = blockIdx.x;
     const uint32_t bz = bid % nbz;
     bid /= nbz;
     const uint32_t by = bid % nby, bx = bid / nby;
-    uint32_t xr, y, z;  // voxel A of this lane (x relative to the slab start)
-    if (EXT == 0) {     // warp (wy, wz), lane (lx, ly, lz): tile 4 x 4 x 4, voxel B = A + 2 cells in x
-        xr = bx * BX + (lane >> 4);
-        y = by * BY + ((warp >> 1) & 1u) * 4u + ((lane >> 2) & 3u);
-        z = bz * BZ + (warp & 1u) * 4u + (lane & 3u);
-    } else {            // warp (wx, wy), lane (lx, ly, lz'): tile 2 x 4 x 8, voxel B = A + 1 cell in z
+    uint32_t xr, y, z0;  // first voxel of this lane's run (x relative to the slab start)
+    if (LAYOUT == 0) {   // warp (wx, wy), lane (lx:2, ly:4, run:4)
         xr = bx * BX + ((warp >> 1) & 1u) * 2u + (lane >> 4);
         y = by * BY + (warp & 1u) * 4u + ((lane >> 2) & 3u);
-        z = bz * BZ + (lane & 3u) * 2u;
+        z0 = bz * BZR + (lane & 3u) * V;
+    } else {             // warp (wy, wz), lane (lx:4, ly:4, run:2)
+        xr = bx * BX + (lane >> 3);
+        y = by * BY + ((warp >> 1) & 1u) * 4u + ((lane >> 1) & 3u);
+        z0 = bz * BZR + (warp & 1u) * 2u * V + (lane & 1u) * V;
     }
     xr += g.xa - g.x0;  // this launch covers planes [xa, xb) of the slab
     const uint32_t x = g.x0 + xr;
-    const uint32_t xB = EXT == 0 ? x + 2u : x, zB = EXT == 0 ? z : z + 1u;
-    const bool validA = x < g.xb && y < g.ny && z < g.nz;
-    const bool validB = xB < g.xb && y < g.ny && zB < g.nz;
-    if (!__any_sync(full, validA || validB)) return;  // warp-uniform
+    const bool valid_xy = x < g.xb && y < g.ny;
+    bool valid[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) valid[i] = valid_xy && z0 + i < g.nz;
+    if (!__any_sync(full, valid[0])) return;  // warp-uniform (voxel 0 is the first of the run to be valid)
 
-    const f3 pA = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z)};
-    const float pBe = EXT == 0 ? cell_center(g.fx, g.sx, xB) : cell_center(g.fz, g.sz, zB);  // B's differing coordinate
-    const f3 pB = {EXT == 0 ? pBe : pA.x, pA.y, EXT == 0 ? pA.z : pBe};
-    const float delta = pBe - (EXT == 0 ? pA.x : pA.z);
+    const f3 p0 = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z0)};
+    float step[V];  // z_i - z_0 (step[0] unused)
+#pragma unroll
+    for (int i = 1; i < V; ++i) step[i] = cell_center(g.fz, g.sz, z0 + i) - p0.z;
 
     const float mag = fmaxf(scene_magnitude(st), grid_mag);
     const float eps = 4.0e-6f * mag;
@@ -836,20 +847,22 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
         const float r = sqrt_approx(d2) + eps;
         return r * r * 1.000001f * inv_s2;
     };
-    float bestA = INFINITY, bestB = INFINITY;
-    uint32_t slotA = 0u, slotB = 0u;
+    float best2[V], bnd[V];
+    uint32_t slot[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best2[i] = INFINITY; slot[i] = 0u; }
 
-    // Seed: the nearest triangle of the voxel with the same (y, z) on the x-far face of the brick one step back in
-    // x (1..4 cells away), published by the warp that computed it; see k_grid_nearest_pkt for why this benign
-    // race cannot change the output. Without one (first brick plane of a launch, stragglers): greedy descent.
+    // Seed: the nearest triangle of the voxel with the same (y, z run) on the x-far face of the brick
+    // `seed_planes` steps back in x, published by the warp that computed it; see k_grid_nearest_pkt for why this
+    // benign race cannot change the output.
     uint32_t nseed = 0xffffffffu;
-    const uint32_t back = seed_planes * nby * nbz;  // dispatch distance of the brick `seed_planes` steps back in x
+    const uint32_t back = seed_planes * nby * nbz;  // dispatch distance of that brick
+    const uint32_t src_warp = LAYOUT == 0 ? (warp | 2u) : warp, src_idx = LAYOUT == 0 ? (lane & 15u) : (lane & 7u);
     if (tile_slot && blockIdx.x >= back) {
-        const uint32_t src_warp = EXT == 0 ? warp : (warp | 2u);
-        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - back) * 4u + src_warp) * 16u + (lane & 15u));
+        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - back) * 4u + src_warp) * 16u + src_idx);
         // a straggler: the brick twice as far back has certainly finished (still a good radius)
         if (nseed == 0xffffffffu && blockIdx.x >= 2u * back)
-            nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - 2u * back) * 4u + src_warp) * 16u + (lane & 15u));
+            nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - 2u * back) * 4u + src_warp) * 16u + src_idx);
     }
 #ifdef M2S_STATS_BUILD
     if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 4, 1ull);
@@ -857,7 +870,7 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     if (__any_sync(full, nseed >= bvh.nt)) {
         // no neighbour result (first brick planes of a launch): one greedy descent for a voxel in the middle of
         // the tile, the same on every lane (uniform loads, no divergence); its triangle seeds the lanes without one
-        const f3 pc = {__shfl_sync(full, pA.x, 13), __shfl_sync(full, pA.y, 13), __shfl_sync(full, pA.z, 13)};
+        const f3 pc = {__shfl_sync(full, p0.x, 13), __shfl_sync(full, p0.y, 13), __shfl_sync(full, p0.z, 13)};
         Near<MODE_UNSIGNED> s;
         s.init(eps);
         greedy_seed<MODE_UNSIGNED>(bvh, pc, s);
@@ -865,13 +878,22 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     }
     if (nseed < bvh.nt) {
         const bool degen = (bvh.tri_id[nseed] & TRI_DEGEN_BIT) != 0u;
-        if (validA) { bestA = exact_d2(bvh, nseed, degen, pA); slotA = nseed; }
-        if (validB) { bestB = exact_d2(bvh, nseed, degen, pB); slotB = nseed; }
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            if (valid[i]) {
+                const f3 pi = {p0.x, p0.y, i == 0 ? p0.z : cell_center(g.fz, g.sz, z0 + i)};
+                best2[i] = exact_d2(bvh, nseed, degen, pi);
+                slot[i] = nseed;
+            }
     }
     // voxels outside the grid never want a child or a triangle
-    float bndA = validA ? bound_of(bestA) : -1.0f, bndB = validB ? bound_of(bestB) : -1.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) bnd[i] = valid[i] ? bound_of(best2[i]) : -1.0f;
     auto warp_max_b = [&]() {
-        return __uint_as_float(__reduce_max_sync(full, __float_as_uint(fmaxf(fmaxf(bndA, bndB), 0.0f))));
+        float m = 0.0f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) m = fmaxf(m, bnd[i]);
+        return __uint_as_float(__reduce_max_sync(full, __float_as_uint(m)));
     };
     float max_b = warp_max_b();
 
@@ -879,32 +901,31 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     int overflow = 0;
     uint32_t n_nodes = 0, n_leaves = 0;
 
-    // every lane calls it; hA / hB: this lane's voxel A / B needs triangle `item`
-    auto enqueue2 = [&](bool hA, bool hB, uint32_t item) {
-        const unsigned mA = __ballot_sync(full, hA), mB = __ballot_sync(full, hB);
-        const int nA = __popc(mA);
-        if (hA) queue[qn + __popc(mA & lt_mask)] = make_uint2(item, lane);
-        if (hB) queue[qn + nA + __popc(mB & lt_mask)] = make_uint2(item, lane + 32u);
-        qn += nA + __popc(mB);
+    // every lane calls it; bit i of h: this lane's voxel i needs triangle `item`
+    auto enqueue = [&](unsigned h, uint32_t item) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const bool w = (h >> i) & 1u;
+            const unsigned m = __ballot_sync(full, w);
+            if (w) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
+            qn += __popc(m);
+        }
     };
     // exact arithmetic on the queued (triangle, voxel) items, 32 at a time, any lane for any voxel of the tile
     auto flush = [&](bool everything) {
         const int nb = everything ? (qn + 31) >> 5 : qn >> 5;
         if (nb == 0) return;
-        best[lane] = pack_best(bestA, slotA);
-        best[lane + 32u] = pack_best(bestB, slotB);
+#pragma unroll
+        for (int i = 0; i < V; ++i) best[lane + 32u * i] = pack_best(best2[i], slot[i]);
         __syncwarp();
         for (int b = 0; b < nb; ++b) {
             const int idx = b * 32 + (int)lane;
             const bool act = idx < qn;
             const uint2 it = act ? queue[idx] : make_uint2(0u, lane);
             const int ow = (int)(it.y & 31u);
-            f3 po = {__shfl_sync(full, pA.x, ow), __shfl_sync(full, pA.y, ow), __shfl_sync(full, pA.z, ow)};
-            const float oe = __shfl_sync(full, pBe, ow);
-            if (it.y & 32u) {
-                if (EXT == 0) po.x = oe;
-                else po.z = oe;
-            }
+            // the owner's position: its z is recomputed exactly as the owner computed it (Grid::get_cell_center)
+            const f3 po = {__shfl_sync(full, p0.x, ow), __shfl_sync(full, p0.y, ow),
+                           cell_center(g.fz, g.sz, __shfl_sync(full, z0, ow) + (it.y >> 5))};
             if (act) {
                 const uint32_t j = it.x & ~TRI_DEGEN_BIT;
                 const float d2 = exact_d2(bvh, j, (it.x & TRI_DEGEN_BIT) != 0u, po);
@@ -914,13 +935,17 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
         __syncwarp();
         const int done = min(nb * 32, qn), rem = qn - done;
         const uint2 keep = (int)lane < rem ? queue[done + lane] : make_uint2(0u, 0u);
-        const unsigned long long vA = best[lane], vB = best[lane + 32u];
+        unsigned long long v[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = best[lane + 32u * i];
         __syncwarp();
         if ((int)lane < rem) queue[lane] = keep;
         qn = rem;
-        const float nA2 = __uint_as_float((unsigned)(vA >> 32)), nB2 = __uint_as_float((unsigned)(vB >> 32));
-        if (nA2 < bestA) { bestA = nA2; slotA = (uint32_t)vA; bndA = bound_of(nA2); }
-        if (nB2 < bestB) { bestB = nB2; slotB = (uint32_t)vB; bndB = bound_of(nB2); }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float n2 = __uint_as_float((unsigned)(v[i] >> 32));
+            if (n2 < best2[i]) { best2[i] = n2; slot[i] = (uint32_t)v[i]; bnd[i] = bound_of(n2); }
+        }
         __syncwarp();
         max_b = warp_max_b();
     };
@@ -939,42 +964,55 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
         const float4 q4 = ldg4(nd + 4), q5 = ldg4(nd + 5), q6 = ldg4(nd + 6), q7 = ldg4(nd + 7);
         const float2 m1 = make_float2(-1.0f, -1.0f);
         // low half: left child, high half: right child
-        const float2 dx = __ffma2_rn(f2lo(q0), m1, make_float2(pA.x, pA.x));
-        const float2 dy = __ffma2_rn(f2hi(q0), m1, make_float2(pA.y, pA.y));
-        const float2 dz = __ffma2_rn(f2lo(q1), m1, make_float2(pA.z, pA.z));
+        const float2 dx = __ffma2_rn(f2lo(q0), m1, make_float2(p0.x, p0.x));
+        const float2 dy = __ffma2_rn(f2hi(q0), m1, make_float2(p0.y, p0.y));
+        const float2 dz = __ffma2_rn(f2lo(q1), m1, make_float2(p0.z, p0.z));
         const float2 tu = __ffma2_rn(dz, f2lo(q3), __ffma2_rn(dy, f2hi(q2), __fmul2_rn(dx, f2lo(q2))));
         const float2 tv = __ffma2_rn(dz, f2lo(q5), __ffma2_rn(dy, f2hi(q4), __fmul2_rn(dx, f2lo(q4))));
         const float2 tw = __ffma2_rn(dz, f2lo(q7), __ffma2_rn(dy, f2hi(q6), __fmul2_rn(dx, f2lo(q6))));
-        const float2 dl2 = make_float2(delta, delta);
-        const float2 tuB = __ffma2_rn(dl2, EXT == 0 ? f2lo(q2) : f2lo(q3), tu);
-        const float2 tvB = __ffma2_rn(dl2, EXT == 0 ? f2lo(q4) : f2lo(q5), tv);
-        const float2 twB = __ffma2_rn(dl2, EXT == 0 ? f2lo(q6) : f2lo(q7), tw);
         const float2 eu = f2hi(q3), ev = f2hi(q5), ew = f2hi(q7);
-        const float2 dA = sumsq2(excess2(tu, eu), excess2(tv, ev), excess2(tw, ew));
-        const float2 dB = sumsq2(excess2(tuB, eu), excess2(tvB, ev), excess2(twB, ew));
-        const bool hAl = dA.x <= bndA, hAr = dA.y <= bndA, hBl = dB.x <= bndB, hBr = dB.y <= bndB;
-        unsigned bl = __ballot_sync(full, hAl || hBl), br = __ballot_sync(full, hAr || hBr);
+        float2 dd[V];  // squared lower bounds of voxel i: (left child, right child)
+        dd[0] = sumsq2(excess2(tu, eu), excess2(tv, ev), excess2(tw, ew));
+#pragma unroll
+        for (int i = 1; i < V; ++i) {
+            const float2 s2 = make_float2(step[i], step[i]);
+            dd[i] = sumsq2(excess2(__ffma2_rn(s2, f2lo(q3), tu), eu), excess2(__ffma2_rn(s2, f2lo(q5), tv), ev),
+                           excess2(__ffma2_rn(s2, f2lo(q7), tw), ew));
+        }
+        unsigned hl = 0u, hr = 0u;  // bit i: voxel i wants the left / right child
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            hl |= dd[i].x <= bnd[i] ? 1u << i : 0u;
+            hr |= dd[i].y <= bnd[i] ? 1u << i : 0u;
+        }
+        unsigned bl = __ballot_sync(full, hl != 0u), br = __ballot_sync(full, hr != 0u);
         const uint32_t lref = __float_as_uint(q1.z), rref = __float_as_uint(q1.w);
-        if (lref & LEAF_BIT) {
-            if (bl) {
-                enqueue2(hAl, hBl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                PKT_COUNT(n_leaves);
+        if ((lref | rref) & LEAF_BIT) {
+            if (lref & LEAF_BIT) {
+                if (bl) {
+                    enqueue(hl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    PKT_COUNT(n_leaves);
+                }
+                bl = 0u;
             }
-            bl = 0u;
-        }
-        if (rref & LEAF_BIT) {
-            if (br) {
-                enqueue2(hAr, hBr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                PKT_COUNT(n_leaves);
+            if (rref & LEAF_BIT) {
+                if (br) {
+                    enqueue(hr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    PKT_COUNT(n_leaves);
+                }
+                br = 0u;
             }
-            br = 0u;
+            if (qn >= 32) flush(false);
         }
-        if (qn >= 32) flush(false);
         if (bl && br) {
             // children ordered by the warp-min lower bound over the voxels that want them
-            const unsigned kl = min(hAl ? __float_as_uint(dA.x) : 0x7f800000u, hBl ? __float_as_uint(dB.x) : 0x7f800000u);
-            const unsigned kr = min(hAr ? __float_as_uint(dA.y) : 0x7f800000u, hBr ? __float_as_uint(dB.y) : 0x7f800000u);
-            const unsigned ml = __reduce_min_sync(full, kl), mr = __reduce_min_sync(full, kr);
+            float kl = INFINITY, kr = INFINITY;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                kl = fminf(kl, (hl >> i) & 1u ? dd[i].x : INFINITY);
+                kr = fminf(kr, (hr >> i) & 1u ? dd[i].y : INFINITY);
+            }
+            const unsigned ml = __reduce_min_sync(full, __float_as_uint(kl)), mr = __reduce_min_sync(full, __float_as_uint(kr));
             const bool left_first = ml <= mr;
             if (sp < PKT_STACK) {
                 if (lane == 0) stack[sp] = left_first ? make_uint2(rref, mr) : make_uint2(lref, ml);
@@ -1006,29 +1044,40 @@ k_grid_nearest_pk2(const Bvh bvh, const GridParams g, const float grid_mag, cons
     }
     flush(true);
 
-    // publish the x-far voxels' nearest triangles for the brick one step further in x
-    if (tile_slot && lane >= 16u && (EXT == 0 || (warp & 2u))) {
-        if (EXT == 0 ? validB : validA)
-            __stcg(tile_slot + ((size_t)blockIdx.x * 4u + warp) * 16u + (lane & 15u), EXT == 0 ? slotB : slotA);
+    // publish the x-far voxels' nearest triangles for the bricks further in x
+    if (tile_slot && (LAYOUT == 0 ? (lane >= 16u && (warp & 2u)) : lane >= 24u)) {
+        // the middle voxel of the run (the first one where the run is cut by the grid's end)
+        if (valid[0]) __stcg(tile_slot + ((size_t)blockIdx.x * 4u + warp) * 16u + src_idx, valid[V / 2] ? slot[V / 2] : slot[0]);
     }
 
     // sqrt is monotone: min sqrt = sqrt min (finish<MODE_UNSIGNED>)
-    float outA = __fsqrt_rn(bestA), outB = __fsqrt_rn(bestB);
-    if (RAYSIGN) {
-        // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd.
+    float res[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) res[i] = __fsqrt_rn(best2[i]);
+    if (RAYSIGN && valid[0]) {
+        // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd. The Z row of the run
+        // is one row: its bits z0 .. z0+V-1 sit in one word (V divides 32)
         const uint32_t rows_x = g.ny * g.nz, rows_y = g.nx * g.nz, rows_z = g.nx * g.ny;
-        auto inside = [&](uint32_t vx, uint32_t vz) {
-            const uint32_t rowx = y * g.nz + vz, rowy = vx * g.nz + vz, rowz = vx * g.ny + y;
-            const uint32_t hx = (px[(size_t)(vx >> 5) * rows_x + rowx] >> (vx & 31)) & 1u;
-            const uint32_t hy = (py[(size_t)(y >> 5) * rows_y + rowy] >> (y & 31)) & 1u;
-            const uint32_t hz = (pz[(size_t)(vz >> 5) * rows_z + rowz] >> (vz & 31)) & 1u;
-            return hx + hy + hz >= 2u;
-        };
-        if (validA && inside(x, z)) outA = -outA;
-        if (validB && inside(xB, zB)) outB = -outB;
+        const uint32_t wz = pz[(size_t)(z0 >> 5) * rows_z + (x * g.ny + y)] >> (z0 & 31u);
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            if (valid[i]) {
+                const uint32_t z = z0 + i;
+                const uint32_t hx = (px[(size_t)(x >> 5) * rows_x + (y * g.nz + z)] >> (x & 31u)) & 1u;
+                const uint32_t hy = (py[(size_t)(y >> 5) * rows_y + (x * g.nz + z)] >> (y & 31u)) & 1u;
+                if (hx + hy + ((wz >> i) & 1u) >= 2u) res[i] = -res[i];
+            }
     }
-    if (validA) out[((size_t)xr * g.ny + y) * g.nz + z] = outA;
-    if (validB) out[((size_t)(xB - g.x0) * g.ny + y) * g.nz + zB] = outB;
+    float* const o = out + ((size_t)xr * g.ny + y) * g.nz + z0;
+    if (V == 4 && valid[3] && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+        *reinterpret_cast<float4*>(o) = make_float4(res[0], res[1], res[2], res[3]);
+    } else if (V == 2 && valid[1] && (reinterpret_cast<uintptr_t>(o) & 7u) == 0) {
+        *reinterpret_cast<float2*>(o) = make_float2(res[0], res[1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            if (valid[i]) o[i] = res[i];
+    }
     if (overflow) atomicExch(&st->stack_overflow, 1);
     if (bvh.stats && lane == 0) {
         atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
@@ -1407,21 +1456,35 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
     BuildStatus* st = d.status.as<BuildStatus>();
     const unsigned nb = (unsigned)nblocks;
     if (d.packet && d.pair && grid_uses_neighbour_seeds(d, mode) && d.bvh.leaf_size == 1u && d.bvh.nleaf >= 2u) {
-        // two voxels per lane; the tile is extended along z when the cells are flat in z, else along x
-        CK(d.tile_slot.ensure((size_t)nb * 4 * 16 * 4));
-        CK(cudaMemsetAsync(d.tile_slot.p, 0xff, (size_t)nb * 4 * 16 * 4, s));
+        // several voxels per lane. M2S_PAIR: 1 = default (V, LAYOUT) = (2, 0); 4..7 = (2,0) (2,1) (4,0) (4,1)
+        const int variant = d.pair < 4 ? 4 : d.pair;
+        const uint32_t V = variant >= 6 ? 4u : 2u;
+        const uint32_t bzr = 4u * V;
+        const uint64_t nrun = (uint64_t)cdiv(g.xb - g.xa, BX) * cdiv(g.ny, BY) * cdiv(g.nz, bzr);
+        if (nrun > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+        const unsigned nbr = (unsigned)nrun;
+        CK(d.tile_slot.ensure((size_t)nbr * 4 * 16 * 4));
+        CK(cudaMemsetAsync(d.tile_slot.p, 0xff, (size_t)nbr * 4 * 16 * 4, s));
         uint32_t* tile_slot = d.tile_slot.as<uint32_t>();
-        const bool ext_z = d.pair == 3 || (d.pair == 1 && fabsf(g.sz) * 1.5f <= fabsf(g.sx));
         const uint32_t *b0 = rb ? rb->bits[0] : nullptr, *b1 = rb ? rb->bits[1] : nullptr, *b2 = rb ? rb->bits[2] : nullptr;
         // seeds come from the brick `planes` steps back in x: far enough in dispatch order to have finished
         // (about 1.25 x the resident blocks), at most 4 steps (16 cells)
-        const uint32_t plane_bricks = cdiv(g.ny, BY) * cdiv(g.nz, BZ);
-        const uint32_t planes = std::min(4u, std::max(1u, cdiv((uint32_t)d.sm_count * PK2_MIN_BLOCKS * 5u / 4u, plane_bricks)));
+        const uint32_t plane_bricks = cdiv(g.ny, BY) * cdiv(g.nz, bzr);
+        const uint32_t resident = (uint32_t)d.sm_count * (V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS);
+        const uint32_t planes = std::min(4u, std::max(1u, cdiv(resident * 5u / 4u, plane_bricks)));
         CK(launch_nodes_interleave(d, mag));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
-        if (rb && ext_z) k_grid_nearest_pk2<true, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
-        else if (rb) k_grid_nearest_pk2<true, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
-        else if (ext_z) k_grid_nearest_pk2<false, 2><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
-        else k_grid_nearest_pk2<false, 0><<<nb, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes);
+#define M2S_RUN(RS, VV, LL) k_grid_nearest_run<RS, VV, LL><<<nbr, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes)
+        switch (variant * 2 + (rb ? 1 : 0)) {
+            case 8: M2S_RUN(false, 2, 0); break;
+            case 9: M2S_RUN(true, 2, 0); break;
+            case 10: M2S_RUN(false, 2, 1); break;
+            case 11: M2S_RUN(true, 2, 1); break;
+            case 12: M2S_RUN(false, 4, 0); break;
+            case 13: M2S_RUN(true, 4, 0); break;
+            case 14: M2S_RUN(false, 4, 1); break;
+            default: M2S_RUN(true, 4, 1); break;
+        }
+#undef M2S_RUN
     } else if (d.packet) {
         uint32_t* tile_slot = nullptr;
         if (grid_uses_neighbour_seeds(d, mode)) {

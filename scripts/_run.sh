@@ -1,5 +1,3 @@
-M2S_LIB=build/libm2s_stats.so python scripts/stats_pair.py 3
-for p in 2 3; do
-  M2S_PAIR=$p timeout 300 python -m pytest tests/test_gpu_grid.py tests/test_gpu_edge.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -2
-done
-M2S_PAIR=3 REPS=4 python scripts/quick_perf.py C3 C5 2>&1 | grep -E "rep[123]"
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/r1g_bench.json 2> gpurun_out/r1g_bench.err; cat gpurun_out/r1g_bench.json
+python scripts/quick_perf.py C2 C4 C5 2>&1 | grep -E "rep[12]"

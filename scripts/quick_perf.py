@@ -5,9 +5,12 @@ import numpy as np
 import mesh_to_sdf_b200 as m2s
 from mesh_to_sdf_b200 import synth
 
-def run_grid(name, nu, nv, n, sign, reps=int(os.environ.get("REPS", "3"))):
+def run_grid(name, nu, nv, n, sign, reps=int(os.environ.get("REPS", "3")), cubic=False):
     verts, tris = synth.bumpy_torus(nu, nv)
     mn, mx = synth.padded_grid_box(verts)
+    if cubic:  # isotropic cells: the box grown to a cube around its centre
+        c, h = 0.5 * (mn + mx), 0.5 * float(np.max(mx - mn))
+        mn, mx = (c - h).astype(np.float32), (c + h).astype(np.float32)
     grid = m2s.Grid.from_bounding_box(mn, mx, [n, n, n])
     ctx = m2s.default_context()
     out = np.empty(n ** 3, np.float32)
@@ -37,6 +40,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["C2", "C3", "C4"]
     if "C2" in which: run_grid("C2", 64, 40, 128, 1)
     if "C3" in which: run_grid("C3", 256, 196, 256, 0)
+    if "C3I" in which: run_grid("C3I", 256, 196, 256, 0, cubic=True)
     if "C3N" in which: run_grid("C3N", 256, 196, 256, 1)
     if "C4" in which: run_points("C4", 640, 392, 1_000_000, 3, 0)
     if "C5" in which: run_grid("C5", 1024, 490, 512, 0, reps=2)

@@ -135,3 +135,27 @@ def test_device_entry_defers_data_errors(m2s):
         assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
         t = c.timings()
         assert t["total_ms"] > 0 and c.launch_count > 0
+
+
+@pytest.mark.parametrize("pair", ["0", "1", "4", "5", "6", "7"])
+@pytest.mark.parametrize("dims", [(37, 21, 30), (9, 50, 5), (64, 64, 64)])
+def test_every_grid_kernel_variant_bit_exact(m2s, oracle, monkeypatch, pair, dims):
+    # M2S_PAIR picks the distance kernel (one voxel per lane / runs of 2 or 4 voxels, two lane layouts); every
+    # variant must give the exact oracle's bits, on ragged grids (runs cut by the grid's end) and slab by slab
+    monkeypatch.setenv("M2S_PAIR", pair)
+    verts, tris = synth.bumpy_torus(40, 24)
+    grid = _grid_for(m2s, verts, list(dims))
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, RAYCAST)
+    with m2s.Context() as c:
+        got = c.grid_sdf(verts, tris, grid, RAYCAST)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        torch = pytest.importorskip("torch")
+        dv = torch.from_numpy(verts).cuda()
+        dt = torch.from_numpy(tris.view(np.int32)).cuda()
+        plane = dims[1] * dims[2]
+        x0, x1 = dims[0] // 3, dims[0] - 2
+        out = torch.empty((x1 - x0) * plane, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        c.grid_sdf_device(dv.data_ptr(), len(verts), dt.data_ptr(), len(tris), grid, RAYCAST, x0, x1, out.data_ptr())
+        c.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want[x0 * plane:x1 * plane].view(np.uint32))

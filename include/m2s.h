@@ -155,6 +155,36 @@ M2S_API m2s_status m2s_generate_sdf_device(m2s_ctx* ctx, const float* d_verts_xy
  * enqueued since the previous m2s_synchronize (M2S_OK, M2S_EINDEX, M2S_ENAN or M2S_ECUDA). */
 M2S_API m2s_status m2s_synchronize(m2s_ctx* ctx);
 
+/* ---- post-passes on a finished grid SDF (what the reference's in-repo caller runs next) ------------------
+ * The reference's only caller of generate_grid_sdf (mesh_to_sdf_client/src/sdf.rs:50-123) sorts the cell
+ * indices by distance, takes min / max and re-uploads the Vec to a GPU buffer that its shaders sample. These
+ * entry points do the same work on the grid while it is still on the device. `*_device` variants take device
+ * pointers on a single-device context and only enqueue on its stream (like the entry points above). */
+
+/* order[i] = index of the i-th cell in ascending distance: `(0..n).sorted_by(|i, j| data[i].total_cmp(&data[j]))`
+ * (stable: equal values keep index order), mesh_to_sdf_client/src/sdf.rs:65-68. minmax = {min, max} as
+ * `data.iter().copied().minmax()` returns them (:123; -0.0 == +0.0 there: the first minimum / last maximum wins).
+ * Either output may be NULL. n < 2^31. NaN distances: order follows total_cmp, minmax is unspecified. */
+M2S_API m2s_status m2s_grid_order(m2s_ctx* ctx, const float* sdf, uint64_t n, uint32_t* order, float minmax[2]);
+M2S_API m2s_status m2s_grid_order_device(m2s_ctx* ctx, const float* d_sdf, uint64_t n, uint32_t* d_order,
+                                         float* d_minmax);
+
+/* raymarch_mode of mesh_to_sdf_client/shaders/draw_raymarching.wgsl (MODE_SNAP / MODE_TRILINEAR / MODE_TETRAHEDRAL) */
+typedef enum m2s_sample_mode { M2S_SAMPLE_SNAP = 0, M2S_SAMPLE_TRILINEAR = 1, M2S_SAMPLE_TETRAHEDRAL = 2 } m2s_sample_mode;
+
+/* out[i] = sdf_grid(points[i], iso) of draw_raymarching.wgsl:118-200: 100.0 outside [first_cell,
+ * Grid::get_last_cell()], else the grid value (minus iso) snapped to the containing cell / interpolated on the
+ * dual grid of cell centres with border clamping (:92-99) trilinearly or over the six-tetrahedra split
+ * (:585-650). This is the "distance from any point with interpolation" the reference lists as TODO
+ * (mesh_to_sdf/src/grid.rs:172). Arithmetic is un-fused fp32 in the shader's evaluation order. */
+M2S_API m2s_status m2s_sample_grid_sdf(m2s_ctx* ctx, const float* sdf, const float first_cell[3],
+                                       const float cell_size[3], const uint64_t cell_count[3],
+                                       const float* points_xyz, uint64_t np, int sample_mode, float iso, float* out);
+M2S_API m2s_status m2s_sample_grid_sdf_device(m2s_ctx* ctx, const float* d_sdf, const float first_cell[3],
+                                              const float cell_size[3], const uint64_t cell_count[3],
+                                              const float* d_points_xyz, uint64_t np, int sample_mode, float iso,
+                                              float* d_out);
+
 /* ---- host-side helpers the facade shares with the tests --------------------------------------------- */
 
 /* Topology::get_triangles, src/lib.rs:175-193. `indices == NULL` is `None` (0..nv). index_bytes is 2

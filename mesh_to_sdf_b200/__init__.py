@@ -90,6 +90,10 @@ def lib() -> C.CDLL:
                                                        C.c_uint64, C.c_uint64, vp]
             L.m2s_generate_sdf_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, C.c_int,
                                                   C.c_int, vp]
+            L.m2s_grid_order.argtypes = [vp, vp, C.c_uint64, vp, vp]
+            L.m2s_grid_order_device.argtypes = [vp, vp, C.c_uint64, vp, vp]
+            L.m2s_sample_grid_sdf.argtypes = [vp, vp, _f, _f, _u64, vp, C.c_uint64, C.c_int, C.c_float, vp]
+            L.m2s_sample_grid_sdf_device.argtypes = [vp, vp, _f, _f, _u64, vp, C.c_uint64, C.c_int, C.c_float, vp]
             L.m2s_expand_topology.argtypes = [C.c_int, vp, C.c_int, C.c_uint64, C.c_uint64, _u32]
             L.m2s_expand_topology.restype = C.c_uint64
             L.m2s_grid_from_bounding_box.argtypes = [_f, _f, _u64, _f, _f]
@@ -376,6 +380,40 @@ class Context:
                                                   int(sign), d_out))
 
 
+    # post-passes on a finished grid (what the reference's in-repo caller runs next, mesh_to_sdf_client/src/sdf.rs)
+    def grid_order(self, sdf, want_order: bool = True, want_minmax: bool = True):
+        """(ordered cell indices by ascending distance (stable, f32::total_cmp), (min, max)) - sdf.rs:65-68, :123."""
+        sdf = np.ascontiguousarray(sdf, np.float32).reshape(-1)
+        order = np.empty(len(sdf), np.uint32) if want_order else None
+        mm = np.zeros(2, np.float32) if want_minmax else None
+        self._check(lib().m2s_grid_order(self._h, sdf.ctypes.data, len(sdf), order.ctypes.data if want_order else None,
+                                         mm.ctypes.data if want_minmax else None))
+        return order, (None if mm is None else (mm[0], mm[1]))
+
+    def grid_order_device(self, d_sdf: int, n: int, d_order: int, d_minmax: int):
+        self._check(lib().m2s_grid_order_device(self._h, d_sdf, n, d_order or None, d_minmax or None))
+
+    def sample_grid_sdf(self, sdf, grid: Grid, points, mode: int = 1, iso: float = 0.0) -> np.ndarray:
+        """sdf_grid() of draw_raymarching.wgsl:118-200 at arbitrary points; mode 0 snap, 1 trilinear, 2 tetrahedral."""
+        sdf = np.ascontiguousarray(sdf, np.float32).reshape(-1)
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        cc = np.asarray(grid.cell_count, np.uint64)
+        if len(sdf) != int(np.prod(cc)):
+            raise ValueError("sdf length does not match the grid")
+        out = np.empty(len(pts), np.float32)
+        self._check(lib().m2s_sample_grid_sdf(self._h, sdf.ctypes.data, grid.first_cell.ctypes.data_as(_f),
+                                              grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
+                                              pts.ctypes.data, len(pts), int(mode), float(iso), out.ctypes.data))
+        return out
+
+    def sample_grid_sdf_device(self, d_sdf: int, grid: Grid, d_points: int, n_points: int, mode: int, iso: float,
+                               d_out: int):
+        cc = np.asarray(grid.cell_count, np.uint64)
+        self._check(lib().m2s_sample_grid_sdf_device(self._h, d_sdf, grid.first_cell.ctypes.data_as(_f),
+                                                     grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
+                                                     d_points, n_points, int(mode), float(iso), d_out))
+
+
 def _mesh_arrays(verts, tris):
     verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
     tris = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
@@ -396,6 +434,13 @@ def default_context() -> Context:
             devices = [int(t) for t in env.split(",") if t.strip() != ""] if env else None
             _default_ctx = Context(devices)
     return _default_ctx
+
+
+class SampleMode(enum.IntEnum):
+    """``raymarch_mode`` of mesh_to_sdf_client/shaders/draw_raymarching.wgsl."""
+    Snap = 0
+    Trilinear = 1
+    Tetrahedral = 2
 
 
 # ---- the two public free functions ----------------------------------------------------------------------------

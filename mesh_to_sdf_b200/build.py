@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libm2s.so")
-SOURCES = ["m2s_build.cu", "m2s_query.cu", "m2s_api.cu"]
+SOURCES = ["m2s_build.cu", "m2s_query.cu", "m2s_post.cu", "m2s_api.cu"]
 HEADERS = ["m2s_geom.cuh", "m2s_internal.h", os.path.join("..", "..", "include", "m2s.h")]
 
 NVCC_FLAGS = [

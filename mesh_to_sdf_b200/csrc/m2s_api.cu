@@ -314,7 +314,8 @@ void m2s_destroy(m2s_ctx* ctx) {
                           &d.keys_out, &d.vals_in, &d.vals_out, &d.cub_tmp, &d.tri_id_sorted, &d.nodes, &d.nodes_il,
                           &d.leaf_parent, &d.node_parent, &d.node_flag, &d.status, &d.rows[0], &d.rows[1],
                           &d.rows[2], &d.big_list, &d.big_count, &d.queries, &d.q_sorted, &d.q_perm,
-                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.tobb, &d.boxes, &d.tile_slot};
+                          &d.q_keys_in, &d.q_keys_out, &d.q_vals_in, &d.out, &d.seeds[0], &d.seeds[1], &d.stats, &d.node_range, &d.tobb, &d.boxes, &d.tile_slot,
+                          &d.post_keys, &d.post_idx, &d.post_mm, &d.post_in, &d.post_pts, &d.post_out};
         for (DevBuf* b : bufs) b->release();
         if (d.h_status) cudaFreeHost(d.h_status);
         for (int k = 0; k < 8; ++k)
@@ -585,6 +586,104 @@ m2s_status m2s_synchronize(m2s_ctx* ctx) {
         }
     }
     return result;
+}
+
+// ---- post-passes on a finished grid -------------------------------------------------------------------
+
+static m2s_status post_ctx(m2s_ctx* ctx) {
+    if (ctx->n_devices != 1) return fail(ctx, M2S_EINVAL, "post-pass entry points need a single-device context");
+    return M2S_OK;
+}
+
+m2s_status m2s_grid_order_device(m2s_ctx* ctx, const float* d_sdf, uint64_t n, uint32_t* d_order, float* d_minmax) {
+    if (!ctx) return M2S_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->last_error.clear();
+    if (post_ctx(ctx) != M2S_OK) return M2S_EINVAL;
+    if (n >= (1ull << 31)) return fail(ctx, M2S_EINVAL, "more than 2^31-1 cells");
+    if (n == 0) return M2S_OK;
+    if (!d_sdf) return fail(ctx, M2S_EINVAL, "null sdf pointer");
+    Device& d = ctx->dev[0];
+    CU(ctx, cudaSetDevice(d.ordinal));
+    CU(ctx, launch_grid_order(d, d_sdf, n, d_order, d_minmax));
+    return M2S_OK;
+}
+
+m2s_status m2s_grid_order(m2s_ctx* ctx, const float* sdf, uint64_t n, uint32_t* order, float minmax[2]) {
+    if (!ctx) return M2S_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->last_error.clear();
+    if (post_ctx(ctx) != M2S_OK) return M2S_EINVAL;
+    if (n >= (1ull << 31)) return fail(ctx, M2S_EINVAL, "more than 2^31-1 cells");
+    if (n == 0) return M2S_OK;
+    if (!sdf) return fail(ctx, M2S_EINVAL, "null sdf pointer");
+    Device& d = ctx->dev[0];
+    CU(ctx, cudaSetDevice(d.ordinal));
+    CU(ctx, d.post_in.ensure(n * 4));
+    CU(ctx, d.post_out.ensure(n * 4 + 8));
+    CU(ctx, cudaMemcpyAsync(d.post_in.p, sdf, n * 4, cudaMemcpyHostToDevice, d.stream));
+    uint32_t* d_order = order ? d.post_out.as<uint32_t>() : nullptr;
+    float* d_mm = minmax ? reinterpret_cast<float*>(d.post_out.as<uint32_t>() + n) : nullptr;
+    CU(ctx, launch_grid_order(d, d.post_in.as<float>(), n, d_order, d_mm));
+    if (order) CU(ctx, cudaMemcpyAsync(order, d_order, n * 4, cudaMemcpyDeviceToHost, d.stream));
+    if (minmax) CU(ctx, cudaMemcpyAsync(minmax, d_mm, 8, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return M2S_OK;
+}
+
+static m2s_status check_sample(m2s_ctx* ctx, const float first[3], const float size[3], const uint64_t count[3],
+                               int mode, uint64_t np, GridArgs* ga) {
+    if (post_ctx(ctx) != M2S_OK) return M2S_EINVAL;
+    if (mode != M2S_SAMPLE_SNAP && mode != M2S_SAMPLE_TRILINEAR && mode != M2S_SAMPLE_TETRAHEDRAL)
+        return fail(ctx, M2S_EINVAL, "unknown sample mode");
+    if (np > 0xffffffffull) return fail(ctx, M2S_EINVAL, "more than 2^32 sample points");
+    m2s_status s = check_grid(ctx, first, size, count, M2S_SIGN_RAYCAST, ga);
+    if (s != M2S_OK) return s;
+    if (ga->total == 0 && np > 0) return fail(ctx, M2S_EINVAL, "sampling an empty grid");
+    return M2S_OK;
+}
+
+m2s_status m2s_sample_grid_sdf_device(m2s_ctx* ctx, const float* d_sdf, const float first_cell[3],
+                                      const float cell_size[3], const uint64_t cell_count[3],
+                                      const float* d_points_xyz, uint64_t np, int sample_mode, float iso,
+                                      float* d_out) {
+    if (!ctx) return M2S_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->last_error.clear();
+    GridArgs ga{};
+    m2s_status s = check_sample(ctx, first_cell, cell_size, cell_count, sample_mode, np, &ga);
+    if (s != M2S_OK) return s;
+    if (np == 0) return M2S_OK;
+    if (!d_sdf || !d_points_xyz || !d_out) return fail(ctx, M2S_EINVAL, "null sdf / point / output pointer");
+    Device& d = ctx->dev[0];
+    CU(ctx, cudaSetDevice(d.ordinal));
+    CU(ctx, launch_grid_sample(d, d_sdf, ga.g, d_points_xyz, np, sample_mode, iso, d_out));
+    return M2S_OK;
+}
+
+m2s_status m2s_sample_grid_sdf(m2s_ctx* ctx, const float* sdf, const float first_cell[3], const float cell_size[3],
+                               const uint64_t cell_count[3], const float* points_xyz, uint64_t np, int sample_mode,
+                               float iso, float* out) {
+    if (!ctx) return M2S_EINVAL;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->last_error.clear();
+    GridArgs ga{};
+    m2s_status s = check_sample(ctx, first_cell, cell_size, cell_count, sample_mode, np, &ga);
+    if (s != M2S_OK) return s;
+    if (np == 0) return M2S_OK;
+    if (!sdf || !points_xyz || !out) return fail(ctx, M2S_EINVAL, "null sdf / point / output pointer");
+    Device& d = ctx->dev[0];
+    CU(ctx, cudaSetDevice(d.ordinal));
+    CU(ctx, d.post_in.ensure(ga.total * 4));
+    CU(ctx, d.post_pts.ensure(np * 12));
+    CU(ctx, d.post_out.ensure(np * 4));
+    CU(ctx, cudaMemcpyAsync(d.post_in.p, sdf, ga.total * 4, cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaMemcpyAsync(d.post_pts.p, points_xyz, np * 12, cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, launch_grid_sample(d, d.post_in.as<float>(), ga.g, d.post_pts.as<float>(), np, sample_mode, iso,
+                               d.post_out.as<float>()));
+    CU(ctx, cudaMemcpyAsync(out, d.post_out.p, np * 4, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return M2S_OK;
 }
 
 // ---- host-side helpers ---------------------------------------------------------------------------------

@@ -140,6 +140,7 @@ struct Device {
     uint32_t seed_stride = 4;  // voxels per seed block edge (M2S_SEED_STRIDE)
     int seed_levels = 1;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
+    DevBuf post_keys, post_idx, post_mm, post_in, post_pts, post_out;  // post-passes (m2s_post.cu) and their host staging
     BuildStatus* h_status = nullptr;  // pinned
     cudaEvent_t ev[8] = {};
     cudaStream_t aux_stream = nullptr;   // high priority: the second half's seed pass hides under the first half's kernel
@@ -181,6 +182,11 @@ cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float
                           cudaEvent_t after_seeds = nullptr);
 
 cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value);
+
+// post-passes on a device-resident grid (m2s_post.cu)
+cudaError_t launch_grid_order(Device& d, const float* d_sdf, uint64_t n, uint32_t* d_order, float* d_minmax);
+cudaError_t launch_grid_sample(Device& d, const float* d_sdf, const GridParams& g, const float* d_points, uint64_t np,
+                               int mode, float iso, float* d_out);
 
 }  // namespace m2s
 

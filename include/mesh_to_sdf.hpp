@@ -223,4 +223,42 @@ std::vector<float> generate_grid_sdf(const std::vector<V>& vertices, Topology<I>
     return out;
 }
 
+// ---- post-passes on a finished grid: what the reference's in-repo caller does next ------------------------------
+// (not part of the crate's API: mesh_to_sdf_client/src/sdf.rs:62-68, :123 and shaders/draw_raymarching.wgsl:118-200)
+
+struct GridOrder {
+    std::vector<uint32_t> ordered_indices;  // (0..n).sorted_by(|i, j| data[i].total_cmp(&data[j]))
+    float min, max;                         // data.iter().copied().minmax()
+};
+inline GridOrder grid_order(const std::vector<float>& sdf) {
+    GridOrder r{std::vector<uint32_t>(sdf.size()), 0.0f, 0.0f};
+    float mm[2] = {0.0f, 0.0f};
+    m2s_ctx* c = detail::context();
+    detail::check(c, m2s_grid_order(c, sdf.data(), sdf.size(), r.ordered_indices.data(), mm));
+    r.min = mm[0];
+    r.max = mm[1];
+    return r;
+}
+
+enum class SampleMode { Snap = 0, Trilinear = 1, Tetrahedral = 2 };  // raymarch_mode of draw_raymarching.wgsl
+
+// sdf_grid(position, iso) at every point: 100.0 outside [first_cell, last_cell], else the snapped / interpolated
+// grid value minus iso — the "distance from any point with interpolation" of the TODO at src/grid.rs:172.
+template <class V>
+std::vector<float> sample_grid_sdf(const std::vector<float>& sdf, const Grid<V>& grid, const std::vector<V>& points,
+                                   SampleMode mode = SampleMode::Trilinear, float iso = 0.0f) {
+    using T = point_traits<V>;
+    if (sdf.size() != grid.get_total_cell_count()) throw Panic(M2S_EINVAL, "sdf length does not match the grid");
+    const V f = grid.get_first_cell(), s = grid.get_cell_size();
+    const float first[3] = {T::x(f), T::y(f), T::z(f)}, size[3] = {T::x(s), T::y(s), T::z(s)};
+    const auto n = grid.get_cell_count();
+    const uint64_t count[3] = {n[0], n[1], n[2]};
+    const std::vector<float> p = detail::pack(points);
+    std::vector<float> out(points.size());
+    m2s_ctx* c = detail::context();
+    detail::check(c, m2s_sample_grid_sdf(c, sdf.data(), first, size, count, p.data(), points.size(), (int)mode, iso,
+                                         out.data()));
+    return out;
+}
+
 }  // namespace mesh_to_sdf

@@ -83,7 +83,29 @@ static void test_panics() {
     CHECK(generate_sdf(vertices, Topology<uint32_t>::triangle_list(), q)[0] == 1.0f);  // TriangleList(None), default method
 }
 
+// the caller-side post-passes (mesh_to_sdf_client/src/sdf.rs:62-68, :123; draw_raymarching.wgsl:118-200)
+static void test_post_passes() {
+    std::vector<V3> vertices = {{0.5f, 1.5f, 0.5f}, {1.f, 2.f, 3.f}, {1.f, 3.f, 7.f}};
+    std::vector<uint32_t> indices = {0, 1, 2};
+    auto grid = Grid<V3>::from_bounding_box({0.f, 0.f, 0.f}, {10.f, 10.f, 10.f}, {6, 5, 4});
+    const auto sdf = generate_grid_sdf(vertices, Topology<uint32_t>::triangle_list(indices), grid, SignMethod::Raycast);
+    const GridOrder o = grid_order(sdf);
+    CHECK(o.ordered_indices.size() == sdf.size());
+    for (size_t i = 1; i < sdf.size(); ++i) {
+        const float a = sdf[o.ordered_indices[i - 1]], b = sdf[o.ordered_indices[i]];
+        CHECK(a < b || (a == b && o.ordered_indices[i - 1] < o.ordered_indices[i]));  // sorted, stable
+    }
+    CHECK(o.min == sdf[o.ordered_indices.front()] && o.max == sdf[o.ordered_indices.back()]);
+    // every mode returns the cell's own value at a cell centre, 100 outside the grid
+    std::vector<V3> pts = {grid.get_cell_center({2, 3, 1}), {-5.f, 0.f, 0.f}};
+    for (SampleMode m : {SampleMode::Snap, SampleMode::Trilinear, SampleMode::Tetrahedral}) {
+        const auto s = sample_grid_sdf(sdf, grid, pts, m);
+        CHECK(std::fabs(s[0] - sdf[grid.get_cell_idx({2, 3, 1})]) <= 1e-6f && s[1] == 100.0f);
+    }
+}
+
 int main() {
+    test_post_passes();
     doc_generate_sdf();
     doc_generate_grid_sdf();
     test_generate_grid();

@@ -297,7 +297,7 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mvoxels/s", "h2d_bytes_per_step": int(12 * len(verts) + 12 * len(tris)),
                 "d2h_bytes_per_step": int(4 * slab_cells), "ms_per_step": float(e2e_t.item()) / args.steps * 1e3,
-                "api": "m2s_generate_grid_sdf_slab (host buffers, pinned)", "phases_ms_last": e2e_phase,
+                "api": "m2s_generate_grid_sdf_slab (host buffers, pinned; H2D copy of the mesh, the result written into the pinned destination by the kernel's own stores over PCIe)", "phases_ms_last": e2e_phase,
                 "checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -147,6 +147,7 @@ struct Device {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_half[2] = {};
     bool split_halves = true;            // M2S_SPLIT=0: one seed pass + one distance launch per slab
     bool last_split = false;
+    bool zero_copy = true;               // M2S_ZEROCOPY=0: stage + copy even when the host destination is pinned
     cudaStream_t copy_stream = nullptr;  // D2H of finished x-chunks overlaps the next chunk's kernel
     cudaEvent_t ev_chunk[8] = {};
     cudaEvent_t ev_copied = nullptr;

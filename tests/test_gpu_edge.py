@@ -168,3 +168,28 @@ def test_random_triangle_soup(m2s, oracle, seed):
     g = m2s.default_context().sdf(verts, tris, q, 2, 0)
     w = oracle.generate_sdf(verts, tris, q, 2, 0)
     assert np.array_equal(np.abs(g).view(np.uint32), np.abs(w).view(np.uint32))
+
+
+def test_pinned_destination_is_written_in_place(m2s, monkeypatch):
+    # a page-locked, mapped destination is written by the kernel itself (zero-copy stores, no staging + D2H);
+    # same bits as the staged path, for a grid, a slab, and the empty-mesh fill
+    torch = pytest.importorskip("torch")
+    verts, tris = synth.bumpy_torus(32, 20)
+    mn, mx = synth.padded_grid_box(verts)
+    grid = m2s.Grid.from_bounding_box(mn, mx, [40, 33, 27])
+    n = 40 * 33 * 27
+    pinned = torch.empty(n, dtype=torch.float32).pin_memory()
+    with m2s.Context() as c:
+        want = c.grid_sdf(verts, tris, grid, 0)                      # pageable numpy destination: staged
+        got = c.grid_sdf(verts, tris, grid, 0, pinned.numpy())       # pinned destination: in place
+        assert got.ctypes.data == pinned.data_ptr()
+        assert np.array_equal(pinned.numpy().view(np.uint32), want.view(np.uint32))
+        assert c.timings()["d2h_ms"] < 0.05
+        pinned.zero_()
+        c.grid_sdf(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), grid, 0, pinned.numpy())
+        assert np.all(pinned.numpy() == np.finfo(np.float32).max)
+    monkeypatch.setenv("M2S_ZEROCOPY", "0")
+    with m2s.Context() as c:
+        pinned.zero_()
+        c.grid_sdf(verts, tris, grid, 0, pinned.numpy())
+        assert np.array_equal(pinned.numpy().view(np.uint32), want.view(np.uint32))

@@ -792,7 +792,33 @@ __device__ __forceinline__ unsigned long long pack_best(float d2, uint32_t slot)
 #define RUN4_MIN_BLOCKS 4
 #endif
 
-template <bool RAYSIGN, int V, int LAYOUT>
+// SIGN: how the sign is found. RUN_SIGN_NONE / RUN_SIGN_RAYCAST search min |d| (Raycast reads the row parities in
+// the epilogue). RUN_SIGN_NORMAL restates the compare_distances fold (lib.rs:242-259) without its dependence on the
+// visiting order: per voxel it keeps the nearest triangle (a positive one wins an exact tie) AND the nearest
+// positive triangle; the result is the positive one if it is approximately equal (2 ulps / 1e-6) to the nearest,
+// else the nearest with its own sign. Everything inside the near-tie window of the radius stays alive, as in
+// Near<MODE_NORMAL>::set_bound. Values can differ from a triangle-order fold by the width of that window
+// (compare_distances is not transitive); signs agree (tests).
+enum : int { RUN_SIGN_NONE = 0, RUN_SIGN_RAYCAST = 1, RUN_SIGN_NORMAL = 2 };
+constexpr uint32_t RUN_NEG_BIT = 0x80000000u;  // in the packed best word of RUN_SIGN_NORMAL: nearest is negative
+
+// Exact squared distance and (NORMAL) the sign test of geo.rs:43-56: dot(p - nearest, ab x ac) > 0 is positive.
+template <bool WANT_SIGN>
+__device__ __forceinline__ float exact_d2_sign(const Bvh& bvh, uint32_t j, bool degen, const f3 p, bool* negative) {
+    const float4 r0 = ldg4(bvh.rec + 3 * (size_t)j);
+    const float4 r1 = ldg4(bvh.rec + 3 * (size_t)j + 1);
+    const float4 r2 = ldg4(bvh.rec + 3 * (size_t)j + 2);
+    const f3 a = {r0.x, r0.y, r0.z}, bb = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
+    const f3 q = degen ? closest_point_triangle_any(p, a, bb, c) : closest_point_triangle(p, a, bb, c);
+    const f3 dir = v_sub(p, q);
+    if (WANT_SIGN) {
+        const f3 n = {r2.y, r2.z, r2.w};
+        *negative = !(v_dot(dir, n) > 0.0f);
+    }
+    return v_dot(dir, dir);
+}
+
+template <int SIGN, int V, int LAYOUT>
 __global__ void __launch_bounds__(128, V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS)
 k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
                    const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
@@ -802,13 +828,16 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     constexpr uint32_t BZR = 4u * V;   // brick extent in z
     __shared__ uint2 s_stack[4][PKT_STACK];
     __shared__ uint2 s_queue[4][QCAP];            // (triangle slot | degen, owner voxel = i * 32 + lane)
-    __shared__ unsigned long long s_best[4][NV];  // per owner voxel: (d2 bits << 32) | slot
+    __shared__ unsigned long long s_best[4][NV];  // per owner voxel: (d2 bits << 32) | [negative bit] | slot
+    __shared__ uint32_t s_pos[4][SIGN == RUN_SIGN_NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
+    constexpr bool NORMAL = SIGN == RUN_SIGN_NORMAL;
     const unsigned full = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint2* const stack = s_stack[warp];
     uint2* const queue = s_queue[warp];
     unsigned long long* const best = s_best[warp];
+    uint32_t* const pos = s_pos[warp];
 
     // bricks numbered z fastest, x slowest: consecutive blocks share tree nodes in L1 / L2
     const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZR - 1) / BZR;
@@ -844,13 +873,19 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const float inv_s = pair_inv_scale(mag), inv_s2 = inv_s * inv_s;
     // (dist + slack)^2, rounded up a little (Near::set_bound), in the squared units of the scaled nodes
     auto bound_of = [&](float d2) {
-        const float r = sqrt_approx(d2) + eps;
+        const float dist = sqrt_approx(d2);
+        float r = dist + eps;
+        if (NORMAL) r += fmaxf(1.0e-6f, dist * 2.4e-7f) * 1.5f;  // the near-tie window of compare_distances
         return r * r * 1.000001f * inv_s2;
     };
     float best2[V], bnd[V];
-    uint32_t slot[V];
+    uint32_t slot[V];            // NORMAL: | RUN_NEG_BIT if that triangle sees the voxel from behind
+    float pos2[NORMAL ? V : 1];  // NORMAL: squared distance of the nearest positive triangle
+    bool nan = false;
 #pragma unroll
     for (int i = 0; i < V; ++i) { best2[i] = INFINITY; slot[i] = 0u; }
+#pragma unroll
+    for (int i = 0; i < (NORMAL ? V : 1); ++i) pos2[i] = INFINITY;
 
     // Seed: the nearest triangle of the voxel with the same (y, z run) on the x-far face of the brick
     // `seed_planes` steps back in x, published by the warp that computed it; see k_grid_nearest_pkt for why this
@@ -882,8 +917,11 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         for (int i = 0; i < V; ++i)
             if (valid[i]) {
                 const f3 pi = {p0.x, p0.y, i == 0 ? p0.z : cell_center(g.fz, g.sz, z0 + i)};
-                best2[i] = exact_d2(bvh, nseed, degen, pi);
-                slot[i] = nseed;
+                bool neg = false;
+                best2[i] = exact_d2_sign<NORMAL>(bvh, nseed, degen, pi, &neg);
+                slot[i] = nseed | (NORMAL && neg ? RUN_NEG_BIT : 0u);
+                if (NORMAL && !neg) pos2[i] = best2[i];
+                if (NORMAL) nan |= !(best2[i] == best2[i]);
             }
     }
     // voxels outside the grid never want a child or a triangle
@@ -916,7 +954,10 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         const int nb = everything ? (qn + 31) >> 5 : qn >> 5;
         if (nb == 0) return;
 #pragma unroll
-        for (int i = 0; i < V; ++i) best[lane + 32u * i] = pack_best(best2[i], slot[i]);
+        for (int i = 0; i < V; ++i) {
+            best[lane + 32u * i] = pack_best(best2[i], slot[i]);
+            if (NORMAL) pos[lane + 32u * i] = __float_as_uint(pos2[i]);
+        }
         __syncwarp();
         for (int b = 0; b < nb; ++b) {
             const int idx = b * 32 + (int)lane;
@@ -928,8 +969,11 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
                            cell_center(g.fz, g.sz, __shfl_sync(full, z0, ow) + (it.y >> 5))};
             if (act) {
                 const uint32_t j = it.x & ~TRI_DEGEN_BIT;
-                const float d2 = exact_d2(bvh, j, (it.x & TRI_DEGEN_BIT) != 0u, po);
-                atomicMin(best + it.y, pack_best(d2, j));
+                bool neg = false;
+                const float d2 = exact_d2_sign<NORMAL>(bvh, j, (it.x & TRI_DEGEN_BIT) != 0u, po, &neg);
+                atomicMin(best + it.y, pack_best(d2, j | (NORMAL && neg ? RUN_NEG_BIT : 0u)));  // tie: positive first
+                if (NORMAL && !neg) atomicMin(pos + it.y, __float_as_uint(d2));
+                if (NORMAL) nan |= !(d2 == d2);
             }
         }
         __syncwarp();
@@ -937,14 +981,19 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         const uint2 keep = (int)lane < rem ? queue[done + lane] : make_uint2(0u, 0u);
         unsigned long long v[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) v[i] = best[lane + 32u * i];
+        for (int i = 0; i < V; ++i) {
+            v[i] = best[lane + 32u * i];
+            if (NORMAL) pos2[i] = __uint_as_float(pos[lane + 32u * i]);
+        }
         __syncwarp();
         if ((int)lane < rem) queue[lane] = keep;
         qn = rem;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const float n2 = __uint_as_float((unsigned)(v[i] >> 32));
-            if (n2 < best2[i]) { best2[i] = n2; slot[i] = (uint32_t)v[i]; bnd[i] = bound_of(n2); }
+            if (n2 < best2[i]) bnd[i] = bound_of(n2);
+            best2[i] = n2;  // the packed minimum: never larger than before; NORMAL: an equal d2 may have turned positive
+            slot[i] = (uint32_t)v[i];
         }
         __syncwarp();
         max_b = warp_max_b();
@@ -1047,14 +1096,27 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     // publish the x-far voxels' nearest triangles for the bricks further in x
     if (tile_slot && (LAYOUT == 0 ? (lane >= 16u && (warp & 2u)) : lane >= 24u)) {
         // the middle voxel of the run (the first one where the run is cut by the grid's end)
-        if (valid[0]) __stcg(tile_slot + ((size_t)blockIdx.x * 4u + warp) * 16u + src_idx, valid[V / 2] ? slot[V / 2] : slot[0]);
+        if (valid[0])
+            __stcg(tile_slot + ((size_t)blockIdx.x * 4u + warp) * 16u + src_idx,
+                   (valid[V / 2] ? slot[V / 2] : slot[0]) & ~(NORMAL ? RUN_NEG_BIT : 0u));
     }
 
     // sqrt is monotone: min sqrt = sqrt min (finish<MODE_UNSIGNED>)
     float res[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) res[i] = __fsqrt_rn(best2[i]);
-    if (RAYSIGN && valid[0]) {
+    if (NORMAL) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            if (slot[i] & RUN_NEG_BIT) {
+                // lib.rs:242-254: an approximately equal positive distance beats the negative one
+                const float dp = __fsqrt_rn(pos2[NORMAL ? i : 0]);
+                res[i] = approx_eq_abs(dp, res[i]) ? dp : -res[i];
+            }
+        }
+        if (__any_sync(full, nan) && lane == 0) atomicExch(&st->nan_distance, 1);  // lib.rs:257 "NaN distance"
+    }
+    if (SIGN == RUN_SIGN_RAYCAST && valid[0]) {
         // generate/grid.rs:622-639: negative iff >= 2 of the 3 per-axis hit counts are odd. The Z row of the run
         // is one row: its bits z0 .. z0+V-1 sit in one word (V divides 32)
         const uint32_t rows_x = g.ny * g.nz, rows_y = g.nx * g.nz, rows_z = g.nx * g.ny;
@@ -1409,8 +1471,13 @@ static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 // Raycast / unsigned grids take their seeds from finished neighbour tiles inside the distance kernel
 // (k_grid_nearest_pkt); everything else runs the separate coarse pass below.
+static bool grid_uses_run_kernel(const Device& d) {
+    return d.packet && d.pair && d.neighbour_seeds && d.bvh.leaf_size == 1u && d.bvh.nleaf >= 2u;
+}
+// k_grid_nearest_pkt keeps the coarse pass for Normal (its fold depends on the visiting order and must stay
+// deterministic); k_grid_nearest_run's Normal rule does not depend on the order.
 bool grid_uses_neighbour_seeds(const Device& d, int mode) {
-    return d.packet && d.neighbour_seeds && mode != MODE_NORMAL;
+    return d.packet && d.neighbour_seeds && (mode != MODE_NORMAL || grid_uses_run_kernel(d));
 }
 
 // Coarse seeding pass(es) over the whole slab [g.x0, g.x1).
@@ -1455,7 +1522,7 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
     const float mag = grid_magnitude(g);
     BuildStatus* st = d.status.as<BuildStatus>();
     const unsigned nb = (unsigned)nblocks;
-    if (d.packet && d.pair && grid_uses_neighbour_seeds(d, mode) && d.bvh.leaf_size == 1u && d.bvh.nleaf >= 2u) {
+    if (grid_uses_run_kernel(d)) {
         // several voxels per lane. M2S_PAIR: 1 = default (V, LAYOUT) = (2, 0); 4..7 = (2,0) (2,1) (4,0) (4,1)
         const int variant = d.pair < 4 ? 4 : d.pair;
         const uint32_t V = variant >= 6 ? 4u : 2u;
@@ -1473,17 +1540,21 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
         const uint32_t resident = (uint32_t)d.sm_count * (V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS);
         const uint32_t planes = std::min(4u, std::max(1u, cdiv(resident * 5u / 4u, plane_bricks)));
         CK(launch_nodes_interleave(d, mag));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
-#define M2S_RUN(RS, VV, LL) k_grid_nearest_run<RS, VV, LL><<<nbr, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes)
-        switch (variant * 2 + (rb ? 1 : 0)) {
-            case 8: M2S_RUN(false, 2, 0); break;
-            case 9: M2S_RUN(true, 2, 0); break;
-            case 10: M2S_RUN(false, 2, 1); break;
-            case 11: M2S_RUN(true, 2, 1); break;
-            case 12: M2S_RUN(false, 4, 0); break;
-            case 13: M2S_RUN(true, 4, 0); break;
-            case 14: M2S_RUN(false, 4, 1); break;
-            default: M2S_RUN(true, 4, 1); break;
+        const int sign = rb ? RUN_SIGN_RAYCAST : (mode == MODE_NORMAL ? RUN_SIGN_NORMAL : RUN_SIGN_NONE);
+#define M2S_RUN(SG, VV, LL) k_grid_nearest_run<SG, VV, LL><<<nbr, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes)
+#define M2S_RUN3(VV, LL)                                            \
+    do {                                                            \
+        if (sign == RUN_SIGN_RAYCAST) M2S_RUN(RUN_SIGN_RAYCAST, VV, LL); \
+        else if (sign == RUN_SIGN_NORMAL) M2S_RUN(RUN_SIGN_NORMAL, VV, LL); \
+        else M2S_RUN(RUN_SIGN_NONE, VV, LL);                        \
+    } while (0)
+        switch (variant) {
+            case 4: M2S_RUN3(2, 0); break;
+            case 5: M2S_RUN3(2, 1); break;
+            case 6: M2S_RUN3(4, 0); break;
+            default: M2S_RUN3(4, 1); break;
         }
+#undef M2S_RUN3
 #undef M2S_RUN
     } else if (d.packet) {
         uint32_t* tile_slot = nullptr;

@@ -146,9 +146,14 @@ def test_every_grid_kernel_variant_bit_exact(m2s, oracle, monkeypatch, pair, dim
     verts, tris = synth.bumpy_torus(40, 24)
     grid = _grid_for(m2s, verts, list(dims))
     want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, RAYCAST)
+    want_n = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, NORMAL)
     with m2s.Context() as c:
         got = c.grid_sdf(verts, tris, grid, RAYCAST)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        # Normal: magnitudes inside the near-tie window of compare_distances, identical signs
+        got_n = c.grid_sdf(verts, tris, grid, NORMAL)
+        assert np.max(np.abs(np.abs(got_n) - np.abs(want_n))) <= 4e-6
+        assert np.array_equal(np.signbit(got_n), np.signbit(want_n))
         torch = pytest.importorskip("torch")
         dv = torch.from_numpy(verts).cuda()
         dt = torch.from_numpy(tris.view(np.int32)).cuda()
@@ -159,3 +164,32 @@ def test_every_grid_kernel_variant_bit_exact(m2s, oracle, monkeypatch, pair, dim
         c.grid_sdf_device(dv.data_ptr(), len(verts), dt.data_ptr(), len(tris), grid, RAYCAST, x0, x1, out.data_ptr())
         c.synchronize()
         assert np.array_equal(out.cpu().numpy().view(np.uint32), want[x0 * plane:x1 * plane].view(np.uint32))
+
+
+def test_normal_sign_near_ties_positive_wins(m2s, oracle):
+    # lib.rs:242-254: approximately equal |d| (2 ulps / 1e-6) -> the positive one wins. Queries in the mid-plane of
+    # a thin slab see two faces at (almost) the same distance from opposite sides; queries straight above a shared
+    # edge of a convex / concave fold see two triangles at exactly the same distance.
+    zb, zd = 0.0625, np.float32(0.0625) + np.float32(5e-7)
+    verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0],          # face A, z = 0, normal +z
+                      [0, 0, zb], [1, 0, zb], [0, 1, zb], [1, 1, zb],      # face B, z = 1/16, normal +z: the mid-plane
+                                                                           # z = 1/32 is a cell centre -> exact tie, + and -
+                      [2, 0, 0], [3, 0, 0], [2, 1, 0], [3, 1, 0],          # face C, z = 0
+                      [2, 0, zd], [3, 0, zd], [2, 1, zd], [3, 1, zd],      # face D, 5e-7 higher: near-tie inside 1e-6
+                      [4, 0, 0], [5, 0, 1], [5, 1, 1], [4, 1, 0], [6, 0, 0], [6, 1, 0]], np.float32)  # a roof fold
+    tris = np.array([[0, 1, 2], [1, 3, 2], [4, 5, 6], [5, 7, 6], [8, 9, 10], [9, 11, 10], [12, 13, 14], [13, 15, 14],
+                     [16, 17, 18], [16, 18, 19], [17, 20, 21], [17, 21, 18]], np.uint32)
+    grid = m2s.Grid([-0.25, -0.25, -0.5], [0.125, 0.125, 0.03125], [56, 14, 64])
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, NORMAL)
+    for pair in ("0", "1"):
+        import os
+        os.environ["M2S_PAIR"] = pair
+        try:
+            with m2s.Context() as c:
+                got = c.grid_sdf(verts, tris, grid, NORMAL)
+        finally:
+            os.environ.pop("M2S_PAIR", None)
+        assert np.max(np.abs(np.abs(got) - np.abs(want))) <= 4e-6
+        assert np.array_equal(np.signbit(got), np.signbit(want)), pair
+        mid = got.reshape(56, 14, 64)[:, :, 17]  # z = 1/32: between A and B (exact tie) and between C and D (near-tie)
+        assert np.all(mid[3:9, 3:9] == np.float32(0.03125)) and np.all(mid[19:25, 3:9] > 0)

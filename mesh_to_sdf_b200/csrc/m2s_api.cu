@@ -279,7 +279,7 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         std::memset(d.h_status, 0, sizeof(BuildStatus));
         if (const char* e = std::getenv("M2S_PACKET")) d.packet = std::atoi(e) != 0;
         if (const char* e = std::getenv("M2S_ZEROCOPY")) d.zero_copy = std::atoi(e) != 0;
-        if (const char* e = std::getenv("M2S_PAIR")) d.pair = std::max(0, std::min(7, std::atoi(e)));
+        if (const char* e = std::getenv("M2S_PAIR")) d.pair = std::max(0, std::min(8, std::atoi(e)));
         if (const char* e = std::getenv("M2S_SEED_PACKET")) d.seed_packet = std::atoi(e) != 0;
         if (const char* e = std::getenv("M2S_OBB_BIAS")) d.obb_bias = (float)std::atof(e);
         if (const char* e = std::getenv("M2S_STATS")) { d.want_stats = std::atoi(e) != 0; d.stats_mode = std::atoi(e); }

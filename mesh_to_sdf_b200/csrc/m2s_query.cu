@@ -1402,6 +1402,281 @@ k_points_pkt(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Run variant for scattered queries (the default, V = 1): the packet walk of k_grid_nearest_run for 32 V consecutive
+// Morton-sorted queries per warp - both children of a node per packed-fp32 instruction (interleaved, pre-scaled
+// nodes, FADD.SAT excess), one warp-shared queue of (triangle, query) items for the exact arithmetic. The queries
+// of a lane are independent points (no lattice step), so every query pays its own projections.
+//   MODE_UNSIGNED: min |d| (+ the ray-parity sign rules below)
+//   MODE_ARGMIN:   signed distance of THE nearest triangle, ties -> lowest original index (rtree.rs:116-123):
+//                  the packed word carries (d2, original index, sign) so the winner's sign comes with it
+//   MODE_NORMAL:   the order-independent restatement of the compare_distances fold (see k_grid_nearest_run)
+// ---------------------------------------------------------------------------------------------------
+#ifndef PRUN_MIN_BLOCKS
+#define PRUN_MIN_BLOCKS 5
+#endif
+
+template <int MODE, int SIGN, int V>
+__global__ void __launch_bounds__(128, PRUN_MIN_BLOCKS)
+k_points_run(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, float* __restrict__ out,
+             BuildStatus* __restrict__ st) {
+    constexpr int NV = 32 * V;
+    constexpr int QCAP = 32 + 2 * NV;
+    constexpr bool NORMAL = MODE == MODE_NORMAL, ARGMIN = MODE == MODE_ARGMIN;
+    __shared__ uint2 s_stack[4][PKT_STACK];
+    __shared__ uint2 s_queue[4][QCAP];            // (triangle slot | degen, owner query = i * 32 + lane)
+    __shared__ unsigned long long s_best[4][NV];  // per owner: (d2 bits << 32) | payload (see pack below)
+    __shared__ uint32_t s_pos[4][NORMAL ? NV : 1];
+    const unsigned full = 0xffffffffu;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint2* const stack = s_stack[warp];
+    uint2* const queue = s_queue[warp];
+    unsigned long long* const best = s_best[warp];
+    uint32_t* const pos = s_pos[warp];
+
+    const uint32_t base = (blockIdx.x * 4u + warp) * (uint32_t)NV;
+    if (base >= nq) return;  // warp-uniform
+    bool valid[V];
+    f3 p[V];
+    uint32_t orig[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const uint32_t idx = base + 32u * i + lane;
+        valid[i] = idx < nq;
+        const float4 q = valid[i] ? q_sorted[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        p[i] = {q.x, q.y, q.z};
+        orig[i] = __float_as_uint(q.w);
+    }
+    const float mag = scene_magnitude(st);
+    const float eps = 4.0e-6f * mag;
+    const float inv_s = pair_inv_scale(mag), inv_s2 = inv_s * inv_s;
+    auto bound_of = [&](float d2) {
+        const float dist = sqrt_approx(d2);
+        float r = dist + eps;
+        if (NORMAL) r += fmaxf(1.0e-6f, dist * 2.4e-7f) * 1.5f;
+        return r * r * 1.000001f * inv_s2;
+    };
+    // payload of the packed best word: UNSIGNED slot; NORMAL [negative bit 31] | slot (a positive triangle wins an
+    // exact tie); ARGMIN (original index << 1) | negative (the lowest original index wins an exact tie)
+    auto payload = [&](uint32_t j, bool neg) -> uint32_t {
+        if (ARGMIN) return ((bvh.tri_id[j] & ~TRI_DEGEN_BIT) << 1) | (neg ? 1u : 0u);
+        if (NORMAL) return j | (neg ? RUN_NEG_BIT : 0u);
+        return j;
+    };
+    float best2[V], bnd[V];
+    uint32_t pay[V];
+    float pos2[NORMAL ? V : 1];
+    bool nan = false;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best2[i] = INFINITY; pay[i] = 0u; }
+#pragma unroll
+    for (int i = 0; i < (NORMAL ? V : 1); ++i) pos2[i] = INFINITY;
+
+    // start: a greedy descent for the lane's first query; its triangle seeds all queries of the lane
+    {
+        Near<MODE_UNSIGNED> s0;
+        s0.init(eps);
+        if (valid[0]) greedy_seed<MODE_UNSIGNED>(bvh, p[0], s0);
+        if (s0.best2 < INFINITY) {
+            const uint32_t j = s0.slot;
+            const bool degen = (bvh.tri_id[j] & TRI_DEGEN_BIT) != 0u;
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (valid[i]) {
+                    bool neg = false;
+                    best2[i] = exact_d2_sign<NORMAL || ARGMIN>(bvh, j, degen, p[i], &neg);
+                    pay[i] = payload(j, neg);
+                    if (NORMAL && !neg) pos2[i] = best2[i];
+                    if (NORMAL) nan |= !(best2[i] == best2[i]);
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) bnd[i] = valid[i] ? bound_of(best2[i]) : -1.0f;
+    auto warp_max_b = [&]() {
+        float m = 0.0f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) m = fmaxf(m, bnd[i]);
+        return __uint_as_float(__reduce_max_sync(full, __float_as_uint(m)));
+    };
+    float max_b = warp_max_b();
+
+    int qn = 0, sp = 0;
+    int overflow = 0;
+    uint32_t n_nodes = 0, n_leaves = 0;
+    auto enqueue = [&](unsigned h, uint32_t item) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const bool w = (h >> i) & 1u;
+            const unsigned m = __ballot_sync(full, w);
+            if (w) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
+            qn += __popc(m);
+        }
+    };
+    auto flush = [&](bool everything) {
+        const int nb = everything ? (qn + 31) >> 5 : qn >> 5;
+        if (nb == 0) return;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            best[lane + 32u * i] = pack_best(best2[i], pay[i]);
+            if (NORMAL) pos[lane + 32u * i] = __float_as_uint(pos2[i]);
+        }
+        __syncwarp();
+        for (int b = 0; b < nb; ++b) {
+            const int idx = b * 32 + (int)lane;
+            const bool act = idx < qn;
+            const uint2 it = act ? queue[idx] : make_uint2(0u, lane);
+            const int ow = (int)(it.y & 31u);
+            f3 po = {__shfl_sync(full, p[0].x, ow), __shfl_sync(full, p[0].y, ow), __shfl_sync(full, p[0].z, ow)};
+#pragma unroll
+            for (int i = 1; i < V; ++i) {
+                const f3 pi = {__shfl_sync(full, p[i].x, ow), __shfl_sync(full, p[i].y, ow), __shfl_sync(full, p[i].z, ow)};
+                if ((int)(it.y >> 5) == i) po = pi;
+            }
+            if (act) {
+                const uint32_t j = it.x & ~TRI_DEGEN_BIT;
+                bool neg = false;
+                const float d2 = exact_d2_sign<NORMAL || ARGMIN>(bvh, j, (it.x & TRI_DEGEN_BIT) != 0u, po, &neg);
+                atomicMin(best + it.y, pack_best(d2, payload(j, neg)));
+                if (NORMAL && !neg) atomicMin(pos + it.y, __float_as_uint(d2));
+                if (NORMAL) nan |= !(d2 == d2);
+            }
+        }
+        __syncwarp();
+        const int done = min(nb * 32, qn), rem = qn - done;
+        const uint2 keep = (int)lane < rem ? queue[done + lane] : make_uint2(0u, 0u);
+        unsigned long long v[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            v[i] = best[lane + 32u * i];
+            if (NORMAL) pos2[i] = __uint_as_float(pos[lane + 32u * i]);
+        }
+        __syncwarp();
+        if ((int)lane < rem) queue[lane] = keep;
+        qn = rem;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float n2 = __uint_as_float((unsigned)(v[i] >> 32));
+            if (n2 < best2[i]) bnd[i] = bound_of(n2);
+            best2[i] = n2;
+            pay[i] = (uint32_t)v[i];
+        }
+        __syncwarp();
+        max_b = warp_max_b();
+    };
+
+    uint32_t cur = bvh.root;  // an internal node (the launcher sends single-leaf trees to k_points_pkt)
+    for (;;) {
+        PKT_COUNT(n_nodes);
+        const float4* nd = bvh.nodes_il + NODE_F4 * (size_t)cur;  // warp-uniform address
+        const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+        const float4 q4 = ldg4(nd + 4), q5 = ldg4(nd + 5), q6 = ldg4(nd + 6), q7 = ldg4(nd + 7);
+        const float2 m1 = make_float2(-1.0f, -1.0f);
+        const float2 eu = f2hi(q3), ev = f2hi(q5), ew = f2hi(q7);
+        float2 dd[V];  // squared lower bounds of query i: (left child, right child)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float2 dx = __ffma2_rn(f2lo(q0), m1, make_float2(p[i].x, p[i].x));
+            const float2 dy = __ffma2_rn(f2hi(q0), m1, make_float2(p[i].y, p[i].y));
+            const float2 dz = __ffma2_rn(f2lo(q1), m1, make_float2(p[i].z, p[i].z));
+            const float2 tu = __ffma2_rn(dz, f2lo(q3), __ffma2_rn(dy, f2hi(q2), __fmul2_rn(dx, f2lo(q2))));
+            const float2 tv = __ffma2_rn(dz, f2lo(q5), __ffma2_rn(dy, f2hi(q4), __fmul2_rn(dx, f2lo(q4))));
+            const float2 tw = __ffma2_rn(dz, f2lo(q7), __ffma2_rn(dy, f2hi(q6), __fmul2_rn(dx, f2lo(q6))));
+            dd[i] = sumsq2(excess2(tu, eu), excess2(tv, ev), excess2(tw, ew));
+        }
+        unsigned hl = 0u, hr = 0u;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            hl |= dd[i].x <= bnd[i] ? 1u << i : 0u;
+            hr |= dd[i].y <= bnd[i] ? 1u << i : 0u;
+        }
+        unsigned bl = __ballot_sync(full, hl != 0u), br = __ballot_sync(full, hr != 0u);
+        const uint32_t lref = __float_as_uint(q1.z), rref = __float_as_uint(q1.w);
+        if ((lref | rref) & LEAF_BIT) {
+            if (lref & LEAF_BIT) {
+                if (bl) {
+                    enqueue(hl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    PKT_COUNT(n_leaves);
+                }
+                bl = 0u;
+            }
+            if (rref & LEAF_BIT) {
+                if (br) {
+                    enqueue(hr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    PKT_COUNT(n_leaves);
+                }
+                br = 0u;
+            }
+            if (qn >= 32) flush(false);
+        }
+        if (bl && br) {
+            float kl = INFINITY, kr = INFINITY;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                kl = fminf(kl, (hl >> i) & 1u ? dd[i].x : INFINITY);
+                kr = fminf(kr, (hr >> i) & 1u ? dd[i].y : INFINITY);
+            }
+            const unsigned ml = __reduce_min_sync(full, __float_as_uint(kl)), mr = __reduce_min_sync(full, __float_as_uint(kr));
+            const bool left_first = ml <= mr;
+            if (sp < PKT_STACK) {
+                if (lane == 0) stack[sp] = left_first ? make_uint2(rref, mr) : make_uint2(lref, ml);
+                ++sp;
+                __syncwarp();
+            } else {
+                overflow = 1;
+            }
+            cur = left_first ? lref : rref;
+        } else if (bl) {
+            cur = lref;
+        } else if (br) {
+            cur = rref;
+        } else {
+            uint32_t r = TRAVERSAL_DONE;
+            while (sp > 0) {
+                const uint2 e = stack[--sp];
+                if (__uint_as_float(e.y) <= max_b) {
+                    r = e.x;
+                    break;
+                }
+            }
+            __syncwarp();
+            if (r == TRAVERSAL_DONE) break;
+            cur = r;
+        }
+    }
+    flush(true);
+
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        if (!valid[i]) continue;
+        float d = __fsqrt_rn(best2[i]);
+        if (ARGMIN) {
+            if (pay[i] & 1u) d = -d;  // sign of THE nearest triangle (rtree.rs:118-123)
+        } else if (NORMAL) {
+            if (pay[i] & RUN_NEG_BIT) {
+                const float dp = __fsqrt_rn(pos2[NORMAL ? i : 0]);
+                d = approx_eq_abs(dp, d) ? dp : -d;
+            }
+        }
+        if (SIGN == 1) {
+            if (ray_parity<0>(bvh, p[i], &overflow)) d = -d;
+        } else if (SIGN == 3) {
+            const uint32_t insides = ray_parity<0>(bvh, p[i], &overflow) + ray_parity<1>(bvh, p[i], &overflow) +
+                                     ray_parity<2>(bvh, p[i], &overflow);
+            if (insides > 1u) d = -d;
+        }
+        out[orig[i]] = d;
+    }
+    if (NORMAL && __any_sync(full, nan) && lane == 0) atomicExch(&st->nan_distance, 1);
+    if (overflow) atomicExch(&st->stack_overflow, 1);
+    if (bvh.stats && lane == 0) {
+        atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
+        atomicAdd(bvh.stats + 1, (unsigned long long)n_leaves);
+        atomicAdd(bvh.stats + 2, 1ull);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_fill(float* __restrict__ out, uint64_t n, float v) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
         out[i] = v;
@@ -1601,6 +1876,27 @@ cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float
     BuildStatus* st = d.status.as<BuildStatus>();
     const uint32_t n = (uint32_t)nq;
 
+    if (d.packet && d.pair && d.bvh.leaf_size == 1u && d.bvh.nleaf >= 2u) {
+        // one query per lane by default: measured on C4, 64-query packets lose more to their wider union of
+        // candidate triangles than they gain (3.79 vs 3.18 ms; k_points_pkt 3.57). M2S_PAIR=8: two per lane (A/B)
+        CK(launch_nodes_interleave(d, 0.0f));  // after sort_queries: the scene bounds now include the queries
+        if (after_seeds) cudaEventRecord(after_seeds, s);
+        const bool one = d.pair != 8;
+        const unsigned nbr = blocks_for(nq, one ? 128 : 256);
+#define M2S_PRUN(MD, SG)                                                              \
+    do {                                                                              \
+        if (one) k_points_run<MD, SG, 1><<<nbr, 128, 0, s>>>(d.bvh, q, n, d_out, st); \
+        else k_points_run<MD, SG, 2><<<nbr, 128, 0, s>>>(d.bvh, q, n, d_out, st);     \
+    } while (0)
+        if (mode == MODE_NORMAL) M2S_PRUN(MODE_NORMAL, 0);
+        else if (mode == MODE_ARGMIN) M2S_PRUN(MODE_ARGMIN, 0);
+        else if (sign_rule == 1) M2S_PRUN(MODE_UNSIGNED, 1);
+        else if (sign_rule == 3) M2S_PRUN(MODE_UNSIGNED, 3);
+        else M2S_PRUN(MODE_UNSIGNED, 0);
+#undef M2S_PRUN
+        d.launches++;
+        return cudaGetLastError();
+    }
     if (d.packet) {
         if (after_seeds) cudaEventRecord(after_seeds, s);
         const unsigned nbp = blocks_for(nq, 256);

@@ -1,4 +1,2 @@
-timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/r1i_bench.json 2> gpurun_out/r1i_bench.err
-timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1i_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r1i_ncu_b.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:k_grid_nearest -s 1 -c 1 -o gpurun_out/r1i_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r1i_ncu_full.log 2>&1
-cat gpurun_out/r1i_bench.json | python -c "import json,sys; d=json.load(sys.stdin); print({k:d[k] for k in ('value','ms_per_step','e2e','phases_ms','roofline','cpu_baseline')})"
+timeout 300 python -m pytest tests/test_gpu_grid.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -2
+for c in -1 0 12 25 40; do echo "== carveout $c"; M2S_CARVEOUT=$c REPS=4 python scripts/quick_perf.py C3 2>&1 | grep -E "rep[3]"; done

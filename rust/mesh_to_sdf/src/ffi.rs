@@ -50,6 +50,12 @@ extern "C" {
         ctx: *mut m2s_ctx, verts_xyz: *const f32, nv: u64, tri_idx: *const u32, nt: u64,
         queries_xyz: *const f32, nq: u64, accel_method: c_int, sign_method: c_int, out: *mut f32,
     ) -> c_int;
+    // post-passes on a finished grid: mesh_to_sdf_client/src/sdf.rs:62-68, :123; shaders/draw_raymarching.wgsl:118-200
+    pub fn m2s_grid_order(ctx: *mut m2s_ctx, sdf: *const f32, n: u64, order: *mut u32, minmax: *mut f32) -> c_int;
+    pub fn m2s_sample_grid_sdf(
+        ctx: *mut m2s_ctx, sdf: *const f32, first_cell: *const f32, cell_size: *const f32, cell_count: *const u64,
+        points_xyz: *const f32, np: u64, sample_mode: c_int, iso: f32, out: *mut f32,
+    ) -> c_int;
     pub fn m2s_expand_topology(
         topology: c_int, indices: *const c_void, index_bytes: c_int, n_indices: u64, nv: u64, out: *mut u32,
     ) -> u64;

@@ -131,6 +131,44 @@ where
     out
 }
 
+/// What the reference's in-repo caller does with the grid next (mesh_to_sdf_client/src/sdf.rs:62-68, :123):
+/// `(0..n).sorted_by(|i, j| data[*i].total_cmp(&data[*j]))` and `data.iter().copied().minmax()`, on the GPU.
+pub fn grid_order(sdf: &[f32]) -> (Vec<u32>, (f32, f32)) {
+    let mut order = vec![0u32; sdf.len()];
+    let mut mm = [0f32; 2];
+    let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+    let rc = unsafe { ffi::m2s_grid_order(c.0, sdf.as_ptr(), sdf.len() as u64, order.as_mut_ptr(), mm.as_mut_ptr()) };
+    check(&c, rc);
+    (order, (mm[0], mm[1]))
+}
+
+/// `raymarch_mode` of mesh_to_sdf_client/shaders/draw_raymarching.wgsl.
+#[derive(Debug, Clone, Copy, PartialEq, Eq, Default)]
+pub enum SampleMode {
+    Snap = 0,
+    #[default]
+    Trilinear = 1,
+    Tetrahedral = 2,
+}
+
+/// Distance at arbitrary points by interpolating a grid SDF — the TODO of the reference's `src/grid.rs:172`, with
+/// the semantics of `sdf_grid()` in the reference's raymarching shader (100.0 outside the grid).
+pub fn sample_grid_sdf<V: Point>(sdf: &[f32], grid: &Grid<V>, points: &[V], mode: SampleMode, iso: f32) -> Vec<f32> {
+    assert_eq!(sdf.len(), grid.get_total_cell_count(), "sdf length does not match the grid");
+    let p = pack(points);
+    let (f, s, n) = (grid.get_first_cell(), grid.get_cell_size(), grid.get_cell_count());
+    let (first, size) = ([f.x(), f.y(), f.z()], [s.x(), s.y(), s.z()]);
+    let count = [n[0] as u64, n[1] as u64, n[2] as u64];
+    let mut out = vec![0f32; points.len()];
+    let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+    let rc = unsafe {
+        ffi::m2s_sample_grid_sdf(c.0, sdf.as_ptr(), first.as_ptr(), size.as_ptr(), count.as_ptr(), p.as_ptr(),
+                                 points.len() as u64, mode as i32, iso, out.as_mut_ptr())
+    };
+    check(&c, rc);
+    out
+}
+
 #[cfg(test)]
 mod tests {
     use super::*;

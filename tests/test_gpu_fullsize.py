@@ -81,3 +81,30 @@ def test_c4_points_1m(m2s, oracle):
     gap = np.linalg.norm(q[i].astype(np.float64) - q[j].astype(np.float64), axis=1)
     assert np.all(np.abs(np.abs(sdf[i]) - np.abs(sdf[j])) <= gap * (1 + 1e-5) + 1e-6)
     assert 0.10 < float(np.mean(sdf < 0)) < 0.20
+
+
+def test_c5_raycast_512_as_eight_slabs(m2s, oracle):
+    # BASELINE config C5 on one GPU: 1 003 520 triangles, 512^3, Raycast, computed as the eight 64-plane x-slabs the
+    # 8-GPU deployment gives its ranks (each through the per-rank entry point), checked against the exact oracle on
+    # a seeded sample, against the whole-grid call on two slabs, and for the distance-field properties on a sub-block
+    verts, tris = synth.bumpy_torus(1024, 490)
+    assert len(tris) == 1_003_520
+    mn, mx = synth.padded_grid_box(verts)
+    n = 512
+    grid = m2s.Grid.from_bounding_box(mn, mx, [n, n, n])
+    ctx = m2s.default_context()
+    sdf = np.empty(n ** 3, np.float32)
+    plane = n * n
+    for r in range(8):
+        ctx.grid_sdf_slab(verts, tris, grid, 0, 64 * r, 64 * (r + 1), sdf[64 * r * plane:64 * (r + 1) * plane])
+    idx = np.random.default_rng(5).choice(n ** 3, 300, replace=False).astype(np.uint64)
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, 0, idx)
+    assert np.array_equal(sdf[idx].view(np.uint32), want.view(np.uint32))  # bit-exact, value and sign
+    whole = ctx.grid_sdf_slab(verts, tris, grid, 0, 192, 320)  # crosses two rank boundaries
+    assert np.array_equal(whole.view(np.uint32), sdf[192 * plane:320 * plane].view(np.uint32))
+    block = sdf.reshape(n, n, n)[128:384, 128:384, 128:384]
+    a = np.abs(block)
+    for axis in range(3):
+        h = float(abs(grid.cell_size[axis]))
+        assert np.max(np.abs(np.diff(a, axis=axis))) <= h * (1 + 1e-4) + 1e-6
+    assert 0.10 < float(np.mean(sdf < 0)) < 0.20

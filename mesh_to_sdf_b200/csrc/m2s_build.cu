@@ -5,6 +5,7 @@
 // (mesh_to_sdf/src/generate/grid.rs:95-111, generic/bvh.rs:62-74, generic/rtree_bvh.rs:108-116) and
 // rstar::RTree::bulk_load (generic/rtree.rs:111, generic/rtree_bvh.rs:118). Leaf boxes are the
 // reference's padded triangle boxes (geo::triangle_bounding_box, src/geo.rs:4-22).
+#include <cuda/atomic>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "m2s_geom.cuh"
@@ -552,25 +553,25 @@ k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
     bool first_level = true;
     for (;;) {
         const uint32_t p = link >> 1, side = link & 1u;
+        const uint32_t up = node_parent[p];  // issued before the wait on the counter: off the critical path
         float4* nd = nodes + BOX_F4 * (size_t)p;
         // write my box into my side of the parent (the child ref lives in .w of the side's first
         // float4, each written only by its own side)
         float4* mine = nd + 2 * side;
         uint32_t ref = __float_as_uint(mine[0].w);
         if (first_level && degen) ref |= LEAF_DEGEN_BIT;
-        mine[0] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(ref));
-        mine[1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        __stcg(mine, make_float4(lo[0], lo[1], lo[2], __uint_as_float(ref)));
+        __stcg(mine + 1, make_float4(hi[0], hi[1], hi[2], 0.0f));
         first_level = false;
-        __threadfence();
-        if (atomicAdd(&node_flag[p], 1u) == 0u) return;  // sibling not there yet
-        __threadfence();
+        // one acq_rel read-modify-write instead of fence + atomic + fence: releases my box, and for the second
+        // arrival acquires the sibling's (read below from L2, where the sibling's release put it)
+        cuda::atomic_ref<uint32_t, cuda::thread_scope_device> flag(node_flag[p]);
+        if (flag.fetch_add(1u, cuda::std::memory_order_acq_rel) == 0u) return;  // sibling not there yet
         // both children present: union and go up
-        const volatile float4* vn = nd;
-        float4 a0 = make_float4(vn[0].x, vn[0].y, vn[0].z, 0.f), a1 = make_float4(vn[1].x, vn[1].y, vn[1].z, 0.f);
-        float4 b0 = make_float4(vn[2].x, vn[2].y, vn[2].z, 0.f), b1 = make_float4(vn[3].x, vn[3].y, vn[3].z, 0.f);
+        const float4 a0 = __ldcg(nd), a1 = __ldcg(nd + 1), b0 = __ldcg(nd + 2), b1 = __ldcg(nd + 3);
         lo[0] = fminf(a0.x, b0.x); lo[1] = fminf(a0.y, b0.y); lo[2] = fminf(a0.z, b0.z);
         hi[0] = fmaxf(a1.x, b1.x); hi[1] = fmaxf(a1.y, b1.y); hi[2] = fmaxf(a1.z, b1.z);
-        link = node_parent[p];
+        link = up;
         if (link == 0xffffffffu) return;  // root done
     }
 }

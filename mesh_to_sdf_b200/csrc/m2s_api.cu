@@ -92,11 +92,19 @@ cudaError_t enqueue_grid(m2s_ctx* ctx, Device& d, const float* d_verts, uint64_t
         if (timed) cudaEventRecord(d.ev[4], d.stream);
         return e;
     }
-    if ((e = launch_build(d, d_verts, nv, d_tris, nt, ctx->leaf_size)) != cudaSuccess) return e;
-    if (timed) cudaEventRecord(d.ev[2], d.stream);
     RowBits rb{};
     const bool raycast = sign == M2S_SIGN_RAYCAST;
-    if (raycast && (e = launch_grid_rows(d, g, &rb)) != cudaSuccess) return e;
+    // The row parities only need the triangle records, so they run on the side stream beside the sort / hierarchy /
+    // refit / box fitting (small, latency-bound launches that leave most SMs idle) and join before the distance kernel.
+    if ((e = launch_build(d, d_verts, nv, d_tris, nt, ctx->leaf_size, raycast ? d.ev_records : nullptr)) != cudaSuccess)
+        return e;
+    if (timed) cudaEventRecord(d.ev[2], d.stream);
+    if (raycast) {
+        if ((e = cudaStreamWaitEvent(d.aux_stream, d.ev_records, 0)) != cudaSuccess) return e;
+        if ((e = launch_grid_rows(d, g, &rb, d.aux_stream, d.rec_orig.as<float4>())) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(d.ev_rows, d.aux_stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(d.stream, d.ev_rows, 0)) != cudaSuccess) return e;
+    }
     if (timed) cudaEventRecord(d.ev[3], d.stream);
     const int mode = raycast ? MODE_UNSIGNED : MODE_NORMAL;
     const RowBits* rbp = raycast ? &rb : nullptr;
@@ -268,6 +276,8 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_records, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_rows, cudaEventDisableTiming);
         for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreate(&d.ev_half[k]);
         if (const char* c = std::getenv("M2S_SPLIT")) d.split_halves = std::atoi(c) != 0;
         if (const char* c = std::getenv("M2S_NSEED")) { d.neighbour_seeds = std::atoi(c) != 0; d.neighbour_and_coarse = std::atoi(c) == 2; }
@@ -326,6 +336,8 @@ void m2s_destroy(m2s_ctx* ctx) {
         if (d.ev_copied) cudaEventDestroy(d.ev_copied);
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);
         if (d.ev_join) cudaEventDestroy(d.ev_join);
+        if (d.ev_records) cudaEventDestroy(d.ev_records);
+        if (d.ev_rows) cudaEventDestroy(d.ev_rows);
         for (int k = 0; k < 2; ++k)
             if (d.ev_half[k]) cudaEventDestroy(d.ev_half[k]);
         if (d.aux_stream) cudaStreamDestroy(d.aux_stream);

@@ -598,7 +598,7 @@ cudaError_t launch_status_reset(Device& d, bool clear_errors) {
 
 // Builds records + LBVH for (d_verts, d_tris) on d.stream. launch_status_reset must have run.
 cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
-                         uint32_t K) {
+                         uint32_t K, cudaEvent_t after_records) {
     cudaStream_t s = d.stream;
     BuildStatus* st = d.status.as<BuildStatus>();
     d.bvh = Bvh{};
@@ -630,6 +630,7 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     k_tri_setup<<<blocks_for(nt, bs), bs, 0, s>>>(d_verts, (uint32_t)nv, d_tris, (uint32_t)nt,
                                                   d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
                                                   d.tri_hi.as<float4>(), st);
+    if (after_records) CK(cudaEventRecord(after_records, s));
     k_tri_morton<<<blocks_for(nt, bs), bs, 0, s>>>(d.tri_lo.as<float4>(), d.tri_hi.as<float4>(), (uint32_t)nt, st,
                                                    d.keys_in.as<uint64_t>(), d.vals_in.as<uint32_t>());
     d.launches += 2;

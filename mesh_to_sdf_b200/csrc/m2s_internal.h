@@ -145,6 +145,7 @@ struct Device {
     cudaEvent_t ev[8] = {};
     cudaStream_t aux_stream = nullptr;   // high priority: the second half's seed pass hides under the first half's kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_half[2] = {};
+    cudaEvent_t ev_records = nullptr, ev_rows = nullptr;  // the row parities run on aux_stream beside the tree build
     bool split_halves = true;            // M2S_SPLIT=0: one seed pass + one distance launch per slab
     bool last_split = false;
     bool zero_copy = true;               // M2S_ZEROCOPY=0: stage + copy even when the host destination is pinned
@@ -158,12 +159,15 @@ struct Device {
 
 // ---- launchers (each returns the CUDA error of its enqueue) ------------------------------------------
 cudaError_t launch_status_reset(Device& d, bool clear_errors);
+// after_records (optional) is recorded once the original-order triangle records exist (what the row kernels need)
 cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
-                         uint32_t leaf_size);
+                         uint32_t leaf_size, cudaEvent_t after_records = nullptr);
 cudaError_t launch_nodes_interleave(Device& d, float grid_mag);
 cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
 
-cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb);
+// stream / rec default to the device's stream and the leaf-order records
+cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb, cudaStream_t stream = nullptr,
+                             const float4* rec = nullptr);
 
 struct SeedLevel {
     const uint32_t* parent;  // nearest-triangle slots of the parent level (nullptr: start unbounded)

@@ -1702,8 +1702,9 @@ static RowCtx make_row_ctx(const GridParams& g) {
 }
 
 // Row parity bitmaps for the slab [g.x0, g.x1) (all X rows; the Y and Z rows of the slab's planes).
-cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb) {
-    cudaStream_t s = d.stream;
+cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb, cudaStream_t stream, const float4* rec) {
+    cudaStream_t s = stream ? stream : d.stream;
+    if (!rec) rec = d.bvh.rec;
     const uint32_t n[3] = {g.nx, g.ny, g.nz};
     for (int a = 0; a < 3; ++a) {
         const int iy = (a + 1) % 3, iz = (a + 2) % 3;
@@ -1720,10 +1721,10 @@ cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb) {
     CK(d.big_count.ensure(4));
     CK(cudaMemsetAsync(d.big_count.p, 0, 4, s));
     const RowCtx c = make_row_ctx(g);
-    // original-order records would do as well; the sorted copy is the one that stays hot in L2
-    k_rows_small<<<blocks_for(nt, 256), 256, 0, s>>>(d.bvh.rec, nt, c, rb->bits[0], rb->bits[1], rb->bits[2],
+    // any order of the records does: every triangle toggles its own rows
+    k_rows_small<<<blocks_for(nt, 256), 256, 0, s>>>(rec, nt, c, rb->bits[0], rb->bits[1], rb->bits[2],
                                                      d.big_list.as<uint32_t>(), d.big_count.as<uint32_t>());
-    k_rows_big<<<d.sm_count * 4, 256, 0, s>>>(d.bvh.rec, c, rb->bits[0], rb->bits[1], rb->bits[2],
+    k_rows_big<<<d.sm_count * 4, 256, 0, s>>>(rec, c, rb->bits[0], rb->bits[1], rb->bits[2],
                                               d.big_list.as<uint32_t>(), d.big_count.as<uint32_t>());
     for (int a = 0; a < 3; ++a)
         k_rows_scan<<<blocks_for(rb->rows[a], 256), 256, 0, s>>>(rb->bits[a], rb->rows[a], rb->words[a]);

@@ -126,6 +126,8 @@ k_tri_setup(const float* __restrict__ verts, uint32_t nv, const uint32_t* __rest
     }
 }
 
+constexpr int MORTON_BITS = 48;
+
 __device__ __forceinline__ uint64_t spread21(uint32_t v) {
     uint64_t x = v & 0x1fffffu;
     x = (x | x << 32) & 0x1f00000000ffffull;
@@ -148,7 +150,9 @@ __device__ __forceinline__ uint64_t morton63(float x, float y, float z, const Bu
         if (!(u == u)) u = 0.0f;
         q[i] = min((uint32_t)(u * 2097152.0f), 2097151u);
     }
-    return (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    // 16 bits per axis are kept (65 536 cells per axis; equal keys are ordered by index, see delta()): 48-bit keys
+    // sort in 6 radix passes instead of 8
+    return ((spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2])) >> (63 - MORTON_BITS);
 }
 
 // K2: Morton key of the centre of the padded box.
@@ -636,11 +640,11 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     d.launches += 2;
     size_t tmp_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.keys_in.as<uint64_t>(), d.keys_out.as<uint64_t>(),
-                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, 63, s));
+                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, MORTON_BITS, s));
     CK(d.cub_tmp.ensure(tmp_bytes));
     CK(cub::DeviceRadixSort::SortPairs(d.cub_tmp.p, tmp_bytes, d.keys_in.as<uint64_t>(), d.keys_out.as<uint64_t>(),
-                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, 63, s));
-    d.launches += 8;  // CUB onesweep: histogram + 8 digit passes (counted approximately)
+                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, MORTON_BITS, s));
+    d.launches += 8;  // CUB onesweep: histogram + scan + 6 digit passes
     k_tri_permute<<<blocks_for(nt, bs), bs, 0, s>>>(d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
                                                     d.vals_out.as<uint32_t>(), (uint32_t)nt, st,
                                                     d.rec_sorted.as<float4>(), d.tobb.as<float4>(),
@@ -704,11 +708,11 @@ cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq) {
                                                      d.q_vals_in.as<uint32_t>());
     size_t tmp_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.q_keys_in.as<uint64_t>(), d.q_keys_out.as<uint64_t>(),
-                                       d.q_vals_in.as<uint32_t>(), d.q_perm.as<uint32_t>(), (int)nq, 0, 63, s));
+                                       d.q_vals_in.as<uint32_t>(), d.q_perm.as<uint32_t>(), (int)nq, 0, MORTON_BITS, s));
     CK(d.cub_tmp.ensure(tmp_bytes));
     CK(cub::DeviceRadixSort::SortPairs(d.cub_tmp.p, tmp_bytes, d.q_keys_in.as<uint64_t>(),
                                        d.q_keys_out.as<uint64_t>(), d.q_vals_in.as<uint32_t>(),
-                                       d.q_perm.as<uint32_t>(), (int)nq, 0, 63, s));
+                                       d.q_perm.as<uint32_t>(), (int)nq, 0, MORTON_BITS, s));
     k_point_gather<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, d.q_perm.as<uint32_t>(), (uint32_t)nq,
                                                      d.q_sorted.as<float4>());
     d.launches += 11;

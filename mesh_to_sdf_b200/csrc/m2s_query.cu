@@ -791,6 +791,9 @@ __device__ __forceinline__ unsigned long long pack_best(float d2, uint32_t slot)
 #ifndef RUN4_MIN_BLOCKS
 #define RUN4_MIN_BLOCKS 4
 #endif
+#ifndef RUN_WARPS
+#define RUN_WARPS 4  // warps per block: 4 (brick 4 x 8 x 4V) or 8 (two such bricks stacked in z)
+#endif
 
 // SIGN: how the sign is found. RUN_SIGN_NONE / RUN_SIGN_RAYCAST search min |d| (Raycast reads the row parities in
 // the epilogue). RUN_SIGN_NORMAL restates the compare_distances fold (lib.rs:242-259) without its dependence on the
@@ -819,17 +822,18 @@ __device__ __forceinline__ float exact_d2_sign(const Bvh& bvh, uint32_t j, bool 
 }
 
 template <int SIGN, int V, int LAYOUT>
-__global__ void __launch_bounds__(128, V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS)
+__global__ void __launch_bounds__(32 * RUN_WARPS, (V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS) * 4 / RUN_WARPS)
 k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
                    const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
                    BuildStatus* __restrict__ st, uint32_t* tile_slot, const uint32_t seed_planes) {
     constexpr int NV = 32 * V;         // voxels per tile
     constexpr int QCAP = 32 + 2 * NV;  // < 32 items left over + at most 2 leaves x NV voxels appended by one node
-    constexpr uint32_t BZR = 4u * V;   // brick extent in z
-    __shared__ uint2 s_stack[4][PKT_STACK];
-    __shared__ uint2 s_queue[4][QCAP];            // (triangle slot | degen, owner voxel = i * 32 + lane)
-    __shared__ unsigned long long s_best[4][NV];  // per owner voxel: (d2 bits << 32) | [negative bit] | slot
-    __shared__ uint32_t s_pos[4][SIGN == RUN_SIGN_NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
+    constexpr uint32_t BZT = 4u * V;   // extent in z of the 4 warps that share an (x, y) footprint
+    constexpr uint32_t BZR = BZT * (RUN_WARPS / 4);  // brick extent in z
+    __shared__ uint2 s_stack[RUN_WARPS][PKT_STACK];
+    __shared__ uint2 s_queue[RUN_WARPS][QCAP];            // (triangle slot | degen, owner voxel = i * 32 + lane)
+    __shared__ unsigned long long s_best[RUN_WARPS][NV];  // per owner voxel: (d2 bits << 32) | [negative bit] | slot
+    __shared__ uint32_t s_pos[RUN_WARPS][SIGN == RUN_SIGN_NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
     constexpr bool NORMAL = SIGN == RUN_SIGN_NORMAL;
     const unsigned full = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -849,11 +853,11 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     if (LAYOUT == 0) {   // warp (wx, wy), lane (lx:2, ly:4, run:4)
         xr = bx * BX + ((warp >> 1) & 1u) * 2u + (lane >> 4);
         y = by * BY + (warp & 1u) * 4u + ((lane >> 2) & 3u);
-        z0 = bz * BZR + (lane & 3u) * V;
+        z0 = bz * BZR + (warp >> 2) * BZT + (lane & 3u) * V;
     } else {             // warp (wy, wz), lane (lx:4, ly:4, run:2)
         xr = bx * BX + (lane >> 3);
         y = by * BY + ((warp >> 1) & 1u) * 4u + ((lane >> 1) & 3u);
-        z0 = bz * BZR + (warp & 1u) * 2u * V + (lane & 1u) * V;
+        z0 = bz * BZR + (warp >> 2) * BZT + (warp & 1u) * 2u * V + (lane & 1u) * V;
     }
     xr += g.xa - g.x0;  // this launch covers planes [xa, xb) of the slab
     const uint32_t x = g.x0 + xr;
@@ -894,10 +898,10 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const uint32_t back = seed_planes * nby * nbz;  // dispatch distance of that brick
     const uint32_t src_warp = LAYOUT == 0 ? (warp | 2u) : warp, src_idx = LAYOUT == 0 ? (lane & 15u) : (lane & 7u);
     if (tile_slot && blockIdx.x >= back) {
-        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - back) * 4u + src_warp) * 16u + src_idx);
+        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - back) * RUN_WARPS + src_warp) * 16u + src_idx);
         // a straggler: the brick twice as far back has certainly finished (still a good radius)
         if (nseed == 0xffffffffu && blockIdx.x >= 2u * back)
-            nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - 2u * back) * 4u + src_warp) * 16u + src_idx);
+            nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - 2u * back) * RUN_WARPS + src_warp) * 16u + src_idx);
     }
 #ifdef M2S_STATS_BUILD
     if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 4, 1ull);
@@ -1054,17 +1058,19 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             if (qn >= 32) flush(false);
         }
         if (bl && br) {
-            // children ordered by the warp-min lower bound over the voxels that want them
+            // the child most lanes are nearer to goes first (two votes: short latency on the path to the next node
+            // load); the other one is pushed with its warp-min lower bound over the voxels that want it
             float kl = INFINITY, kr = INFINITY;
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 kl = fminf(kl, (hl >> i) & 1u ? dd[i].x : INFINITY);
                 kr = fminf(kr, (hr >> i) & 1u ? dd[i].y : INFINITY);
             }
-            const unsigned ml = __reduce_min_sync(full, __float_as_uint(kl)), mr = __reduce_min_sync(full, __float_as_uint(kr));
-            const bool left_first = ml <= mr;
+            const unsigned pref_l = __ballot_sync(full, kl < kr), pref_r = __ballot_sync(full, kr < kl);
+            const bool left_first = __popc(pref_l) >= __popc(pref_r);
+            const unsigned mfar = __reduce_min_sync(full, __float_as_uint(left_first ? kr : kl));
             if (sp < PKT_STACK) {
-                if (lane == 0) stack[sp] = left_first ? make_uint2(rref, mr) : make_uint2(lref, ml);
+                if (lane == 0) stack[sp] = make_uint2(left_first ? rref : lref, mfar);
                 ++sp;
                 __syncwarp();
             } else {
@@ -1097,7 +1103,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     if (tile_slot && (LAYOUT == 0 ? (lane >= 16u && (warp & 2u)) : lane >= 24u)) {
         // the middle voxel of the run (the first one where the run is cut by the grid's end)
         if (valid[0])
-            __stcg(tile_slot + ((size_t)blockIdx.x * 4u + warp) * 16u + src_idx,
+            __stcg(tile_slot + ((size_t)blockIdx.x * RUN_WARPS + warp) * 16u + src_idx,
                    (valid[V / 2] ? slot[V / 2] : slot[0]) & ~(NORMAL ? RUN_NEG_BIT : 0u));
     }
 
@@ -1802,22 +1808,22 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
         // several voxels per lane. M2S_PAIR: 1 = default (V, LAYOUT) = (2, 0); 4..7 = (2,0) (2,1) (4,0) (4,1)
         const int variant = d.pair < 4 ? 4 : d.pair;
         const uint32_t V = variant >= 6 ? 4u : 2u;
-        const uint32_t bzr = 4u * V;
+        const uint32_t bzr = 4u * V * (RUN_WARPS / 4);
         const uint64_t nrun = (uint64_t)cdiv(g.xb - g.xa, BX) * cdiv(g.ny, BY) * cdiv(g.nz, bzr);
         if (nrun > 0x7fffffffull) return cudaErrorInvalidConfiguration;
         const unsigned nbr = (unsigned)nrun;
-        CK(d.tile_slot.ensure((size_t)nbr * 4 * 16 * 4));
-        CK(cudaMemsetAsync(d.tile_slot.p, 0xff, (size_t)nbr * 4 * 16 * 4, s));
+        CK(d.tile_slot.ensure((size_t)nbr * RUN_WARPS * 16 * 4));
+        CK(cudaMemsetAsync(d.tile_slot.p, 0xff, (size_t)nbr * RUN_WARPS * 16 * 4, s));
         uint32_t* tile_slot = d.tile_slot.as<uint32_t>();
         const uint32_t *b0 = rb ? rb->bits[0] : nullptr, *b1 = rb ? rb->bits[1] : nullptr, *b2 = rb ? rb->bits[2] : nullptr;
         // seeds come from the brick `planes` steps back in x: far enough in dispatch order to have finished
         // (about 1.25 x the resident blocks), at most 4 steps (16 cells)
         const uint32_t plane_bricks = cdiv(g.ny, BY) * cdiv(g.nz, bzr);
-        const uint32_t resident = (uint32_t)d.sm_count * (V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS);
+        const uint32_t resident = (uint32_t)d.sm_count * (V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS) * 4u / RUN_WARPS;
         const uint32_t planes = std::min(4u, std::max(1u, cdiv(resident * 5u / 4u, plane_bricks)));
         CK(launch_nodes_interleave(d, mag));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
         const int sign = rb ? RUN_SIGN_RAYCAST : (mode == MODE_NORMAL ? RUN_SIGN_NORMAL : RUN_SIGN_NONE);
-#define M2S_RUN(SG, VV, LL) k_grid_nearest_run<SG, VV, LL><<<nbr, 128, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes)
+#define M2S_RUN(SG, VV, LL) k_grid_nearest_run<SG, VV, LL><<<nbr, 32 * RUN_WARPS, 0, s>>>(d.bvh, g, mag, b0, b1, b2, d_out, st, tile_slot, planes)
 #define M2S_RUN3(VV, LL)                                            \
     do {                                                            \
         if (sign == RUN_SIGN_RAYCAST) M2S_RUN(RUN_SIGN_RAYCAST, VV, LL); \

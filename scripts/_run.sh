@@ -1,3 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline | python -c "import json,sys; d=json.load(sys.stdin); print({k:d[k] for k in ('value','ms_per_step','phases_ms')}, d['e2e']['value'], d['e2e']['ms_per_step'])"
-python scripts/quick_perf.py C4 C2 | grep rep2
+for v in "" build/libm2s_w8.so; do echo "== lib=$v"; M2S_LIB=$v REPS=4 python scripts/quick_perf.py C3 C3I | grep -E "rep3"; done
+M2S_LIB=build/libm2s_w8.so timeout 300 python -m pytest tests/test_gpu_grid.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -2

@@ -433,7 +433,7 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
         // better served by the axis-aligned box, which is also cheaper to test)
         const float vo = (E.hi[0] - E.lo[0] + 1e-4f) * (E.hi[1] - E.lo[1] + 1e-4f) * (E.hi[2] - E.lo[2] + 1e-4f);
         const float va = (c1.x - c0.x) * (c1.y - c0.y) * (c1.z - c0.z);
-        use_obb = vo <= obb_bias * va;
+        use_obb = vo > 0.0f && isfinite(vo) && vo <= obb_bias * va;  // NaN / overflowed fits fall back to the padded box
     }
     if (lane == 0) {
         if (use_obb) {

@@ -368,7 +368,6 @@ __device__ __forceinline__ float finish(const Bvh& bvh, const f3 p, const Near<M
 // itself stays exact.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BX = 4, BY = 8, BZ = 8;
-constexpr uint32_t SEED_STRIDE = 4;  // ratio between consecutive levels
 
 __device__ __forceinline__ void brick_coords(uint32_t nby, uint32_t nbz, uint32_t* x, uint32_t* y, uint32_t* z) {
     uint32_t bid = blockIdx.x;

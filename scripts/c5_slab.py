@@ -1,3 +1,4 @@
+"""Timing of one 64-plane rank slab of config C5 (1 003 520 triangles, 512^3) through the host entry point (development aid)."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, mesh_to_sdf_b200 as m2s

@@ -942,13 +942,12 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     int overflow = 0;
     uint32_t n_nodes = 0, n_leaves = 0;
 
-    // every lane calls it; bit i of h: this lane's voxel i needs triangle `item`
-    auto enqueue = [&](unsigned h, uint32_t item) {
+    // every lane calls it; w[i]: this lane's voxel i needs triangle `item`
+    auto enqueue = [&](const bool (&w)[V], uint32_t item) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const bool w = (h >> i) & 1u;
-            const unsigned m = __ballot_sync(full, w);
-            if (w) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
+            const unsigned m = __ballot_sync(full, w[i]);
+            if (w[i]) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
             qn += __popc(m);
         }
     };
@@ -1004,6 +1003,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
 
     uint32_t cur = bvh.root;  // always an internal node: leaves are consumed at their parent
     for (;;) {
+        if (qn >= 32) flush(false);  // here, where the loop-carried state merges anyway
         PKT_COUNT(n_nodes);
 #ifdef M2S_STATS_BUILD
         if (bvh.stats && lane == 0) {
@@ -1031,30 +1031,32 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             dd[i] = sumsq2(excess2(__ffma2_rn(s2, f2lo(q3), tu), eu), excess2(__ffma2_rn(s2, f2lo(q5), tv), ev),
                            excess2(__ffma2_rn(s2, f2lo(q7), tw), ew));
         }
-        unsigned hl = 0u, hr = 0u;  // bit i: voxel i wants the left / right child
+        bool wl[V], wr[V];  // voxel i wants the left / right child
+        bool any_l = false, any_r = false;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            hl |= dd[i].x <= bnd[i] ? 1u << i : 0u;
-            hr |= dd[i].y <= bnd[i] ? 1u << i : 0u;
+            wl[i] = dd[i].x <= bnd[i];
+            wr[i] = dd[i].y <= bnd[i];
+            any_l |= wl[i];
+            any_r |= wr[i];
         }
-        unsigned bl = __ballot_sync(full, hl != 0u), br = __ballot_sync(full, hr != 0u);
+        unsigned bl = __ballot_sync(full, any_l), br = __ballot_sync(full, any_r);
         const uint32_t lref = __float_as_uint(q1.z), rref = __float_as_uint(q1.w);
         if ((lref | rref) & LEAF_BIT) {
             if (lref & LEAF_BIT) {
                 if (bl) {
-                    enqueue(hl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    enqueue(wl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
                     PKT_COUNT(n_leaves);
                 }
                 bl = 0u;
             }
             if (rref & LEAF_BIT) {
                 if (br) {
-                    enqueue(hr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    enqueue(wr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
                     PKT_COUNT(n_leaves);
                 }
                 br = 0u;
             }
-            if (qn >= 32) flush(false);
         }
         if (bl && br) {
             // the child most lanes are nearer to goes first (two votes: short latency on the path to the next node
@@ -1062,8 +1064,8 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             float kl = INFINITY, kr = INFINITY;
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                kl = fminf(kl, (hl >> i) & 1u ? dd[i].x : INFINITY);
-                kr = fminf(kr, (hr >> i) & 1u ? dd[i].y : INFINITY);
+                kl = fminf(kl, wl[i] ? dd[i].x : INFINITY);
+                kr = fminf(kr, wr[i] ? dd[i].y : INFINITY);
             }
             const unsigned pref_l = __ballot_sync(full, kl < kr), pref_r = __ballot_sync(full, kr < kl);
             const bool left_first = __popc(pref_l) >= __popc(pref_r);

@@ -1512,12 +1512,11 @@ k_points_run(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, fl
     int qn = 0, sp = 0;
     int overflow = 0;
     uint32_t n_nodes = 0, n_leaves = 0;
-    auto enqueue = [&](unsigned h, uint32_t item) {
+    auto enqueue = [&](const bool (&w)[V], uint32_t item) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const bool w = (h >> i) & 1u;
-            const unsigned m = __ballot_sync(full, w);
-            if (w) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
+            const unsigned m = __ballot_sync(full, w[i]);
+            if (w[i]) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
             qn += __popc(m);
         }
     };
@@ -1575,6 +1574,7 @@ k_points_run(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, fl
 
     uint32_t cur = bvh.root;  // an internal node (the launcher sends single-leaf trees to k_points_pkt)
     for (;;) {
+        if (qn >= 32) flush(false);  // here, where the loop-carried state merges anyway
         PKT_COUNT(n_nodes);
         const float4* nd = bvh.nodes_il + NODE_F4 * (size_t)cur;  // warp-uniform address
         const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
@@ -1592,42 +1592,46 @@ k_points_run(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, fl
             const float2 tw = __ffma2_rn(dz, f2lo(q7), __ffma2_rn(dy, f2hi(q6), __fmul2_rn(dx, f2lo(q6))));
             dd[i] = sumsq2(excess2(tu, eu), excess2(tv, ev), excess2(tw, ew));
         }
-        unsigned hl = 0u, hr = 0u;
+        bool wl[V], wr[V];  // query i wants the left / right child
+        bool any_l = false, any_r = false;
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            hl |= dd[i].x <= bnd[i] ? 1u << i : 0u;
-            hr |= dd[i].y <= bnd[i] ? 1u << i : 0u;
+            wl[i] = dd[i].x <= bnd[i];
+            wr[i] = dd[i].y <= bnd[i];
+            any_l |= wl[i];
+            any_r |= wr[i];
         }
-        unsigned bl = __ballot_sync(full, hl != 0u), br = __ballot_sync(full, hr != 0u);
+        unsigned bl = __ballot_sync(full, any_l), br = __ballot_sync(full, any_r);
         const uint32_t lref = __float_as_uint(q1.z), rref = __float_as_uint(q1.w);
         if ((lref | rref) & LEAF_BIT) {
             if (lref & LEAF_BIT) {
                 if (bl) {
-                    enqueue(hl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    enqueue(wl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
                     PKT_COUNT(n_leaves);
                 }
                 bl = 0u;
             }
             if (rref & LEAF_BIT) {
                 if (br) {
-                    enqueue(hr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    enqueue(wr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
                     PKT_COUNT(n_leaves);
                 }
                 br = 0u;
             }
-            if (qn >= 32) flush(false);
         }
         if (bl && br) {
             float kl = INFINITY, kr = INFINITY;
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                kl = fminf(kl, (hl >> i) & 1u ? dd[i].x : INFINITY);
-                kr = fminf(kr, (hr >> i) & 1u ? dd[i].y : INFINITY);
+                kl = fminf(kl, wl[i] ? dd[i].x : INFINITY);
+                kr = fminf(kr, wr[i] ? dd[i].y : INFINITY);
             }
-            const unsigned ml = __reduce_min_sync(full, __float_as_uint(kl)), mr = __reduce_min_sync(full, __float_as_uint(kr));
-            const bool left_first = ml <= mr;
+            // the child most lanes are nearer to goes first; the other is pushed with its warp-min lower bound
+            const unsigned pref_l = __ballot_sync(full, kl < kr), pref_r = __ballot_sync(full, kr < kl);
+            const bool left_first = __popc(pref_l) >= __popc(pref_r);
+            const unsigned mfar = __reduce_min_sync(full, __float_as_uint(left_first ? kr : kl));
             if (sp < PKT_STACK) {
-                if (lane == 0) stack[sp] = left_first ? make_uint2(rref, mr) : make_uint2(lref, ml);
+                if (lane == 0) stack[sp] = make_uint2(left_first ? rref : lref, mfar);
                 ++sp;
                 __syncwarp();
             } else {

@@ -790,6 +790,9 @@ __device__ __forceinline__ unsigned long long pack_best(float d2, uint32_t slot)
 #ifndef RUN4_MIN_BLOCKS
 #define RUN4_MIN_BLOCKS 4
 #endif
+#ifndef RUN_SEED_BLOCKS
+#define RUN_SEED_BLOCKS 5  // resident blocks per SM assumed when choosing how far back the seeds come from
+#endif
 #ifndef RUN_WARPS
 #define RUN_WARPS 4  // warps per block: 4 (brick 4 x 8 x 4V) or 8 (two such bricks stacked in z)
 #endif
@@ -1824,7 +1827,7 @@ cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L
         // seeds come from the brick `planes` steps back in x: far enough in dispatch order to have finished
         // (about 1.25 x the resident blocks), at most 4 steps (16 cells)
         const uint32_t plane_bricks = cdiv(g.ny, BY) * cdiv(g.nz, bzr);
-        const uint32_t resident = (uint32_t)d.sm_count * (V == 4 ? RUN4_MIN_BLOCKS : RUN2_MIN_BLOCKS) * 4u / RUN_WARPS;
+        const uint32_t resident = (uint32_t)d.sm_count * (V == 4 ? RUN4_MIN_BLOCKS : RUN_SEED_BLOCKS) * 4u / RUN_WARPS;
         const uint32_t planes = std::min(4u, std::max(1u, cdiv(resident * 5u / 4u, plane_bricks)));
         CK(launch_nodes_interleave(d, mag));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
         const int sign = rb ? RUN_SIGN_RAYCAST : (mode == MODE_NORMAL ? RUN_SIGN_NORMAL : RUN_SIGN_NONE);

@@ -134,8 +134,12 @@ def test_multi_device_context_matches_single(m2s):
         assert c2.device_count == 2
         two = c2.grid_sdf(verts, tris, grid, RAYCAST)
         qb = c2.sdf(verts, tris, q, 3, 0)
+        # a pinned destination: every device writes its own slab in place (zero-copy stores)
+        pinned = torch.empty(37 * 20 * 24, dtype=torch.float32).pin_memory()
+        c2.grid_sdf(verts, tris, grid, RAYCAST, pinned.numpy())
     assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
     assert np.array_equal(qa.view(np.uint32), qb.view(np.uint32))
+    assert np.array_equal(one.view(np.uint32), pinned.numpy().view(np.uint32))
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])

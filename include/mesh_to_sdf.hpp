@@ -9,11 +9,15 @@
 //   generate_grid_sdf(&v, Topology, &g, s) generate_grid_sdf(v, topology, grid, sign)  -> std::vector<float>
 //   panic!                                 throws mesh_to_sdf::Panic
 //   trait Point                            any type with .x .y .z floats or operator[] (see point_traits)
+// Extensions that have no counterpart in the crate (they remove copies the GPU path would otherwise pay):
+//   PinnedVec + generate_grid_sdf_into     the result lands in page-locked memory, written by the kernel itself
+//   Mesh                                   upload + LBVH once, then any number of grids / query sets
 #pragma once
 #include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <mutex>
 #include <optional>
@@ -30,6 +34,19 @@ struct Panic : std::runtime_error {
     int status;
     Panic(int s, const std::string& m) : std::runtime_error(m), status(s) {}
 };
+
+namespace detail {
+// a + n * b and a - b * c with the product rounded before the sum: rustc never contracts to FMA, a host compiler
+// may (GCC's default -ffp-contract=fast on aarch64), and Grid must stay bit-identical to src/grid.rs
+inline float mul_then_add(float a, float n, float b) {
+    volatile float prod = n * b;
+    return a + prod;
+}
+inline float mul_then_sub(float a, float b, float c) {
+    volatile float prod = b * c;
+    return a - prod;
+}
+}  // namespace detail
 
 // ---- Point (src/point.rs:21-62): constructor + x/y/z ------------------------------------------------------------
 template <class V, class = void>
@@ -107,16 +124,18 @@ class Grid {
     std::array<size_t, 3> get_cell_count() const { return cell_count_; }
     size_t get_total_cell_count() const { return cell_count_[0] * cell_count_[1] * cell_count_[2]; }
     V get_last_cell() const {
-        return T::make(T::x(first_cell_) + (float)cell_count_[0] * T::x(cell_size_),
-                       T::y(first_cell_) + (float)cell_count_[1] * T::y(cell_size_),
-                       T::z(first_cell_) + (float)cell_count_[2] * T::z(cell_size_));
+        return T::make(detail::mul_then_add(T::x(first_cell_), (float)cell_count_[0], T::x(cell_size_)),
+                       detail::mul_then_add(T::y(first_cell_), (float)cell_count_[1], T::y(cell_size_)),
+                       detail::mul_then_add(T::z(first_cell_), (float)cell_count_[2], T::z(cell_size_)));
     }
     std::pair<V, V> get_bounding_box() const {
-        const float lo[3] = {T::x(first_cell_) - T::x(cell_size_) * 0.5f, T::y(first_cell_) - T::y(cell_size_) * 0.5f,
-                             T::z(first_cell_) - T::z(cell_size_) * 0.5f};
+        const float lo[3] = {detail::mul_then_sub(T::x(first_cell_), T::x(cell_size_), 0.5f),
+                             detail::mul_then_sub(T::y(first_cell_), T::y(cell_size_), 0.5f),
+                             detail::mul_then_sub(T::z(first_cell_), T::z(cell_size_), 0.5f)};
         return {T::make(lo[0], lo[1], lo[2]),
-                T::make(lo[0] + (float)cell_count_[0] * T::x(cell_size_), lo[1] + (float)cell_count_[1] * T::y(cell_size_),
-                        lo[2] + (float)cell_count_[2] * T::z(cell_size_))};
+                T::make(detail::mul_then_add(lo[0], (float)cell_count_[0], T::x(cell_size_)),
+                        detail::mul_then_add(lo[1], (float)cell_count_[1], T::y(cell_size_)),
+                        detail::mul_then_add(lo[2], (float)cell_count_[2], T::z(cell_size_)))};
     }
     size_t get_cell_idx(const std::array<size_t, 3>& c) const {
         return c[2] + cell_count_[2] * (c[1] + cell_count_[1] * c[0]);
@@ -125,8 +144,9 @@ class Grid {
         return {idx / (cell_count_[1] * cell_count_[2]), (idx / cell_count_[2]) % cell_count_[1], idx % cell_count_[2]};
     }
     V get_cell_center(const std::array<size_t, 3>& c) const {
-        return T::make(T::x(first_cell_) + (float)c[0] * T::x(cell_size_), T::y(first_cell_) + (float)c[1] * T::y(cell_size_),
-                       T::z(first_cell_) + (float)c[2] * T::z(cell_size_));
+        return T::make(detail::mul_then_add(T::x(first_cell_), (float)c[0], T::x(cell_size_)),
+                       detail::mul_then_add(T::y(first_cell_), (float)c[1], T::y(cell_size_)),
+                       detail::mul_then_add(T::z(first_cell_), (float)c[2], T::z(cell_size_)));
     }
     SnapResult snap_point_to_grid(const V& p) const {
         const V lo = get_bounding_box().first;
@@ -168,9 +188,18 @@ inline m2s_ctx* context() {
     }();
     return ctx;
 }
+// one facade-wide lock around a call and the read of its error text: the free functions stay callable from any thread
+// and a panic always carries the message of its own call
+inline std::mutex& call_mutex() {
+    static std::mutex mu;
+    return mu;
+}
 inline void check(m2s_ctx* c, m2s_status rc) {
     if (rc == M2S_OK) return;
-    const std::string msg = m2s_last_error(c);
+    char buf[512];
+    buf[0] = '\0';
+    m2s_last_error_copy(c, buf, sizeof buf);
+    const std::string msg = buf;
     if (rc == M2S_ENAN) throw Panic(rc, "NaN distance (" + msg + ")");           // lib.rs:257
     if (rc == M2S_EINDEX) throw Panic(rc, "index out of bounds (" + msg + ")");  // slice index panic
     if (rc == M2S_EEMPTY) throw Panic(rc, "called `Option::unwrap()` on a `None` value (" + msg + ")");  // rtree.rs:117
@@ -197,9 +226,8 @@ std::vector<float> generate_sdf(const std::vector<V>& vertices, Topology<I> indi
     if (tris.empty() && method.kind == AccelerationMethod::RtreeBvh) return {};  // rtree_bvh.rs:104-106
     const std::vector<float> v = detail::pack(vertices), q = detail::pack(query_points);
     std::vector<float> out(query_points.size());
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
     m2s_ctx* c = detail::context();
+    std::lock_guard<std::mutex> lock(detail::call_mutex());
     detail::check(c, m2s_generate_sdf(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, q.data(),
                                       query_points.size(), (int)method.kind, (int)method.sign, out.data()));
     return out;
@@ -216,12 +244,120 @@ std::vector<float> generate_grid_sdf(const std::vector<V>& vertices, Topology<I>
     const float first[3] = {T::x(f), T::y(f), T::z(f)}, size[3] = {T::x(s), T::y(s), T::z(s)};
     const auto n = grid.get_cell_count();
     const uint64_t count[3] = {n[0], n[1], n[2]};
+    // a pageable Vec like the reference's (generate/grid.rs:376): libm2s fills it from its pinned ring with host
+    // threads while the kernel is still running (m2s_timings.host_path == M2S_PATH_PIPELINED for >= 4 MiB)
     std::vector<float> out(grid.get_total_cell_count());
     m2s_ctx* c = detail::context();
+    std::lock_guard<std::mutex> lock(detail::call_mutex());
     detail::check(c, m2s_generate_grid_sdf(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, first, size, count,
                                            (int)sign_method, out.data()));
     return out;
 }
+
+// ---- extensions: page-locked results and mesh handles -----------------------------------------------------------
+
+// A Vec<f32>-like buffer in page-locked, mapped host memory (m2s_host_alloc). generate_grid_sdf_into writes it in
+// place: the distance kernel's own stores cross PCIe while it computes, so there is no staging buffer and no copy.
+class PinnedVec {
+    float* p_ = nullptr;
+    size_t n_ = 0;
+
+  public:
+    PinnedVec() = default;
+    explicit PinnedVec(size_t n) { resize(n); }
+    PinnedVec(const PinnedVec&) = delete;
+    PinnedVec& operator=(const PinnedVec&) = delete;
+    PinnedVec(PinnedVec&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    PinnedVec& operator=(PinnedVec&& o) noexcept {
+        if (this != &o) { m2s_host_free(p_); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    ~PinnedVec() { m2s_host_free(p_); }
+    void resize(size_t n) {  // contents are not preserved
+        if (n == n_) return;
+        m2s_host_free(p_);
+        p_ = nullptr;
+        n_ = 0;
+        void* q = nullptr;
+        if (m2s_host_alloc(n * sizeof(float), &q) != M2S_OK) throw Panic(M2S_ECUDA, "mesh_to_sdf: page-locked allocation failed");
+        p_ = static_cast<float*>(q);
+        n_ = n;
+    }
+    float* data() { return p_; }
+    const float* data() const { return p_; }
+    size_t size() const { return n_; }
+    float& operator[](size_t i) { return p_[i]; }
+    const float& operator[](size_t i) const { return p_[i]; }
+    const float* begin() const { return p_; }
+    const float* end() const { return p_ + n_; }
+};
+
+// generate_grid_sdf into a caller-owned PinnedVec (resized to the grid). Same values as generate_grid_sdf.
+template <class V, class I>
+void generate_grid_sdf_into(const std::vector<V>& vertices, Topology<I> indices, const Grid<V>& grid, SignMethod sign_method,
+                            PinnedVec& out) {
+    using T = point_traits<V>;
+    const std::vector<uint32_t> tris = indices.get_triangles(vertices.size());
+    const std::vector<float> v = detail::pack(vertices);
+    const V f = grid.get_first_cell(), s = grid.get_cell_size();
+    const float first[3] = {T::x(f), T::y(f), T::z(f)}, size[3] = {T::x(s), T::y(s), T::z(s)};
+    const auto n = grid.get_cell_count();
+    const uint64_t count[3] = {n[0], n[1], n[2]};
+    out.resize(grid.get_total_cell_count());
+    m2s_ctx* c = detail::context();
+    std::lock_guard<std::mutex> lock(detail::call_mutex());
+    detail::check(c, m2s_generate_grid_sdf(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, first, size, count,
+                                           (int)sign_method, out.data()));
+}
+
+// How the result of the last grid call reached the host (m2s_host_path_taken) and its phase timings.
+inline m2s_timings last_timings() {
+    m2s_timings t{};
+    m2s_last_timings(detail::context(), &t);
+    return t;
+}
+
+// A mesh uploaded once with its LBVH (m2s_mesh): the reference rebuilds its trees per call; its viewer regenerates
+// the grid of ONE mesh on every parameter change (mesh_to_sdf_client/src/sdf_program.rs:679-721).
+template <class V>
+class Mesh {
+    m2s_mesh* h_ = nullptr;
+
+  public:
+    template <class I>
+    Mesh(const std::vector<V>& vertices, Topology<I> indices) {
+        const std::vector<uint32_t> tris = indices.get_triangles(vertices.size());
+        const std::vector<float> v = detail::pack(vertices);
+        m2s_ctx* c = detail::context();
+        std::lock_guard<std::mutex> lock(detail::call_mutex());
+        detail::check(c, m2s_mesh_create(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, &h_));
+    }
+    Mesh(const Mesh&) = delete;
+    Mesh& operator=(const Mesh&) = delete;
+    ~Mesh() { m2s_mesh_destroy(h_); }
+    std::vector<float> generate_grid_sdf(const Grid<V>& grid, SignMethod sign_method = SignMethod::Raycast) const {
+        using T = point_traits<V>;
+        const V f = grid.get_first_cell(), s = grid.get_cell_size();
+        const float first[3] = {T::x(f), T::y(f), T::z(f)}, size[3] = {T::x(s), T::y(s), T::z(s)};
+        const auto n = grid.get_cell_count();
+        const uint64_t count[3] = {n[0], n[1], n[2]};
+        std::vector<float> out(grid.get_total_cell_count());
+        m2s_ctx* c = detail::context();
+        std::lock_guard<std::mutex> lock(detail::call_mutex());
+        detail::check(c, m2s_mesh_grid_sdf(c, h_, first, size, count, (int)sign_method, 0, n[0], out.data()));
+        return out;
+    }
+    std::vector<float> generate_sdf(const std::vector<V>& query_points, AccelerationMethod method = {}) const {
+        const std::vector<float> q = detail::pack(query_points);
+        std::vector<float> out(query_points.size());
+        m2s_ctx* c = detail::context();
+        std::lock_guard<std::mutex> lock(detail::call_mutex());
+        const m2s_status rc = m2s_mesh_sdf(c, h_, q.data(), query_points.size(), (int)method.kind, (int)method.sign, out.data());
+        if (rc == M2S_EEMPTY && method.kind == AccelerationMethod::RtreeBvh) return {};  // rtree_bvh.rs:104-106
+        detail::check(c, rc);
+        return out;
+    }
+};
 
 // ---- post-passes on a finished grid: what the reference's in-repo caller does next ------------------------------
 // (not part of the crate's API: mesh_to_sdf_client/src/sdf.rs:62-68, :123 and shaders/draw_raymarching.wgsl:118-200)
@@ -234,6 +370,7 @@ inline GridOrder grid_order(const std::vector<float>& sdf) {
     GridOrder r{std::vector<uint32_t>(sdf.size()), 0.0f, 0.0f};
     float mm[2] = {0.0f, 0.0f};
     m2s_ctx* c = detail::context();
+    std::lock_guard<std::mutex> lock(detail::call_mutex());
     detail::check(c, m2s_grid_order(c, sdf.data(), sdf.size(), r.ordered_indices.data(), mm));
     r.min = mm[0];
     r.max = mm[1];
@@ -256,6 +393,7 @@ std::vector<float> sample_grid_sdf(const std::vector<float>& sdf, const Grid<V>&
     const std::vector<float> p = detail::pack(points);
     std::vector<float> out(points.size());
     m2s_ctx* c = detail::context();
+    std::lock_guard<std::mutex> lock(detail::call_mutex());
     detail::check(c, m2s_sample_grid_sdf(c, sdf.data(), first, size, count, p.data(), points.size(), (int)mode, iso,
                                          out.data()));
     return out;

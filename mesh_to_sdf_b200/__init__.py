@@ -26,7 +26,7 @@ LIB_PATH = os.environ.get("M2S_LIB") or os.path.join(_HERE, "libm2s.so")
 
 __all__ = [
     "generate_sdf", "generate_grid_sdf", "Grid", "SnapResult", "Topology", "SignMethod", "AccelerationMethod",
-    "M2SError", "Context", "lib", "LIB_PATH",
+    "M2SError", "Context", "Mesh", "lib", "LIB_PATH", "host_alloc", "host_register", "host_unregister",
 ]
 
 _f = C.POINTER(C.c_float)
@@ -49,10 +49,20 @@ _STATUS_NAMES = {0: "M2S_OK", 1: "M2S_EINVAL", 2: "M2S_EINDEX", 3: "M2S_ENAN", 4
 
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("build_ms", C.c_float), ("sign_ms", C.c_float), ("dist_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("seed_ms", C.c_float)]
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("seed_ms", C.c_float), ("host_path", C.c_int)]
 
     def as_dict(self):
-        return {k: float(getattr(self, k)) for k, _ in self._fields_}
+        d = {k: float(getattr(self, k)) for k, _ in self._fields_ if k != "host_path"}
+        d["host_path"] = HOST_PATH_NAMES.get(int(self.host_path), str(int(self.host_path)))
+        return d
+
+
+# m2s_host_path_taken (m2s.h): how the result of the last call reached its host destination
+HOST_PATH_NAMES = {0: "device", 1: "zerocopy", 2: "pipelined", 3: "staged", 4: "registered"}
+# m2s_set_option keys / values (m2s.h)
+OPT_BUILD_MODE, OPT_HOST_PATH, OPT_COPY_THREADS = 1, 2, 3
+BUILD_REPLICATED, BUILD_BROADCAST = 0, 1
+HOST_AUTO, HOST_STAGED, HOST_PIPELINED, HOST_REGISTER = 0, 1, 2, 3
 
 
 _lib = None
@@ -77,6 +87,27 @@ def lib() -> C.CDLL:
             L.m2s_last_error.argtypes = [vp]
             L.m2s_last_error.restype = C.c_char_p
             L.m2s_last_timings.argtypes = [vp, C.POINTER(Timings)]
+            L.m2s_last_timings_device.argtypes = [vp, C.c_int, C.POINTER(Timings)]
+            L.m2s_last_error_copy.argtypes = [vp, C.c_char_p, C.c_size_t]
+            L.m2s_set_option.argtypes = [vp, C.c_int, C.c_int64]
+            L.m2s_mesh_create.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(vp)]
+            L.m2s_mesh_create_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(vp)]
+            L.m2s_mesh_destroy.argtypes = [vp]
+            L.m2s_mesh_destroy.restype = None
+            L.m2s_mesh_grid_sdf.argtypes = [vp, vp, _f, _f, _u64, C.c_int, C.c_uint64, C.c_uint64, vp]
+            L.m2s_mesh_grid_sdf_device.argtypes = [vp, vp, _f, _f, _u64, C.c_int, C.c_uint64, C.c_uint64, vp]
+            L.m2s_mesh_sdf.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp]
+            L.m2s_mesh_sdf_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp]
+            L.m2s_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+            L.m2s_host_free.argtypes = [vp]
+            L.m2s_host_free.restype = None
+            L.m2s_host_register.argtypes = [vp, C.c_size_t]
+            L.m2s_host_unregister.argtypes = [vp]
+            L.m2s_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+            L.m2s_device_free.argtypes = [vp, vp]
+            L.m2s_ipc_export.argtypes = [vp, vp, C.c_char_p]
+            L.m2s_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+            L.m2s_ipc_close.argtypes = [vp, vp]
             L.m2s_launch_count.argtypes = [vp]
             L.m2s_launch_count.restype = C.c_uint64
             L.m2s_device_count.argtypes = [vp]
@@ -272,6 +303,8 @@ class Context:
     def __init__(self, devices: Optional[Sequence[int]] = None, stream: Optional[int] = None):
         L = lib()
         self._h = C.c_void_p()
+        # one call at a time per context, and the error text is read before another thread's call can replace it
+        self._lock = threading.RLock()
         if stream is not None:
             dev = 0 if not devices else int(devices[0])
             rc = L.m2s_create_on_stream(dev, C.c_void_p(stream), C.byref(self._h))
@@ -304,7 +337,17 @@ class Context:
 
     def _check(self, rc: int):
         if rc != M2S_OK:
-            raise M2SError(rc, (lib().m2s_last_error(self._h) or b"").decode())
+            buf = C.create_string_buffer(512)
+            lib().m2s_last_error_copy(self._h, buf, len(buf))
+            raise M2SError(rc, buf.value.decode(errors="replace"))
+
+    def _call(self, fn, *args):
+        with self._lock:
+            self._check(fn(self._h, *args))
+
+    def set_option(self, option: int, value: int):
+        """``m2s_set_option``: OPT_BUILD_MODE / OPT_HOST_PATH / OPT_COPY_THREADS."""
+        self._call(lib().m2s_set_option, int(option), int(value))
 
     @property
     def launch_count(self) -> int:
@@ -314,40 +357,33 @@ class Context:
     def device_count(self) -> int:
         return int(lib().m2s_device_count(self._h))
 
-    def timings(self) -> dict:
+    def timings(self, device_index: int = 0) -> dict:
         t = Timings()
-        lib().m2s_last_timings(self._h, C.byref(t))
+        lib().m2s_last_timings_device(self._h, int(device_index), C.byref(t))
         return t.as_dict()
 
     def synchronize(self):
-        self._check(lib().m2s_synchronize(self._h))
+        self._call(lib().m2s_synchronize)
 
     # host-buffer entry points (numpy in, numpy out)
     def grid_sdf(self, verts: np.ndarray, tris: np.ndarray, grid: Grid, sign: int, out: Optional[np.ndarray] = None):
         verts, tris = _mesh_arrays(verts, tris)
-        total = grid.get_total_cell_count()
-        if out is None:
-            out = np.empty(total, np.float32)
-        assert out.dtype == np.float32 and out.size == total and out.flags.c_contiguous
+        out = _out_array(out, grid.get_total_cell_count())
         cc = np.asarray(grid.cell_count, np.uint64)
-        self._check(lib().m2s_generate_grid_sdf(self._h, verts.ctypes.data, len(verts), tris.ctypes.data, len(tris),
-                                                grid.first_cell.ctypes.data_as(_f), grid.cell_size.ctypes.data_as(_f),
-                                                cc.ctypes.data_as(_u64), int(sign), out.ctypes.data))
+        self._call(lib().m2s_generate_grid_sdf, verts.ctypes.data, len(verts), tris.ctypes.data, len(tris),
+                   grid.first_cell.ctypes.data_as(_f), grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
+                   int(sign), out.ctypes.data)
         return out
 
     def grid_sdf_slab(self, verts: np.ndarray, tris: np.ndarray, grid: Grid, sign: int, x_begin: int, x_end: int,
                       out: Optional[np.ndarray] = None):
         """Cells x in [x_begin, x_end) of ``grid`` (the per-rank call of a one-process-per-GPU deployment)."""
         verts, tris = _mesh_arrays(verts, tris)
-        n = (x_end - x_begin) * grid.cell_count[1] * grid.cell_count[2]
-        if out is None:
-            out = np.empty(n, np.float32)
-        assert out.dtype == np.float32 and out.size == n and out.flags.c_contiguous
+        out = _out_array(out, max(0, x_end - x_begin) * grid.cell_count[1] * grid.cell_count[2])
         cc = np.asarray(grid.cell_count, np.uint64)
-        self._check(lib().m2s_generate_grid_sdf_slab(self._h, verts.ctypes.data, len(verts), tris.ctypes.data,
-                                                     len(tris), grid.first_cell.ctypes.data_as(_f),
-                                                     grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
-                                                     int(sign), x_begin, x_end, out.ctypes.data))
+        self._call(lib().m2s_generate_grid_sdf_slab, verts.ctypes.data, len(verts), tris.ctypes.data, len(tris),
+                   grid.first_cell.ctypes.data_as(_f), grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
+                   int(sign), x_begin, x_end, out.ctypes.data)
         return out
 
     def debug_stats(self):
@@ -359,26 +395,50 @@ class Context:
             out: Optional[np.ndarray] = None):
         verts, tris = _mesh_arrays(verts, tris)
         queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
-        if out is None:
-            out = np.empty(len(queries), np.float32)
-        self._check(lib().m2s_generate_sdf(self._h, verts.ctypes.data, len(verts), tris.ctypes.data, len(tris),
-                                           queries.ctypes.data, len(queries), int(accel), int(sign), out.ctypes.data))
+        out = _out_array(out, len(queries))
+        self._call(lib().m2s_generate_sdf, verts.ctypes.data, len(verts), tris.ctypes.data, len(tris),
+                   queries.ctypes.data, len(queries), int(accel), int(sign), out.ctypes.data)
         return out
 
     # device-buffer entry points (raw device pointers as ints; enqueue only)
     def grid_sdf_device(self, d_verts: int, nv: int, d_tris: int, nt: int, grid: Grid, sign: int, x_begin: int,
                         x_end: int, d_out: int):
         cc = np.asarray(grid.cell_count, np.uint64)
-        self._check(lib().m2s_generate_grid_sdf_device(self._h, d_verts, nv, d_tris, nt,
-                                                       grid.first_cell.ctypes.data_as(_f),
-                                                       grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
-                                                       int(sign), x_begin, x_end, d_out))
+        self._call(lib().m2s_generate_grid_sdf_device, d_verts, nv, d_tris, nt, grid.first_cell.ctypes.data_as(_f),
+                   grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64), int(sign), x_begin, x_end, d_out)
 
     def sdf_device(self, d_verts: int, nv: int, d_tris: int, nt: int, d_queries: int, nq: int, accel: int, sign: int,
                    d_out: int):
-        self._check(lib().m2s_generate_sdf_device(self._h, d_verts, nv, d_tris, nt, d_queries, nq, int(accel),
-                                                  int(sign), d_out))
+        self._call(lib().m2s_generate_sdf_device, d_verts, nv, d_tris, nt, d_queries, nq, int(accel), int(sign), d_out)
 
+    # mesh handles: upload + build once, query many times
+    def mesh(self, verts: np.ndarray, tris: np.ndarray) -> "Mesh":
+        return Mesh(self, verts, tris)
+
+    def mesh_device(self, d_verts: int, nv: int, d_tris: int, nt: int) -> "Mesh":
+        return Mesh(self, None, None, device_ptrs=(d_verts, nv, d_tris, nt))
+
+    # device memory that other processes can map (one process per GPU): see m2s.h
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._call(lib().m2s_device_alloc, nbytes, C.byref(p))
+        return int(p.value)
+
+    def device_free(self, d_ptr: int):
+        self._call(lib().m2s_device_free, d_ptr)
+
+    def ipc_export(self, d_ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._call(lib().m2s_ipc_export, d_ptr, buf)
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._call(lib().m2s_ipc_open, C.create_string_buffer(bytes(handle), 64), C.byref(p))
+        return int(p.value)
+
+    def ipc_close(self, d_ptr: int):
+        self._call(lib().m2s_ipc_close, d_ptr)
 
     # post-passes on a finished grid (what the reference's in-repo caller runs next, mesh_to_sdf_client/src/sdf.rs)
     def grid_order(self, sdf, want_order: bool = True, want_minmax: bool = True):
@@ -386,12 +446,12 @@ class Context:
         sdf = np.ascontiguousarray(sdf, np.float32).reshape(-1)
         order = np.empty(len(sdf), np.uint32) if want_order else None
         mm = np.zeros(2, np.float32) if want_minmax else None
-        self._check(lib().m2s_grid_order(self._h, sdf.ctypes.data, len(sdf), order.ctypes.data if want_order else None,
-                                         mm.ctypes.data if want_minmax else None))
+        self._call(lib().m2s_grid_order, sdf.ctypes.data, len(sdf), order.ctypes.data if want_order else None,
+                   mm.ctypes.data if want_minmax else None)
         return order, (None if mm is None else (mm[0], mm[1]))
 
     def grid_order_device(self, d_sdf: int, n: int, d_order: int, d_minmax: int):
-        self._check(lib().m2s_grid_order_device(self._h, d_sdf, n, d_order or None, d_minmax or None))
+        self._call(lib().m2s_grid_order_device, d_sdf, n, d_order or None, d_minmax or None)
 
     def sample_grid_sdf(self, sdf, grid: Grid, points, mode: int = 1, iso: float = 0.0) -> np.ndarray:
         """sdf_grid() of draw_raymarching.wgsl:118-200 at arbitrary points; mode 0 snap, 1 trilinear, 2 tetrahedral."""
@@ -401,23 +461,134 @@ class Context:
         if len(sdf) != int(np.prod(cc)):
             raise ValueError("sdf length does not match the grid")
         out = np.empty(len(pts), np.float32)
-        self._check(lib().m2s_sample_grid_sdf(self._h, sdf.ctypes.data, grid.first_cell.ctypes.data_as(_f),
-                                              grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
-                                              pts.ctypes.data, len(pts), int(mode), float(iso), out.ctypes.data))
+        self._call(lib().m2s_sample_grid_sdf, sdf.ctypes.data, grid.first_cell.ctypes.data_as(_f),
+                   grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64), pts.ctypes.data, len(pts), int(mode),
+                   float(iso), out.ctypes.data)
         return out
 
     def sample_grid_sdf_device(self, d_sdf: int, grid: Grid, d_points: int, n_points: int, mode: int, iso: float,
                                d_out: int):
         cc = np.asarray(grid.cell_count, np.uint64)
-        self._check(lib().m2s_sample_grid_sdf_device(self._h, d_sdf, grid.first_cell.ctypes.data_as(_f),
-                                                     grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64),
-                                                     d_points, n_points, int(mode), float(iso), d_out))
+        self._call(lib().m2s_sample_grid_sdf_device, d_sdf, grid.first_cell.ctypes.data_as(_f),
+                   grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64), d_points, n_points, int(mode),
+                   float(iso), d_out)
 
 
 def _mesh_arrays(verts, tris):
     verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
     tris = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
     return verts, tris
+
+
+def _out_array(out, n: int) -> np.ndarray:
+    """The destination libm2s writes ``n`` float32 into: allocated here, or the caller's array after checking that
+    it is exactly that (a wrong dtype / size / stride would make the library write past the buffer)."""
+    if out is None:
+        return np.empty(n, np.float32)
+    if not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.size != n or not out.flags.c_contiguous \
+            or not out.flags.writeable:
+        raise ValueError(f"out must be a writeable C-contiguous float32 array of {n} elements")
+    return out
+
+
+class Mesh:
+    """``m2s_mesh``: a mesh uploaded once with its LBVH on every device of the context. Calls on it pay neither the
+    upload nor the build (the reference's viewer regenerates the grid of one mesh on every parameter change,
+    mesh_to_sdf_client/src/sdf_program.rs:679-721). Destroy it before its context."""
+
+    def __init__(self, ctx: "Context", verts, tris, device_ptrs=None):
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        if device_ptrs is not None:
+            d_verts, nv, d_tris, nt = device_ptrs
+            ctx._call(lib().m2s_mesh_create_device, d_verts, nv, d_tris, nt, C.byref(self._h))
+        else:
+            verts, tris = _mesh_arrays(verts, tris)
+            ctx._call(lib().m2s_mesh_create, verts.ctypes.data, len(verts), tris.ctypes.data, len(tris),
+                      C.byref(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value and self._ctx._h.value:
+            lib().m2s_mesh_destroy(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def grid_sdf(self, grid: Grid, sign: int, x_begin: int = 0, x_end: Optional[int] = None,
+                 out: Optional[np.ndarray] = None) -> np.ndarray:
+        x_end = grid.cell_count[0] if x_end is None else x_end
+        out = _out_array(out, max(0, x_end - x_begin) * grid.cell_count[1] * grid.cell_count[2])
+        cc = np.asarray(grid.cell_count, np.uint64)
+        self._ctx._call(lib().m2s_mesh_grid_sdf, self._h, grid.first_cell.ctypes.data_as(_f),
+                        grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64), int(sign), x_begin, x_end,
+                        out.ctypes.data)
+        return out
+
+    def grid_sdf_device(self, grid: Grid, sign: int, x_begin: int, x_end: int, d_out: int):
+        cc = np.asarray(grid.cell_count, np.uint64)
+        self._ctx._call(lib().m2s_mesh_grid_sdf_device, self._h, grid.first_cell.ctypes.data_as(_f),
+                        grid.cell_size.ctypes.data_as(_f), cc.ctypes.data_as(_u64), int(sign), x_begin, x_end, d_out)
+
+    def sdf(self, queries, accel: int, sign: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+        out = _out_array(out, len(queries))
+        self._ctx._call(lib().m2s_mesh_sdf, self._h, queries.ctypes.data, len(queries), int(accel), int(sign),
+                        out.ctypes.data)
+        return out
+
+    def sdf_device(self, d_queries: int, nq: int, accel: int, sign: int, d_out: int):
+        self._ctx._call(lib().m2s_mesh_sdf_device, self._h, d_queries, nq, int(accel), int(sign), d_out)
+
+
+class PinnedArray:
+    """float32 array in page-locked, mapped host memory from ``m2s_host_alloc``: a destination the distance kernel
+    writes in place (no staging, no copy). ``.array`` is the numpy view; free with ``close()``."""
+
+    def __init__(self, n: int):
+        self._p = C.c_void_p()
+        rc = lib().m2s_host_alloc(max(1, n) * 4, C.byref(self._p))
+        if rc != M2S_OK:
+            raise M2SError(rc, "m2s_host_alloc failed")
+        self.array = np.ctypeslib.as_array(C.cast(self._p, _f), shape=(n,))
+
+    def close(self):
+        if self._p.value:
+            self.array = None
+            lib().m2s_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_alloc(n: int) -> PinnedArray:
+    return PinnedArray(n)
+
+
+def host_register(a: np.ndarray):
+    """Page-locks memory the caller owns (``m2s_host_register``); unregister before freeing it."""
+    rc = lib().m2s_host_register(a.ctypes.data, a.nbytes)
+    if rc != M2S_OK:
+        raise M2SError(rc, "m2s_host_register failed")
+
+
+def host_unregister(a: np.ndarray):
+    rc = lib().m2s_host_unregister(a.ctypes.data)
+    if rc != M2S_OK:
+        raise M2SError(rc, "m2s_host_unregister failed")
 
 
 _default_ctx: Optional[Context] = None

@@ -16,15 +16,18 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libm2s.so")
-SOURCES = ["m2s_build.cu", "m2s_query.cu", "m2s_post.cu", "m2s_api.cu"]
-HEADERS = ["m2s_geom.cuh", "m2s_internal.h", os.path.join("..", "..", "include", "m2s.h")]
+SOURCES = ["m2s_build.cu", "m2s_grid.cu", "m2s_points.cu", "m2s_post.cu", "m2s_api.cu"]
+HEADERS = ["m2s_geom.cuh", "m2s_search.cuh", "m2s_internal.h", os.path.join("..", "..", "include", "m2s.h")]
 
-NVCC_FLAGS = [
+NVCC_COMPILE = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-Xptxas", "-v",
+]
+NVCC_LINK = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-cudart", "static", "-lpthread",
 ]
 
 
@@ -43,24 +46,43 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
-    """out: alternative output path for development A/B builds (loaded with M2S_LIB=<path>)."""
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra: list | None = None) -> str:
+    """Compiles every translation unit in parallel (one nvcc each) and links them. out / extra: alternative output
+    path and extra nvcc flags for development A/B builds (loaded with M2S_LIB=<path>)."""
     if out is None and not force and not is_stale():
         return SO
-    extra = os.environ.get("M2S_NVCC_EXTRA", "").split()  # development: e.g. -DPKT_MIN_BLOCKS=5
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", out or SO] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    log = r.stdout + r.stderr
+    extra = list(extra or []) + os.environ.get("M2S_NVCC_EXTRA", "").split()  # development: e.g. -DRUN_MIN_BLOCKS=6
+    target = out or SO
+    objdir = os.path.join(HERE, "..", "build", "obj_" + os.path.basename(target).replace(".", "_"))
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = nvcc_path()
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_COMPILE + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, failed = "", False
+    for cmd, obj, p in procs:
+        o, _ = p.communicate()
+        log += " ".join(cmd) + "\n" + o
+        failed |= p.returncode != 0
+    if not failed:
+        cmd = [nvcc] + NVCC_LINK + ["-o", target] + [obj for _, obj, _ in procs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + r.stdout + r.stderr
+        failed |= r.returncode != 0
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if r.returncode != 0:
+        f.write(log)
+    if failed:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libm2s.so")
     if verbose:
         print(log)
-    return out or SO
+    return target
 
 
 if __name__ == "__main__":
     _out = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=_out[0] if _out else None))
+    _extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=_out[0] if _out else None,
+                extra=_extra))

@@ -1,5 +1,5 @@
-// LBVH build on the GPU: triangle records -> 63-bit Morton keys -> radix sort -> Karras hierarchy
-// over leaves of K consecutive sorted triangles -> bottom-up refit.
+// LBVH build on the GPU: triangle records -> 48-bit Morton keys -> radix sort -> Karras hierarchy over
+// single-triangle leaves -> bottom-up refit -> oriented boxes per child slot.
 //
 // Replaces the reference's per-call acceleration-structure builds: bvh::Bvh::build_par
 // (mesh_to_sdf/src/generate/grid.rs:95-111, generic/bvh.rs:62-74, generic/rtree_bvh.rs:108-116) and
@@ -36,6 +36,37 @@ void DevBuf::release() {
     cap = 0;
 }
 
+cudaError_t PinBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) {
+        cudaError_t e = cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        if (e != cudaSuccess) return e;
+    }
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return e;
+    }
+    cap = want;
+    return cudaSuccess;
+}
+void PinBuf::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
+void MeshDev::release() {
+    DevBuf* bufs[] = {&rec_sorted, &tri_id_sorted, &nodes, &nodes_il, &boxes, &status, &node_range};
+    for (DevBuf* b : bufs) b->release();
+    bvh = Bvh{};
+    nv = nt = 0;
+    nodes_il_mag = -1.0f;
+}
+
 namespace {
 
 // order-preserving float <-> int mapping for atomicMin/atomicMax
@@ -54,18 +85,39 @@ __device__ __forceinline__ float scene_mag(const BuildStatus* __restrict__ st) {
     return m;
 }
 
-__global__ void k_status_init(BuildStatus* st, int clear_errors) {
+// The mesh's status block: error flags of the mesh (bad index, non-finite vertex), degenerate count, bounds.
+__global__ void k_mesh_status_init(BuildStatus* st) {
     if (threadIdx.x == 0) {
-        if (clear_errors) {
-            st->bad_index = 0;
-            st->nonfinite = 0;
-            st->stack_overflow = 0;
-            st->nan_distance = 0;
-        }
+        st->bad_index = 0;
+        st->nonfinite = 0;
+        st->stack_overflow = 0;
+        st->nan_distance = 0;
         st->n_degenerate = 0;
         for (int i = 0; i < 3; ++i) {
             st->lo[i] = f2ord(INFINITY);
             st->hi[i] = f2ord(-INFINITY);
+        }
+    }
+}
+
+// The call's status block starts from the mesh's (bounds, mesh errors); the sticky error flags of earlier device
+// calls survive until the host has read them (clear_errors).
+__global__ void k_call_status_init(BuildStatus* st, const BuildStatus* mesh, int clear_errors) {
+    if (threadIdx.x == 0) {
+        const int bad = mesh ? mesh->bad_index : 0, nonf = mesh ? mesh->nonfinite : 0;
+        if (clear_errors) {
+            st->bad_index = bad;
+            st->nonfinite = nonf;
+            st->stack_overflow = 0;
+            st->nan_distance = 0;
+        } else {
+            st->bad_index |= bad;
+            st->nonfinite |= nonf;
+        }
+        st->n_degenerate = mesh ? mesh->n_degenerate : 0;
+        for (int i = 0; i < 3; ++i) {
+            st->lo[i] = mesh ? mesh->lo[i] : f2ord(INFINITY);
+            st->hi[i] = mesh ? mesh->hi[i] : f2ord(-INFINITY);
         }
     }
 }
@@ -348,7 +400,7 @@ k_tri_permute(const float4* __restrict__ rec, const float4* __restrict__ tri_lo,
 constexpr uint32_t OBB_MAX_TRIS = M2S_OBB_MAX_TRIS;
 
 __global__ void __launch_bounds__(256)
-k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__ tobb, uint32_t nt, uint32_t K,
+k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__ tobb, uint32_t nt,
                int nleaf, const float4* __restrict__ boxes, float4* __restrict__ nodes,
                const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st, float obb_bias) {
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -360,22 +412,20 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
     const uint32_t ref = __float_as_uint(c0.w);
     uint32_t l0, l1;
     if (ref & LEAF_BIT) {
-        l0 = l1 = ref & LEAF_INDEX_MASK;
-        if (K == 1u) {
-            // single-triangle leaf: its oriented box was already fitted by k_tri_permute
-            if (lane < 4) {
-                float4 v = tobb[4 * (size_t)l0 + lane];
-                if (lane == 0) v.w = __uint_as_float(ref);
-                ch[lane] = v;
-            }
-            return;
+        // single-triangle leaf: its oriented box was already fitted by k_tri_permute
+        l0 = ref & LEAF_INDEX_MASK;
+        if (lane < 4) {
+            float4 v = tobb[4 * (size_t)l0 + lane];
+            if (lane == 0) v.w = __uint_as_float(ref);
+            ch[lane] = v;
         }
+        return;
     } else {
         const uint2 r = node_range[ref];
         l0 = r.x;
         l1 = r.y;
     }
-    const uint32_t b = l0 * K, e = min(nt, (l1 + 1) * K);
+    const uint32_t b = l0, e = min(nt, l1 + 1);
     const float3 origin = make_float3(0.5f * (c0.x + c1.x), 0.5f * (c0.y + c1.y), 0.5f * (c0.z + c1.z));
     const unsigned full = 0xffffffffu;
     bool use_obb = (e - b) <= OBB_MAX_TRIS;
@@ -480,35 +530,35 @@ k_nodes_interleave(const float4* __restrict__ nodes, uint32_t n_nodes, float4* _
     }
 }
 
-// Karras 2012 delta over the leaf keys (leaf l's key = key of its first sorted triangle).
-__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, int i, int j) {
+// Karras 2012 delta over the leaf keys (leaf l = sorted triangle l; equal keys are ordered by index).
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int nleaf, int i, int j) {
     if (j < 0 || j >= nleaf) return -1;
-    const uint64_t a = keys[(size_t)i * K], b = keys[(size_t)j * K];
+    const uint64_t a = keys[i], b = keys[j];
     if (a == b) return 64 + __clz(i ^ j);
     return __clzll((long long)(a ^ b));
 }
 
 // K4b: one thread per internal node: children + parent links.
 __global__ void __launch_bounds__(256)
-k_hierarchy(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, float4* __restrict__ nodes,
+k_hierarchy(const uint64_t* __restrict__ keys, int nleaf, float4* __restrict__ nodes,
             uint32_t* __restrict__ leaf_parent, uint32_t* __restrict__ node_parent,
             uint2* __restrict__ node_range) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nleaf - 1) return;
-    const int d = (delta(keys, K, nleaf, i, i + 1) - delta(keys, K, nleaf, i, i - 1)) >= 0 ? 1 : -1;
-    const int dmin = delta(keys, K, nleaf, i, i - d);
+    const int d = (delta(keys, nleaf, i, i + 1) - delta(keys, nleaf, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, nleaf, i, i - d);
     int lmax = 2;
-    while (delta(keys, K, nleaf, i, i + lmax * d) > dmin) lmax <<= 1;
+    while (delta(keys, nleaf, i, i + lmax * d) > dmin) lmax <<= 1;
     int l = 0;
     for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (delta(keys, K, nleaf, i, i + (l + t) * d) > dmin) l += t;
+        if (delta(keys, nleaf, i, i + (l + t) * d) > dmin) l += t;
     const int j = i + l * d;
-    const int dnode = delta(keys, K, nleaf, i, j);
+    const int dnode = delta(keys, nleaf, i, j);
     int s = 0;
     int t = l;
     do {
         t = (t + 1) >> 1;
-        if (delta(keys, K, nleaf, i, i + (s + t) * d) > dnode) s += t;
+        if (delta(keys, nleaf, i, i + (s + t) * d) > dnode) s += t;
     } while (t > 1);
     const int gamma = i + s * d + min(d, 0);
     const int lo = min(i, j), hi = max(i, j);
@@ -537,22 +587,17 @@ k_hierarchy(const uint64_t* __restrict__ keys, uint32_t K, int nleaf, float4* __
 // K4c: bottom-up refit. One thread per leaf; the second thread to reach a node continues upwards.
 __global__ void __launch_bounds__(256)
 k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
-        const uint32_t* __restrict__ order, uint32_t nt, uint32_t K, int nleaf, float4* nodes,
+        const uint32_t* __restrict__ order, int nleaf, float4* nodes,
         const uint32_t* __restrict__ leaf_parent, const uint32_t* __restrict__ node_parent,
         uint32_t* __restrict__ node_flag) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nleaf) return;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    bool degen = false;
-    const uint32_t b = (uint32_t)l * K, e = min(nt, b + K);
-    for (uint32_t j = b; j < e; ++j) {
-        const uint32_t t = order[j];
-        const float4 tl = tri_lo[t], th = tri_hi[t];
-        lo[0] = fminf(lo[0], tl.x); lo[1] = fminf(lo[1], tl.y); lo[2] = fminf(lo[2], tl.z);
-        hi[0] = fmaxf(hi[0], th.x); hi[1] = fmaxf(hi[1], th.y); hi[2] = fmaxf(hi[2], th.z);
-        degen |= (tl.w != 0.0f);
-    }
-    if (nleaf == 1) return;  // the root is this leaf; nothing to refit
+    float lo[3], hi[3];
+    const uint32_t t = order[l];
+    const float4 tl = tri_lo[t], th = tri_hi[t];
+    lo[0] = tl.x; lo[1] = tl.y; lo[2] = tl.z;
+    hi[0] = th.x; hi[1] = th.y; hi[2] = th.z;
+    const bool degen = tl.w != 0.0f;
     uint32_t link = leaf_parent[l];
     bool first_level = true;
     for (;;) {
@@ -580,6 +625,33 @@ k_refit(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi,
     }
 }
 
+// A mesh of ONE triangle: node 0 = (the triangle, an unreachable copy of it), so that every tree has an internal
+// root and the query kernels need no special case. The copy's search box has extents of -1e30 (every bound
+// saturates), its ray box is empty (lo = +inf, hi = -inf).
+__global__ void k_single_root(const float4* __restrict__ tobb, const float4* __restrict__ tri_lo,
+                              const float4* __restrict__ tri_hi, float4* __restrict__ nodes, float4* __restrict__ boxes,
+                              uint2* __restrict__ node_range) {
+    if (threadIdx.x != 0) return;
+    const bool degen = tri_lo[0].w != 0.0f;
+    const uint32_t ref = LEAF_BIT | (degen ? LEAF_DEGEN_BIT : 0u);
+    float4 c = tobb[0];
+    c.w = __uint_as_float(ref);
+    nodes[0] = c;
+    nodes[1] = tobb[1];
+    nodes[2] = tobb[2];
+    nodes[3] = tobb[3];
+    nodes[4] = c;
+    nodes[5] = make_float4(1.f, 0.f, 0.f, -1.0e30f);
+    nodes[6] = make_float4(0.f, 1.f, 0.f, -1.0e30f);
+    nodes[7] = make_float4(0.f, 0.f, 1.f, -1.0e30f);
+    const float4 l = tri_lo[0], h = tri_hi[0];
+    boxes[0] = make_float4(l.x, l.y, l.z, __uint_as_float(ref));
+    boxes[1] = make_float4(h.x, h.y, h.z, 0.0f);
+    boxes[2] = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(ref));
+    boxes[3] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+    node_range[0] = make_uint2(0u, 0u);
+}
+
 }  // namespace
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -590,41 +662,51 @@ static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((
         if (e__ != cudaSuccess) return e__; \
     } while (0)
 
-// Resets the per-call part of the status block (scene bounds, degenerate count) and, on request, the
-// sticky error flags.
-cudaError_t launch_status_reset(Device& d, bool clear_errors) {
-    const bool fresh = d.status.p == nullptr;
-    CK(d.status.ensure(sizeof(BuildStatus)));
-    k_status_init<<<1, 32, 0, d.stream>>>(d.status.as<BuildStatus>(), (clear_errors || fresh) ? 1 : 0);
+// The mesh's own status block (bounds + mesh errors), written by the build.
+cudaError_t launch_mesh_status_reset(Device& d, MeshDev& m) {
+    CK(m.status.ensure(sizeof(BuildStatus)));
+    k_mesh_status_init<<<1, 32, 0, d.stream>>>(m.status.as<BuildStatus>());
     d.launches++;
     return cudaGetLastError();
 }
 
-// Builds records + LBVH for (d_verts, d_tris) on d.stream. launch_status_reset must have run.
-cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
-                         uint32_t K, cudaEvent_t after_records) {
-    cudaStream_t s = d.stream;
-    BuildStatus* st = d.status.as<BuildStatus>();
-    d.bvh = Bvh{};
-    d.bvh.nt = (uint32_t)nt;
-    d.bvh.leaf_size = K;
-    d.bvh.st = st;
-    if (nt == 0) return cudaGetLastError();
+// The call's status block = the mesh's block (or empty bounds for an empty mesh) + this call's flags.
+cudaError_t launch_call_status_init(Device& d, const MeshDev& m, bool clear_errors) {
+    const bool fresh = d.call_status.p == nullptr;
+    CK(d.call_status.ensure(sizeof(BuildStatus)));
+    k_call_status_init<<<1, 32, 0, d.stream>>>(d.call_status.as<BuildStatus>(),
+                                               m.nt ? m.status.as<BuildStatus>() : nullptr, (clear_errors || fresh) ? 1 : 0);
+    d.launches++;
+    return cudaGetLastError();
+}
 
-    const uint32_t nleaf = (uint32_t)((nt + K - 1) / K);
+// Builds records + LBVH for (d_verts, d_tris) into m, on d.stream.
+cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
+                         cudaEvent_t after_records) {
+    cudaStream_t s = d.stream;
+    m.bvh = Bvh{};
+    m.nv = nv;
+    m.nt = nt;
+    m.nodes_il_mag = -1.0f;
+    if (nt == 0) return cudaSuccess;
+    CK(launch_mesh_status_reset(d, m));
+    BuildStatus* st = m.status.as<BuildStatus>();
+
+    const uint32_t nleaf = (uint32_t)nt;
+    const size_t n_nodes = nleaf > 1 ? nleaf - 1 : 1;
     CK(d.rec_orig.ensure(nt * 48));
-    CK(d.rec_sorted.ensure(nt * 48));
+    CK(m.rec_sorted.ensure(nt * 48));
     CK(d.tri_lo.ensure(nt * 16));
     CK(d.tri_hi.ensure(nt * 16));
     CK(d.keys_in.ensure(nt * 8));
     CK(d.keys_out.ensure(nt * 8));
     CK(d.vals_in.ensure(nt * 4));
     CK(d.vals_out.ensure(nt * 4));
-    CK(d.tri_id_sorted.ensure(nt * 4));
-    CK(d.nodes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * NODE_F4 * 16));
-    CK(d.nodes_il.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * NODE_F4 * 16));
-    CK(d.boxes.ensure((size_t)(nleaf > 1 ? nleaf - 1 : 1) * BOX_F4 * 16));
-    CK(d.node_range.ensure((size_t)nleaf * 8));
+    CK(m.tri_id_sorted.ensure(nt * 4));
+    CK(m.nodes.ensure(n_nodes * NODE_F4 * 16));
+    CK(m.nodes_il.ensure(n_nodes * NODE_F4 * 16));
+    CK(m.boxes.ensure(n_nodes * BOX_F4 * 16));
+    CK(m.node_range.ensure((size_t)nleaf * 8));
     CK(d.tobb.ensure(nt * 64));
     CK(d.leaf_parent.ensure((size_t)nleaf * 4));
     CK(d.node_parent.ensure((size_t)nleaf * 4));
@@ -647,57 +729,57 @@ cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uin
     d.launches += 8;  // CUB onesweep: histogram + scan + 6 digit passes
     k_tri_permute<<<blocks_for(nt, bs), bs, 0, s>>>(d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
                                                     d.vals_out.as<uint32_t>(), (uint32_t)nt, st,
-                                                    d.rec_sorted.as<float4>(), d.tobb.as<float4>(),
-                                                    d.tri_id_sorted.as<uint32_t>());
+                                                    m.rec_sorted.as<float4>(), d.tobb.as<float4>(),
+                                                    m.tri_id_sorted.as<uint32_t>());
     d.launches++;
     if (nleaf > 1) {
         CK(cudaMemsetAsync(d.node_flag.p, 0, (size_t)nleaf * 4, s));
-        k_hierarchy<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.keys_out.as<uint64_t>(), K, (int)nleaf,
-                                                             d.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
-                                                             d.node_parent.as<uint32_t>(), d.node_range.as<uint2>());
+        k_hierarchy<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.keys_out.as<uint64_t>(), (int)nleaf,
+                                                             m.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
+                                                             d.node_parent.as<uint32_t>(), m.node_range.as<uint2>());
         k_refit<<<blocks_for(nleaf, bs), bs, 0, s>>>(d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),
-                                                     d.vals_out.as<uint32_t>(), (uint32_t)nt, K, (int)nleaf,
-                                                     d.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
+                                                     d.vals_out.as<uint32_t>(), (int)nleaf,
+                                                     m.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                      d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
         k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
-            d.rec_sorted.as<float4>(), d.tobb.as<float4>(), (uint32_t)nt, K, (int)nleaf, d.boxes.as<float4>(),
-            d.nodes.as<float4>(), d.node_range.as<uint2>(), st, d.obb_bias);
+            m.rec_sorted.as<float4>(), d.tobb.as<float4>(), (uint32_t)nt, (int)nleaf, m.boxes.as<float4>(),
+            m.nodes.as<float4>(), m.node_range.as<uint2>(), st, 1.0f);
         d.launches += 3;
+    } else {
+        k_single_root<<<1, 32, 0, s>>>(d.tobb.as<float4>(), d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),
+                                       m.nodes.as<float4>(), m.boxes.as<float4>(), m.node_range.as<uint2>());
+        d.launches++;
     }
-    d.bvh.rec = d.rec_sorted.as<float4>();
-    d.bvh.tobb = d.tobb.as<float4>();
-    d.bvh.boxes = d.boxes.as<float4>();
-    d.bvh.tri_id = d.tri_id_sorted.as<uint32_t>();
-    d.bvh.nodes = d.nodes.as<float4>();
-    d.bvh.nodes_il = d.nodes_il.as<float4>();
-    d.nodes_il_mag = -1.0f;  // the interleaved copy is written by launch_nodes_interleave once the grid is known
-    d.bvh.nleaf = nleaf;
-    d.bvh.node_range = d.node_range.as<uint2>();
-    if (d.want_stats) {
-        CK(d.stats.ensure(64 + 32 * 8));
-        CK(cudaMemsetAsync(d.stats.p, 0, 64 + 32 * 8, s));
-        if (d.stats_mode == 2) CK(cudaMemsetAsync((char*)d.stats.p + 24, 2, 1, s));
-        d.bvh.stats = d.stats.as<unsigned long long>();
-    }
-    d.bvh.root = nleaf > 1 ? 0u : (LEAF_BIT | LEAF_DEGEN_BIT);  // single leaf: always take the guarded path
+    m.bvh.rec = m.rec_sorted.as<float4>();
+    m.bvh.boxes = m.boxes.as<float4>();
+    m.bvh.tri_id = m.tri_id_sorted.as<uint32_t>();
+    m.bvh.nodes = m.nodes.as<float4>();
+    m.bvh.nodes_il = m.nodes_il.as<float4>();
+    m.bvh.nt = (uint32_t)nt;
+    m.bvh.n_nodes = (uint32_t)n_nodes;
+    m.bvh.node_range = m.node_range.as<uint2>();
+    m.bvh.stats = nullptr;
     return cudaGetLastError();
 }
 
-// Writes Bvh::nodes_il for a grid of magnitude grid_mag (see k_nodes_interleave); a no-op if it is current.
-cudaError_t launch_nodes_interleave(Device& d, float grid_mag) {
-    if (d.bvh.nleaf < 2 || d.nodes_il_mag == grid_mag) return cudaSuccess;
-    k_nodes_interleave<<<blocks_for(d.bvh.nleaf - 1, 256), 256, 0, d.stream>>>(
-        d.nodes.as<float4>(), d.bvh.nleaf - 1, d.nodes_il.as<float4>(), d.status.as<BuildStatus>(), grid_mag);
+// Writes Bvh::nodes_il in units of S = 2^k >= 4 x max(scene magnitude of the CALL's status block, mag_key).
+// Grids pass their host-known magnitude as the key (a no-op when it is current); point calls force it, because
+// the call's bounds include the queries, which only the device knows.
+cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool force) {
+    if (m.bvh.n_nodes == 0 || (!force && m.nodes_il_mag == mag_key)) return cudaSuccess;
+    k_nodes_interleave<<<blocks_for(m.bvh.n_nodes, 256), 256, 0, d.stream>>>(
+        m.nodes.as<float4>(), m.bvh.n_nodes, m.nodes_il.as<float4>(), d.call_status.as<BuildStatus>(), mag_key);
     d.launches++;
-    d.nodes_il_mag = grid_mag;
+    m.nodes_il_mag = force ? -1.0f : mag_key;
     return cudaGetLastError();
 }
 
-// Sorts the queries along a Morton curve (coherent packets). Produces q_sorted (xyz + original index).
+// Sorts the queries along a Morton curve (coherent packets). Produces q_sorted (xyz + original index) and adds the
+// query bounds to the call's status block.
 cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq) {
     cudaStream_t s = d.stream;
     const unsigned bs = 256;
-    BuildStatus* st = d.status.as<BuildStatus>();
+    BuildStatus* st = d.call_status.as<BuildStatus>();
     CK(d.q_sorted.ensure(nq * 16));
     CK(d.q_keys_in.ensure(nq * 8));
     CK(d.q_keys_out.ensure(nq * 8));

@@ -3,30 +3,35 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/m2s.h"
 
 namespace m2s {
 
 // ---------------------------------------------------------------------------------------------------
-// Device-side layouts (all in HBM; the whole mesh + LBVH of config C3 is ~14 MB and stays L2-resident)
+// Device-side layouts (all in HBM; the whole mesh + LBVH of config C3 is ~26 MB and stays L2-resident)
 //
-//   triangle record, 48 B = 3 x float4 (one per triangle, two copies: original order for the
-//   brute-force / row kernels, leaf (Morton) order for the LBVH kernels):
+//   triangle record, 48 B = 3 x float4, leaf (Morton) order:
 //       r0 = (a.x, a.y, a.z, b.x)   r1 = (b.y, b.z, c.x, c.y)   r2 = (c.z, n.x, n.y, n.z)
 //       n = cross(b - a, c - a), un-normalised, un-fused (geo.rs:60-64)
 //   triangle oriented box, 64 B = 4 x float4 (leaf order): (centre.xyz, 0) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew)
-//   with u = unit normal, v along the longest edge: the cheap pretest in front of the exact arithmetic
-//   box node, 64 B = 4 x float4 (`boxes`): per child (min.xyz, bits(child ref)) (max.xyz, 0), padded
+//   with u = unit normal, v along the longest edge: becomes the child slot of the triangle's parent node
+//   box node, 64 B = 4 x float4 (`boxes`): per child (min.xyz, bits(child ref)) (max.xyz, escape), padded
 //   -/+1e-4 like geo.rs:18-21. Written by the refit; read by the ray walks.
 //   search node, 128 B = 8 x float4 (`nodes`): per child 4 x float4 = an oriented box
 //   (centre.xyz, ref) (u.xyz, eu) (v.xyz, ev) (w.xyz, ew), either fitted to the child's triangles or,
 //   where that is not smaller, the padded axis-aligned box written with the identity frame; m2s_build.cu.
-//   child ref: >= 0 internal node index; < 0 leaf: bit31 set, bit30 = "leaf holds a degenerate
-//   triangle" (slow path with the geo.rs:73-88 guards), bits 0..29 = leaf index. Leaf l owns the
-//   sorted triangles [l*K, min((l+1)*K, nt)).
+//   child ref: >= 0 internal node index; < 0 leaf: bit31 set, bit30 = "the triangle is degenerate"
+//   (slow path with the geo.rs:73-88 guards), bits 0..29 = leaf = sorted triangle index (one triangle per leaf).
+//   A mesh of ONE triangle gets a root node whose second child is an unreachable copy of the first, so every
+//   tree has at least one internal node and there is a single code path.
 // ---------------------------------------------------------------------------------------------------
 constexpr int NODE_F4 = 8;   // float4 per node
 constexpr int CHILD_F4 = 4;  // float4 per child slot
@@ -36,14 +41,14 @@ constexpr uint32_t LEAF_DEGEN_BIT = 0x40000000u;
 constexpr uint32_t LEAF_INDEX_MASK = 0x3fffffffu;
 constexpr uint32_t TRI_DEGEN_BIT = 0x80000000u;  // in tri_id_sorted
 
-// Written by the build kernels, read back once per call (64 B).
+// Status block, 64 B. One per mesh (written by the build: error flags of the mesh + its bounds) and one per
+// call (k_call_status_init copies the mesh's block, the query kernels add the query bounds and their own flags).
 struct BuildStatus {
     int bad_index;      // some triangle index >= nv
     int nonfinite;      // some referenced vertex / query / grid parameter is NaN or +-inf
     int n_degenerate;   // triangles with two equal vertices
-    int stack_overflow; // traversal stack overflow (cannot happen for depth <= 128; checked anyway)
-                        // the four error flags above/below are sticky until launch_status_reset(clear)
-    int nan_distance;   // brute-force Normal fold hit the reference's "NaN distance" panic
+    int stack_overflow; // packet stack overflow (cannot happen for depth <= 128; checked anyway)
+    int nan_distance;   // Normal fold hit the reference's "NaN distance" panic (lib.rs:257)
     int lo[3];          // scene bounds (padded boxes), order-preserving int encoding of float
     int hi[3];
     int pad[5];
@@ -52,18 +57,13 @@ static_assert(sizeof(BuildStatus) == 64, "BuildStatus must be 64 bytes");
 
 struct Bvh {
     const float4* rec;        // leaf-order triangle records
-    const float4* tobb;       // leaf-order triangle oriented boxes (pretest)
     const float4* boxes;      // box nodes (ray walks)
     const uint32_t* tri_id;   // leaf-order -> original triangle id (| TRI_DEGEN_BIT)
-    const float4* nodes;      // internal nodes
-    const float4* nodes_il;   // the same nodes, children interleaved for packed-fp32 tests (m2s_build.cu, K4e)
-    uint32_t nt;              // triangles
-    uint32_t nleaf;           // leaves
-    uint32_t leaf_size;       // K
-    uint32_t root;            // root ref (a leaf ref when nleaf == 1)
-    const BuildStatus* st;    // device pointer: scene bounds (-> pruning slack) and error flags
-    unsigned long long* stats; // optional traversal counters (M2S_STATS=1): nodes, leaves, searches; with
-                               // -DM2S_STATS_BUILD also [8 + k]: visits of nodes spanning [2^k, 2^(k+1)) leaves
+    const float4* nodes;      // search nodes
+    const float4* nodes_il;   // the same nodes, children interleaved for packed-fp32 tests (k_nodes_interleave)
+    uint32_t nt;              // triangles = leaves
+    uint32_t n_nodes;         // internal nodes (>= 1 when nt >= 1)
+    unsigned long long* stats; // optional traversal counters (-DM2S_STATS_BUILD + M2S_STATS=1): nodes, leaves, tiles
     const uint2* node_range;   // per internal node: first / last leaf (diagnostics only)
 };
 
@@ -71,13 +71,20 @@ struct GridParams {
     float fx, fy, fz;     // Grid::first_cell
     float sx, sy, sz;     // Grid::cell_size
     uint32_t nx, ny, nz;  // Grid::cell_count
-    uint32_t x0, x1;      // slab [x0, x1): origin of the output / seed indexing
-    uint32_t xa, xb;      // planes [xa, xb) of the slab computed by this launch (chunked host copies)
+    uint32_t x0, x1;      // slab [x0, x1) computed by this launch; the output starts at plane x0
+};
+
+// Completion signalling of the distance kernel for host destinations that are copied while it runs: every warp
+// bumps count[brick plane] after its stores; the last one publishes flag[brick plane] = epoch in mapped host memory.
+struct Progress {
+    uint32_t* count;            // device, one per brick plane (4 x-planes), zeroed before the launch
+    volatile uint32_t* flag;    // mapped pinned host memory (device alias), one per brick plane
+    uint32_t epoch;
 };
 
 #ifdef __CUDACC__
-// Scale of the interleaved nodes (k_nodes_interleave / k_grid_nearest_run): 1 / S with S the power of two
-// >= 4 x mag, mag = largest |coordinate| of mesh and grid. Both kernels derive it from the same device-side
+// Scale of the interleaved nodes (k_nodes_interleave / the run kernels): 1 / S with S the power of two
+// >= 4 x mag, mag = largest |coordinate| of mesh and grid / queries. Both sides derive it from the same device-side
 // inputs, so the host never has to know the mesh bounds.
 __device__ __forceinline__ float pair_inv_scale(float mag) {
     if (!(mag > 0.0f) || !isfinite(mag)) return 1.0f;
@@ -112,6 +119,24 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Growable page-locked + mapped + portable host buffer (staging ring of the pageable-destination path).
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes);
+    void release();
+};
+
+// A mesh + its LBVH on one device: everything the query kernels read. Owned either by a Device (the scratch mesh
+// of the one-shot entry points, rebuilt per call) or by an m2s_mesh handle (built once, queried many times).
+struct MeshDev {
+    DevBuf rec_sorted, tri_id_sorted, nodes, nodes_il, boxes, status, node_range;
+    Bvh bvh{};
+    uint64_t nv = 0, nt = 0;
+    float nodes_il_mag = -1.0f;  // magnitude key the interleaved nodes were last written for (< 0: stale)
+    void release();
+};
+
 // Everything a context owns on one device.
 struct Device {
     int ordinal = 0;
@@ -119,74 +144,74 @@ struct Device {
     bool own_stream = false;
     int sm_count = 148;
     uint64_t launches = 0;
+    bool peer_to_first = false;   // this device can store into / load from the context's first device
 
-    // mesh + LBVH
-    DevBuf verts, tris;  // staging for the host entry points
-    DevBuf rec_orig, rec_sorted, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
-    DevBuf tri_id_sorted, nodes, nodes_il, leaf_parent, node_parent, node_flag, node_range, tobb, boxes, status;
+    DevBuf verts, tris;           // staging for the host entry points
+    // build scratch (dead after launch_build)
+    DevBuf rec_orig, tobb, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
+    DevBuf leaf_parent, node_parent, node_flag;
+    MeshDev scratch;              // the mesh of the one-shot entry points
+    DevBuf call_status;           // per-call BuildStatus (mesh block + query bounds + this call's flags)
     DevBuf rows[3], big_list, big_count;
-    DevBuf stats;             // traversal counters, only with M2S_STATS=1
+    DevBuf stats;                 // traversal counters (stats builds only)
     bool want_stats = false;
-    int stats_mode = 0;
-    float obb_bias = 1.0f;     // oriented box kept when its volume <= obb_bias * padded box volume (M2S_OBB_BIAS)
-    bool seed_packet = false;  // M2S_SEED_PACKET=0: per-lane traversal for the seed pass
-    bool packet = true;        // M2S_PACKET=0 selects the per-lane traversal grid kernel
-    int pair = 1;              // M2S_PAIR: 0 = one voxel per lane (k_grid_nearest_pkt); 1 = k_grid_nearest_run, V = 2 voxels
-                               // per lane; 4..7 = its (V, LAYOUT) variants for A/B runs
-    DevBuf tile_slot;         // per-tile nearest-triangle slots published by the distance kernel
-    bool neighbour_and_coarse = false;  // experiment (M2S_NSEED=2): coarse pass as the fallback of neighbour seeds
-    bool neighbour_seeds = true;  // M2S_NSEED=0: separate coarse seed pass for every grid
-    DevBuf seeds[2];          // nearest-triangle slots of the coarse seeding levels
-    uint32_t seed_stride = 4;  // voxels per seed block edge (M2S_SEED_STRIDE)
-    int seed_levels = 1;      // 0 disables the coarse-to-fine seeding (M2S_SEED_LEVELS)
+    DevBuf tile_slot;             // per-tile nearest-triangle slots published by the distance kernel
+    DevBuf progress;              // per brick plane completion counters (pipelined host copies)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
     DevBuf post_keys, post_idx, post_mm, post_in, post_pts, post_out;  // post-passes (m2s_post.cu) and their host staging
+    PinBuf stage;                 // pinned staging ring: pageable destinations are filled from here by host threads
+    PinBuf flags;                 // mapped completion flags of the pipelined path
+    uint32_t epoch = 0;
     BuildStatus* h_status = nullptr;  // pinned
-    cudaEvent_t ev[8] = {};
-    cudaStream_t aux_stream = nullptr;   // high priority: the second half's seed pass hides under the first half's kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_half[2] = {};
-    cudaEvent_t ev_records = nullptr, ev_rows = nullptr;  // the row parities run on aux_stream beside the tree build
-    bool split_halves = true;            // M2S_SPLIT=0: one seed pass + one distance launch per slab
-    bool last_split = false;
-    bool zero_copy = true;               // M2S_ZEROCOPY=0: stage + copy even when the host destination is pinned
-    cudaStream_t copy_stream = nullptr;  // D2H of finished x-chunks overlaps the next chunk's kernel
-    cudaEvent_t ev_chunk[8] = {};
-    cudaEvent_t ev_copied = nullptr;
+    cudaEvent_t ev[8] = {};       // 0 start, 1 inputs on device, 2 build done, 3 sign done, 4 kernel done, 5 end, 6 pre-kernel
+    cudaStream_t aux_stream = nullptr;   // high priority: row parities beside the tree build
+    cudaEvent_t ev_records = nullptr, ev_rows = nullptr;
+    cudaEvent_t ev_inputs = nullptr, ev_done = nullptr, ev_built = nullptr;  // cross-device ordering (multi-device contexts)
+    m2s_timings timings{};
+};
 
-    Bvh bvh{};
-    float nodes_il_mag = -1.0f;  // grid magnitude the interleaved nodes were last written for (< 0: stale)
+// Host worker threads that copy finished plane groups from the pinned ring into pageable destinations.
+class CopyPool {
+public:
+    explicit CopyPool(int n);
+    ~CopyPool();
+    void start(const std::function<void(int)>* job, int n_jobs);  // workers run (*job)(i) for i in [0, n_jobs)
+    void wait();                                                   // until every job has returned
+    int threads() const { return (int)workers_.size(); }
+private:
+    void loop();
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* job_ = nullptr;
+    std::atomic<int> next_{0};
+    int total_ = 0, active_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
 };
 
 // ---- launchers (each returns the CUDA error of its enqueue) ------------------------------------------
-cudaError_t launch_status_reset(Device& d, bool clear_errors);
-// after_records (optional) is recorded once the original-order triangle records exist (what the row kernels need)
-cudaError_t launch_build(Device& d, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
-                         uint32_t leaf_size, cudaEvent_t after_records = nullptr);
-cudaError_t launch_nodes_interleave(Device& d, float grid_mag);
+cudaError_t launch_mesh_status_reset(Device& d, MeshDev& m);
+cudaError_t launch_call_status_init(Device& d, const MeshDev& m, bool clear_errors);
+// after_records (optional) is recorded once the leaf-order triangle records exist (what the row kernels need)
+cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
+                         cudaEvent_t after_records = nullptr);
+cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool force);
 cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
 
-// stream / rec default to the device's stream and the leaf-order records
-cudaError_t launch_grid_rows(Device& d, const GridParams& g, RowBits* rb, cudaStream_t stream = nullptr,
-                             const float4* rec = nullptr);
-
-struct SeedLevel {
-    const uint32_t* parent;  // nearest-triangle slots of the parent level (nullptr: start unbounded)
-    uint32_t px, py, pz;     // parent level dims
-    uint32_t pstride;        // parent level stride in voxels
-};
-bool grid_uses_neighbour_seeds(const Device& d, int mode);
-cudaError_t launch_grid_seeds(Device& d, const GridParams& g, SeedLevel* L, int slot = 0, cudaStream_t stream = nullptr);
-cudaError_t launch_grid_final(Device& d, const GridParams& g, const SeedLevel& L, int mode, const RowBits* rb,
-                              float* d_out);
-cudaError_t launch_grid_nearest(Device& d, const GridParams& g, int mode, const RowBits* rb, float* d_out,
-                                cudaEvent_t after_seeds = nullptr);
+// rec: triangle records in any order (every triangle toggles its own rows)
+cudaError_t launch_grid_rows(Device& d, const float4* rec, uint32_t nt, const GridParams& g, RowBits* rb, cudaStream_t stream);
+cudaError_t launch_grid_nearest(Device& d, MeshDev& m, const GridParams& g, int mode, const RowBits* rb, float* d_out,
+                                const Progress* progress);
+uint32_t grid_brick_planes(const GridParams& g);  // number of completion flags a launch over g publishes
+float grid_magnitude(const GridParams& g);       // largest |coordinate| of the grid's box: key of the node interleave
+constexpr uint32_t GRID_BRICK_X = 4;               // x-planes per brick plane
 
 // queries must have been Morton-sorted into d.q_sorted by sort_queries().
 // sign_rule: 0 = value already signed / unsigned, 1 = +X ray parity, 3 = best of the three axes
-cudaError_t launch_points(Device& d, uint64_t nq, int mode, int sign_rule, float* d_out,
-                          cudaEvent_t after_seeds = nullptr);
+cudaError_t launch_points(Device& d, MeshDev& m, uint64_t nq, int mode, int sign_rule, float* d_out);
 
-cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value);
+cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value, const Progress* progress, uint32_t planes);
 
 // post-passes on a device-resident grid (m2s_post.cu)
 cudaError_t launch_grid_order(Device& d, const float* d_sdf, uint64_t n, uint32_t* d_order, float* d_minmax);
@@ -195,11 +220,19 @@ cudaError_t launch_grid_sample(Device& d, const float* d_sdf, const GridParams& 
 
 }  // namespace m2s
 
+struct m2s_mesh {
+    m2s_ctx* owner = nullptr;
+    m2s::MeshDev* dev = nullptr;  // one per device of the owning context
+    uint64_t nv = 0, nt = 0;
+};
+
 struct m2s_ctx {
     int n_devices = 0;
     m2s::Device* dev = nullptr;
     std::string last_error;
-    m2s_timings timings{};
-    uint32_t leaf_size = 1;
+    int build_mode = M2S_BUILD_REPLICATED;
+    int host_path = M2S_HOST_AUTO;
+    int copy_threads = 4;
+    m2s::CopyPool* pool = nullptr;
     std::mutex mu;  // a context serves one call at a time
 };

@@ -104,7 +104,47 @@ static void test_post_passes() {
     }
 }
 
+// How results reach the host: a pageable Vec of >= 4 MiB is filled through the pinned ring while the kernel runs,
+// a PinnedVec is written in place, a Mesh handle pays neither upload nor build. All three give the same bits.
+static void test_host_paths_and_handles() {
+    std::vector<V3> vertices;
+    std::vector<uint32_t> indices;
+    const int nu = 48, nv = 32;  // a torus, outward wound
+    for (int i = 0; i < nu; ++i)
+        for (int j = 0; j < nv; ++j) {
+            const float u = 6.2831853f * i / nu, v = 6.2831853f * j / nv;
+            vertices.push_back({(1.f + 0.35f * std::cos(v)) * std::cos(u), (1.f + 0.35f * std::cos(v)) * std::sin(u), 0.35f * std::sin(v)});
+        }
+    for (int i = 0; i < nu; ++i)
+        for (int j = 0; j < nv; ++j) {
+            const uint32_t a = i * nv + j, b = ((i + 1) % nu) * nv + j, c = ((i + 1) % nu) * nv + (j + 1) % nv, d = i * nv + (j + 1) % nv;
+            for (uint32_t k : {a, b, c, a, c, d}) indices.push_back(k);
+        }
+    auto grid = Grid<V3>::from_bounding_box({-1.7f, -1.6f, -0.6f}, {1.75f, 1.65f, 0.66f}, {112, 104, 96});  // 4.3 MiB
+    const auto topo = Topology<uint32_t>::triangle_list(indices);
+    const auto sdf = generate_grid_sdf(vertices, topo, grid, SignMethod::Raycast);
+    CHECK(last_timings().host_path == M2S_PATH_PIPELINED);  // the drop-in Vec<f32> path
+    PinnedVec pinned;
+    generate_grid_sdf_into(vertices, topo, grid, SignMethod::Raycast, pinned);
+    CHECK(last_timings().host_path == M2S_PATH_ZEROCOPY && pinned.size() == sdf.size());
+    CHECK(std::memcmp(pinned.data(), sdf.data(), sdf.size() * sizeof(float)) == 0);
+    Mesh<V3> mesh(vertices, topo);
+    const auto again = mesh.generate_grid_sdf(grid, SignMethod::Raycast);
+    const m2s_timings t = last_timings();
+    CHECK(t.build_ms < 0.01f && t.h2d_ms < 0.01f && t.host_path == M2S_PATH_PIPELINED);
+    CHECK(std::memcmp(again.data(), sdf.data(), sdf.size() * sizeof(float)) == 0);
+    size_t inside = 0;
+    for (float d : sdf) inside += d < 0.f;
+    CHECK(inside > sdf.size() / 20 && inside < sdf.size() / 3);
+    std::vector<V3> q = {{1.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {3.f, 0.f, 0.f}};
+    const auto d = mesh.generate_sdf(q);
+    const auto e = generate_sdf(vertices, topo, q);
+    CHECK(d.size() == 3 && d[0] < 0.f && d[1] > 0.f && d[2] > 0.f);
+    for (size_t i = 0; i < 3; ++i) CHECK(d[i] == e[i]);
+}
+
 int main() {
+    test_host_paths_and_handles();
     test_post_passes();
     doc_generate_sdf();
     doc_generate_grid_sdf();

@@ -21,7 +21,10 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for must in ["m2s_create", "m2s_destroy", "m2s_generate_grid_sdf", "m2s_generate_sdf",
                  "m2s_generate_grid_sdf_device", "m2s_generate_sdf_device", "m2s_synchronize", "m2s_last_error",
-                 "m2s_last_timings", "m2s_launch_count", "m2s_expand_topology", "m2s_grid_from_bounding_box"]:
+                 "m2s_last_timings", "m2s_launch_count", "m2s_expand_topology", "m2s_grid_from_bounding_box",
+                 "m2s_mesh_create", "m2s_mesh_destroy", "m2s_mesh_grid_sdf", "m2s_mesh_grid_sdf_device", "m2s_mesh_sdf",
+                 "m2s_host_alloc", "m2s_host_register", "m2s_device_alloc", "m2s_ipc_export", "m2s_ipc_open",
+                 "m2s_set_option", "m2s_last_error_copy", "m2s_last_timings_device"]:
         assert must in syms
 
 
@@ -29,7 +32,7 @@ def test_library_exports_every_declared_symbol(m2s):
     L = m2s.lib()
     for name in declared_symbols():
         assert hasattr(L, name), f"libm2s.so does not export {name}"
-    assert L.m2s_abi_version() == 1
+    assert L.m2s_abi_version() == 2
 
 
 def test_library_exports_only_the_abi(m2s):

@@ -129,17 +129,49 @@ def test_multi_device_context_matches_single(m2s):
     grid = m2s.Grid.from_bounding_box(mn, mx, [37, 20, 24])
     q = synth.splitmix64_points(10001, mn, mx)
     one = m2s.default_context().grid_sdf(verts, tris, grid, RAYCAST)
+    one_n = m2s.default_context().grid_sdf(verts, tris, grid, NORMAL)
     qa = m2s.default_context().sdf(verts, tris, q, 3, 0)
-    with m2s.Context([0, 1]) as c2:
-        assert c2.device_count == 2
-        two = c2.grid_sdf(verts, tris, grid, RAYCAST)
-        qb = c2.sdf(verts, tris, q, 3, 0)
-        # a pinned destination: every device writes its own slab in place (zero-copy stores)
-        pinned = torch.empty(37 * 20 * 24, dtype=torch.float32).pin_memory()
-        c2.grid_sdf(verts, tris, grid, RAYCAST, pinned.numpy())
-    assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
-    assert np.array_equal(qa.view(np.uint32), qb.view(np.uint32))
-    assert np.array_equal(one.view(np.uint32), pinned.numpy().view(np.uint32))
+    n = 37 * 20 * 24
+    for build_mode in (m2s.BUILD_REPLICATED, m2s.BUILD_BROADCAST):
+        with m2s.Context([0, 1]) as c2:
+            assert c2.device_count == 2
+            c2.set_option(m2s.OPT_BUILD_MODE, build_mode)
+            # pageable destination: staged (small grid), then forced through the pinned ring
+            two = c2.grid_sdf(verts, tris, grid, RAYCAST)
+            assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
+            c2.set_option(m2s.OPT_HOST_PATH, m2s.HOST_PIPELINED)
+            two = c2.grid_sdf(verts, tris, grid, RAYCAST)
+            assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
+            assert c2.timings(0)["host_path"] == "pipelined" and c2.timings(1)["host_path"] == "pipelined"
+            c2.set_option(m2s.OPT_HOST_PATH, m2s.HOST_AUTO)
+            assert np.array_equal(one_n.view(np.uint32), c2.grid_sdf(verts, tris, grid, NORMAL).view(np.uint32))
+            qb = c2.sdf(verts, tris, q, 3, 0)
+            assert np.array_equal(qa.view(np.uint32), qb.view(np.uint32))
+            # a pinned destination: every device writes its own slab in place (zero-copy stores)
+            pinned = m2s.host_alloc(n)
+            c2.grid_sdf(verts, tris, grid, RAYCAST, pinned.array)
+            assert np.array_equal(one.view(np.uint32), pinned.array.view(np.uint32))
+            assert c2.timings(1)["host_path"] == "zerocopy"
+            pinned.close()
+            # device-resident: inputs and the assembled grid live on the first device; the second device pulls the
+            # mesh over NVLink and stores its slab straight into the first device's buffer (peer-mapped pointer)
+            with torch.cuda.device(0):
+                dv = torch.from_numpy(verts).cuda()
+                dt = torch.from_numpy(tris.view(np.int32)).cuda()
+                dq = torch.from_numpy(q).cuda()
+                out = torch.zeros(n, dtype=torch.float32, device="cuda:0")
+                qout = torch.zeros(len(q), dtype=torch.float32, device="cuda:0")
+                torch.cuda.synchronize()
+                c2.grid_sdf_device(dv.data_ptr(), len(verts), dt.data_ptr(), len(tris), grid, RAYCAST, 0, 37, out.data_ptr())
+                c2.sdf_device(dv.data_ptr(), len(verts), dt.data_ptr(), len(tris), dq.data_ptr(), len(q), 3, 0, qout.data_ptr())
+                c2.synchronize()
+                assert np.array_equal(out.cpu().numpy().view(np.uint32), one.view(np.uint32))
+                assert np.array_equal(qout.cpu().numpy().view(np.uint32), qa.view(np.uint32))
+                assert torch.cuda.current_device() == 0  # the library restores the caller's device
+            # a mesh handle on both devices
+            with c2.mesh(verts, tris) as mesh:
+                assert np.array_equal(mesh.grid_sdf(grid, RAYCAST).view(np.uint32), one.view(np.uint32))
+                assert np.array_equal(mesh.sdf(q, 3).view(np.uint32), qa.view(np.uint32))
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
@@ -174,7 +206,7 @@ def test_random_triangle_soup(m2s, oracle, seed):
     assert np.array_equal(np.abs(g).view(np.uint32), np.abs(w).view(np.uint32))
 
 
-def test_pinned_destination_is_written_in_place(m2s, monkeypatch):
+def test_pinned_destination_is_written_in_place(m2s):
     # a page-locked, mapped destination is written by the kernel itself (zero-copy stores, no staging + D2H);
     # same bits as the staged path, for a grid, a slab, and the empty-mesh fill
     torch = pytest.importorskip("torch")
@@ -184,16 +216,19 @@ def test_pinned_destination_is_written_in_place(m2s, monkeypatch):
     n = 40 * 33 * 27
     pinned = torch.empty(n, dtype=torch.float32).pin_memory()
     with m2s.Context() as c:
-        want = c.grid_sdf(verts, tris, grid, 0)                      # pageable numpy destination: staged
+        want = c.grid_sdf(verts, tris, grid, 0)                      # pageable numpy destination: staged (small)
+        assert c.timings()["host_path"] == "staged"
         got = c.grid_sdf(verts, tris, grid, 0, pinned.numpy())       # pinned destination: in place
         assert got.ctypes.data == pinned.data_ptr()
+        assert c.timings()["host_path"] == "zerocopy"
         assert np.array_equal(pinned.numpy().view(np.uint32), want.view(np.uint32))
         assert c.timings()["d2h_ms"] < 0.5  # no staged copy: only the 64-byte status read sits between the two events
         pinned.zero_()
         c.grid_sdf(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), grid, 0, pinned.numpy())
         assert np.all(pinned.numpy() == np.finfo(np.float32).max)
-    monkeypatch.setenv("M2S_ZEROCOPY", "0")
-    with m2s.Context() as c:
+        # a destination that only STARTS inside a pinned allocation must not take the in-place path
+        c.set_option(m2s.OPT_HOST_PATH, m2s.HOST_STAGED)
         pinned.zero_()
         c.grid_sdf(verts, tris, grid, 0, pinned.numpy())
+        assert c.timings()["host_path"] == "staged"
         assert np.array_equal(pinned.numpy().view(np.uint32), want.view(np.uint32))

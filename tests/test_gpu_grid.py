@@ -137,12 +137,11 @@ def test_device_entry_defers_data_errors(m2s):
         assert t["total_ms"] > 0 and c.launch_count > 0
 
 
-@pytest.mark.parametrize("pair", ["0", "1", "4", "5", "6", "7"])
-@pytest.mark.parametrize("dims", [(37, 21, 30), (9, 50, 5), (64, 64, 64)])
-def test_every_grid_kernel_variant_bit_exact(m2s, oracle, monkeypatch, pair, dims):
-    # M2S_PAIR picks the distance kernel (one voxel per lane / runs of 2 or 4 voxels, two lane layouts); every
-    # variant must give the exact oracle's bits, on ragged grids (runs cut by the grid's end) and slab by slab
-    monkeypatch.setenv("M2S_PAIR", pair)
+@pytest.mark.parametrize("dims", [(37, 21, 30), (9, 50, 5), (64, 64, 64), (5, 9, 131)])
+def test_ragged_grids_and_slabs_bit_exact(m2s, oracle, dims):
+    # the distance kernel works on 2 x 4 x 8 voxel tiles (runs of 2 voxels per lane): grids whose sides are not
+    # multiples of the tile (runs cut by the grid's end, partial bricks) and slabs that start inside a brick must
+    # give the exact oracle's bits
     verts, tris = synth.bumpy_torus(40, 24)
     grid = _grid_for(m2s, verts, list(dims))
     want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, RAYCAST)
@@ -181,15 +180,9 @@ def test_normal_sign_near_ties_positive_wins(m2s, oracle):
                      [16, 17, 18], [16, 18, 19], [17, 20, 21], [17, 21, 18]], np.uint32)
     grid = m2s.Grid([-0.25, -0.25, -0.5], [0.125, 0.125, 0.03125], [56, 14, 64])
     want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, NORMAL)
-    for pair in ("0", "1"):
-        import os
-        os.environ["M2S_PAIR"] = pair
-        try:
-            with m2s.Context() as c:
-                got = c.grid_sdf(verts, tris, grid, NORMAL)
-        finally:
-            os.environ.pop("M2S_PAIR", None)
-        assert np.max(np.abs(np.abs(got) - np.abs(want))) <= 4e-6
-        assert np.array_equal(np.signbit(got), np.signbit(want)), pair
-        mid = got.reshape(56, 14, 64)[:, :, 17]  # z = 1/32: between A and B (exact tie) and between C and D (near-tie)
-        assert np.all(mid[3:9, 3:9] == np.float32(0.03125)) and np.all(mid[19:25, 3:9] > 0)
+    with m2s.Context() as c:
+        got = c.grid_sdf(verts, tris, grid, NORMAL)
+    assert np.max(np.abs(np.abs(got) - np.abs(want))) <= 4e-6
+    assert np.array_equal(np.signbit(got), np.signbit(want))
+    mid = got.reshape(56, 14, 64)[:, :, 17]  # z = 1/32: between A and B (exact tie) and between C and D (near-tie)
+    assert np.all(mid[3:9, 3:9] == np.float32(0.03125)) and np.all(mid[19:25, 3:9] > 0)

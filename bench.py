@@ -1,21 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the hot path: Mvoxels/s of generate_grid_sdf on BASELINE config C3
-(~100k-triangle watertight synthetic mesh, 256^3 grid, SignMethod::Raycast), one process per GPU.
+"""bench.py — benchmark of the hot path of mesh_to_sdf on B200: generate_grid_sdf / generate_sdf on the BASELINE
+configs, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C2|C5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C4|C5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A step = one full pass of the hot path over one slab: triangle records + Morton sort + LBVH + oriented boxes, the
-Raycast row parities, the seeding passes and the nearest-triangle kernel with the sign epilogue.
-  value : inputs already resident in HBM (m2s_generate_grid_sdf_device), timed with CUDA events on the stream
-          the kernels are launched on; L2 is flushed between steps (256 MiB write, outside the event pairs).
-  e2e   : the same step through the host-buffer C ABI call a facade user makes (m2s_generate_grid_sdf_slab):
-          pinned host buffers, H2D of vertices+indices and D2H of the slab inside the timed region.
-  N > 1 : weak scaling — every rank computes a 256-plane x-slab of a (256*N) x 256 x 256 grid over the same
-          box (slabs along x, the slowest axis of Grid::get_cell_idx); no data-path collective.
-  --impl reference : the reference's CPU algorithm (restated C++, oracle/, all host threads) on a bounded
-          sample of the same workload; rank 0 only.
+N = 1 (default): workload C3 (the configuration BASELINE.json's metric is quoted on: ~100k triangles, 256^3 grid,
+  Raycast); the other single-GPU configurations (C2, C4, C5 on one GPU) ride along in `extra_configs`.
+N > 1: workload C5 (1M triangles, 512^3 grid, Raycast), STRONG scaling: the x-slabs of ONE grid are computed by the
+  N ranks and assembled into ONE flat result — device-resident on rank 0 (every rank's distance kernel stores its
+  slab straight into rank 0's buffer over NVLink: cudaIpc mapping, no gather step) for `value`, one host buffer
+  shared by the ranks for `e2e`. The timed region ends when the whole grid is there.
+
+A step = one full pass of the hot path: triangle records + Morton sort + LBVH + oriented boxes (rebuilt every step,
+like the reference rebuilds its structures every call), the Raycast row parities, the nearest-triangle kernel with
+the sign epilogue.
+  value : inputs already resident in HBM (m2s_generate_grid_sdf_device / m2s_generate_sdf_device), timed with CUDA
+          events on the stream the kernels are launched on; L2 flushed between steps (256 MiB write).
+  e2e   : the same step through the call a facade user makes, with the buffers the facade has: PAGEABLE host
+          vertices / indices / queries and a pageable destination (include/mesh_to_sdf.hpp allocates a std::vector,
+          the Rust facade a Vec) — H2D and D2H inside the timed region. `e2e.pinned` is the same call with a
+          page-locked destination (m2s_host_alloc: the kernel's own stores write it in place).
+  --impl reference : the reference's CPU algorithm (restated C++, oracle/, all host threads) on a bounded sample
+          of the same workload; rank 0 only; never loads libm2s.so.
 torch is plumbing here: device buffers, the stream, torch.distributed. The compute is libm2s.so.
 """
 from __future__ import annotations
@@ -33,25 +41,82 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (Nu, Nv, n, sign)  — BASELINE.md §4
-    "C2": (64, 40, 128, 1),
-    "C3": (256, 196, 256, 0),
-    "C5": (1024, 490, 512, 0),
-}
+# name: (Nu, Nv, grid n, sign) / (Nu, Nv, queries) — BASELINE.md §4, SURVEY §8d
+GRID_WORKLOADS = {"C2": (64, 40, 128, 1), "C3": (256, 196, 256, 0), "C5": (1024, 490, 512, 0)}
+POINT_WORKLOADS = {"C4": (640, 392, 1_000_000)}
 METRIC = "Mvoxels/s at 256^3 grid, 1/2/4/8 GPU vs ref CPU; HBM GB/s % peak"
+RAYCAST, NORMAL, ACCEL_RTREE_BVH = 0, 1, 3
 
 
-def make_workload(name: str, world: int, scaling: str):
-    from mesh_to_sdf_b200 import synth
-    import mesh_to_sdf_b200 as m2s
+# ---------------------------------------------------------------------------------------------------------------
+# workloads (numpy only: the reference arm must not load libm2s)
+# ---------------------------------------------------------------------------------------------------------------
+class PlainGrid:
+    """Grid::from_bounding_box (src/grid.rs:59-74) in numpy float32 — same arithmetic as the library helper."""
 
-    nu, nv, n, sign = WORKLOADS[name]
+    def __init__(self, bmin, bmax, count):
+        bmin, bmax = np.asarray(bmin, np.float32), np.asarray(bmax, np.float32)
+        self.cell_count = [int(c) for c in count]
+        self.cell_size = ((bmax - bmin) / np.asarray(self.cell_count, np.float32)).astype(np.float32)
+        self.first_cell = (bmin + self.cell_size * np.float32(0.5)).astype(np.float32)
+
+
+def synth_module():
+    """mesh_to_sdf_b200/synth.py loaded by path, so that the reference arm does not import the package."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("m2s_synth", os.path.join(ROOT, "mesh_to_sdf_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_grid_workload(name: str):
+    synth = synth_module()
+    nu, nv, n, sign = GRID_WORKLOADS[name]
     verts, tris = synth.bumpy_torus(nu, nv)
     mn, mx = synth.padded_grid_box(verts)
-    nx = n * world if scaling == "weak" else n
-    grid = m2s.Grid.from_bounding_box(mn, mx, [nx, n, n])
-    return verts, tris, grid, sign, n
+    return verts, tris, PlainGrid(mn, mx, [n, n, n]), sign, synth.mesh_diag(verts)
+
+
+def make_point_workload(name: str):
+    synth = synth_module()
+    nu, nv, nq = POINT_WORKLOADS[name]
+    verts, tris = synth.bumpy_torus(nu, nv)
+    mn, mx = synth.padded_grid_box(verts)
+    return verts, tris, synth.splitmix64_points(nq, mn, mx), synth.mesh_diag(verts)
+
+
+def slab_bounds(nx: int, world: int):
+    return [(nx * r // world, nx * (r + 1) // world) for r in range(world)]
+
+
+def grid_config(name, verts, tris, grid, sign, world):
+    nu, nv = GRID_WORKLOADS[name][:2]
+    return {
+        "workload": f"{name}: bumpy torus T({nu},{nv}) {len(tris)} triangles / {len(verts)} vertices, grid "
+                    f"{grid.cell_count[0]}x{grid.cell_count[1]}x{grid.cell_count[2]}, "
+                    f"SignMethod::{'Raycast' if sign == 0 else 'Normal'}",
+        "triangles": int(len(tris)), "vertices": int(len(verts)), "grid": list(grid.cell_count),
+        "sign_method": "Raycast" if sign == 0 else "Normal",
+        "partition": (f"x-slabs of ONE grid over {world} ranks, strong scaling, assembled into one flat result "
+                      f"(device: peer-mapped stores into rank 0's buffer; host: one shared buffer)")
+        if world > 1 else "single GPU, whole grid",
+        "l2": "flushed between steps (256 MiB device write outside the per-step event pairs)",
+        "step": "records + Morton sort + LBVH + oriented boxes + row parities + nearest kernel, rebuilt every step",
+    }
+
+
+def points_config(name, verts, tris, nq):
+    nu, nv = POINT_WORKLOADS[name][:2]
+    return {
+        "workload": f"{name}: generate_sdf, {nq} scattered queries (splitmix64, uniform in the padded box) on a bumpy "
+                    f"torus T({nu},{nv}) {len(tris)} triangles / {len(verts)} vertices, AccelerationMethod::RtreeBvh",
+        "triangles": int(len(tris)), "vertices": int(len(verts)), "queries": int(nq),
+        "l2": "flushed between steps (256 MiB device write outside the per-step event pairs)",
+        "step": "records + Morton sort + LBVH + oriented boxes + query Morton sort + nearest kernel with the three "
+                "axis-ray parities, rebuilt every step",
+    }
 
 
 def measured_peak():
@@ -62,11 +127,11 @@ def measured_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def ncu_traffic(key: str):
+    """dram bytes per launch of a kernel from the committed ncu capture (profiles/roofline_traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get("k_grid_nearest_dram_bytes_per_launch")
+            return json.load(f).get(key)
     except Exception:
         return None
 
@@ -122,205 +187,564 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_step(oracle, verts, tris, grid, sign, planes: int, threads: int = 0):
-    """The reference CPU path (generate/grid.rs restated, oracle/) on `planes` x-planes cut from the middle of
-    the grid — same mesh, same cell size, same sign method. Returns (seconds, voxels)."""
+# ---------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle/ = test infrastructure: only here, as the checker / the reported baseline)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_grid_sample(oracle, verts, tris, grid, sign, planes: int, threads: int = 0):
+    """The reference CPU path (generate/grid.rs restated, oracle/) on `planes` x-planes cut from the middle of the
+    grid — same mesh, same cell size, same sign method. Returns (seconds, voxels, sdf of the sample, first plane)."""
     nx, ny, nz = grid.cell_count
     planes = min(planes, nx)
     x0 = (nx - planes) // 2
     first = grid.first_cell.copy()
     first[0] = np.float32(first[0] + np.float32(x0) * grid.cell_size[0])
     t0 = time.perf_counter()
-    oracle.generate_grid_sdf_faithful(verts, tris, first, grid.cell_size, [planes, ny, nz], sign, threads)
-    return time.perf_counter() - t0, planes * ny * nz
+    sdf = oracle.generate_grid_sdf_faithful(verts, tris, first, grid.cell_size, [planes, ny, nz], sign, threads)[0]
+    return time.perf_counter() - t0, planes * ny * nz, sdf, x0
+
+
+def grid_parity(oracle, verts, tris, grid, sign, diag, gpu_sdf, faithful, fx0, n_exact=3000):
+    """the three deviation numbers of a grid config. gpu_sdf: our full grid (host); faithful: the
+    reference restatement on the x-planes [fx0, fx0 + planes) (the reference's grid driver propagates candidates
+    between neighbouring cells and can miss the true nearest triangle: generic/bvh.rs:237-239 'sometimes fails')."""
+    nx, ny, nz = grid.cell_count
+    tol = 1e-4 * diag
+    rng = np.random.default_rng(20261017)
+    idx = rng.choice(nx * ny * nz, size=min(n_exact, nx * ny * nz), replace=False).astype(np.uint64)
+    exact = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, sign, idx)
+    got = gpu_sdf[idx.astype(np.int64)]
+    out = {"tolerance": tol, "tolerance_rule": "1e-4 * mesh bbox diagonal",
+           "exact_sample_cells": int(len(idx)),
+           "max_abs_vs_exact_sample": float(np.max(np.abs(got - exact))),
+           "bit_exact_vs_exact_sample": bool(np.array_equal(got.view(np.uint32), exact.view(np.uint32))),
+           "sign_mismatch_vs_exact_sample": int(np.sum(np.signbit(got) != np.signbit(exact)))}
+    planes = len(faithful) // (ny * nz)
+    ours = gpu_sdf[fx0 * ny * nz:(fx0 + planes) * ny * nz]
+    diff = np.abs(faithful) - np.abs(ours)
+    off = np.abs(diff) > tol
+    out.update({
+        "faithful_cells": int(len(faithful)),
+        "frac_gt_tol_vs_faithful": float(np.mean(off)),
+        "one_sided": bool(np.all(diff[off] > 0)),  # wherever they differ the reference's |d| is the LARGER one
+        "max_excess_of_faithful": float(diff.max()) if len(diff) else 0.0,
+        "sign_mismatch_frac_vs_faithful": float(np.mean(np.signbit(faithful[~off]) != np.signbit(ours[~off]))),
+        "note": "faithful = step-by-step restatement of generate/grid.rs (restated C++, not rustc-built); its "
+                "propagation over-estimates some cells, ours is the exact minimum",
+    })
+    return out
+
+
+def libm2s_mapped() -> bool:
+    try:
+        with open("/proc/self/maps") as f:
+            return any("libm2s.so" in line for line in f)
+    except OSError:
+        return False
 
 
 def run_reference(args):
+    """The reference arm: rank 0 only, CPU only; never imports mesh_to_sdf_b200 (asserted on /proc/self/maps)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle
 
     oracle.build()
-    verts, tris, grid, sign, n = make_workload(args.workload, max(1, args.gpus), "weak")
     cores = oracle.hardware_threads()
-    planes = args.ref_planes
+    name = args.workload or ("C3" if args.gpus <= 1 else "C5")
+    if name in POINT_WORKLOADS:
+        verts, tris, queries, _ = make_point_workload(name)
+        nq = min(len(queries), args.ref_queries)
+        unit, cfg = "Mqueries/s", points_config(name, verts, tris, len(queries))
+        sample = (f"SAMPLED: the first {nq} of {len(queries)} queries per step, full mesh, both trees rebuilt per step; "
+                  "tree-accelerated restatement of generic/rtree_bvh.rs (restated C++, not rustc-built)")
+
+        def step():
+            t0 = time.perf_counter()
+            oracle.generate_sdf_tree(verts, tris, queries[:nq], ACCEL_RTREE_BVH, RAYCAST, 0)
+            return time.perf_counter() - t0, nq
+    else:
+        verts, tris, grid, sign, _ = make_grid_workload(name)
+        planes = min(args.ref_planes if name != "C5" else min(args.ref_planes, 16), grid.cell_count[0])
+        n = grid.cell_count[1]
+        unit, cfg = "Mvoxels/s", grid_config(name, verts, tris, grid, sign, max(1, args.gpus))
+        sample = (f"SAMPLED: {planes} of {grid.cell_count[0]} x-planes per step ({planes}x{n}x{n} voxels from the "
+                  f"middle of the grid), full mesh; faithful restatement of generate/grid.rs (restated C++, not "
+                  f"rustc-built)")
+
+        def step():
+            s, v, _, _ = cpu_grid_sample(oracle, verts, tris, grid, sign, planes)
+            return s, v
+    cfg["workload"] += " — reference arm " + sample
     for _ in range(args.warmup):
-        cpu_reference_step(oracle, verts, tris, grid, sign, planes)
+        step()
     tot_s, tot_v = 0.0, 0
     for _ in range(args.steps):
-        s, v = cpu_reference_step(oracle, verts, tris, grid, sign, planes)
+        s, v = step()
         tot_s += s
         tot_v += v
     value = tot_v / tot_s / 1e6
-    sample = (f"{planes} of {grid.cell_count[0]} x-planes (x {planes}x{n}x{n} voxels, middle of the grid) per step, "
-              f"full mesh; faithful restatement of generate/grid.rs (restated C++, not rustc-built)")
+    assert not libm2s_mapped(), "the reference arm must not load the product library"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, verts, tris, grid, sign, max(1, args.gpus), "weak"),
-        "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "higher_is_better": True, "scaling": "weak" if args.gpus <= 1 else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "libm2s_mapped": False,
     }
     print(json.dumps(line), flush=True)
     return 0
 
 
-def workload_config(name, verts, tris, grid, sign, world, scaling):
-    return {
-        "workload": f"{name}: bumpy torus T({WORKLOADS[name][0]},{WORKLOADS[name][1]}) {len(tris)} triangles / "
-                    f"{len(verts)} vertices, grid {grid.cell_count[0]}x{grid.cell_count[1]}x{grid.cell_count[2]}, "
-                    f"SignMethod::{'Raycast' if sign == 0 else 'Normal'}",
-        "triangles": int(len(tris)), "vertices": int(len(verts)), "grid": list(grid.cell_count),
-        "sign_method": "Raycast" if sign == 0 else "Normal",
-        "partition": f"x-slabs, {world} rank(s), {scaling} scaling" if world > 1 else "single GPU, whole grid",
-        "l2": "flushed between steps (256 MiB device write outside the per-step event pairs)",
-        "step": "records + Morton sort + LBVH + oriented boxes + row parities + nearest kernel (neighbour seeds), per step",
-    }
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class Env:
+    """torch / torch.distributed plumbing of one rank."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        if args.gpus > 1 and self.world == 1:
+            raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one process per GPU)")
+        if not torch.cuda.is_available():
+            raise SystemExit("no CUDA device: libm2s has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_list(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-
-    import mesh_to_sdf_b200 as m2s
-    from mesh_to_sdf_b200 import sharding
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one process per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("no CUDA device: libm2s has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    verts, tris, grid, sign, n = make_workload(args.workload, world, args.scaling)
-    nx, ny, nz = grid.cell_count
-    x0, x1 = sharding.slab_bounds(nx, world)[rank]
-    slab_cells = (x1 - x0) * ny * nz
-    total_cells = nx * ny * nz
-
-    stream = torch.cuda.current_stream(dev)
-    ctx = m2s.Context([local_rank], stream=stream.cuda_stream)
-    d_verts = torch.from_numpy(verts).to(dev)
-    d_tris = torch.from_numpy(tris.view(np.int32)).to(dev)
-    d_out = torch.empty(slab_cells, dtype=torch.float32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step_device():
-        ctx.grid_sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), grid, sign, x0, x1,
-                            d_out.data_ptr())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- device-resident arm ("value") ----
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        step_device()
+def timed_device_steps(env, ctx, step, steps, warmup, phase_keys=("build_ms", "sign_ms", "seed_ms", "dist_ms")):
+    """W untimed + K timed steps of `step()` (enqueue only) with an L2 flush before each, CUDA events on the launching
+    stream. Returns (sum of step ms [max over ranks], mean kernel ms [max over ranks], phases of this rank, launches)."""
+    torch = env.torch
+    for _ in range(warmup):
+        env.flush.fill_(1)
+        step()
     ctx.synchronize()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
+    env.barrier()
     launches0 = ctx.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, phase = [], {"build_ms": 0.0, "sign_ms": 0.0, "seed_ms": 0.0, "dist_ms": 0.0}
-    for k in range(args.steps):
-        flush.fill_(k & 0xff)
-        ev[k][0].record(stream)
-        step_device()
-        ev[k][1].record(stream)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    phases = {k: 0.0 for k in phase_keys}
+    kernel_ms = []
+    for k in range(steps):
+        env.flush.fill_(k & 0xff)
+        ev[k][0].record(env.stream)
+        step()
+        ev[k][1].record(env.stream)
         ctx.synchronize()  # also surfaces deferred data errors; outside the event pair's GPU time
         t = ctx.timings()
         kernel_ms.append(t["dist_ms"])
-        for key in phase:
-            phase[key] += t[key] / args.steps
-    barrier()
+        for key in phases:
+            phases[key] += t[key] / steps
+    env.barrier()
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    kern = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    value = total_cells * args.steps / (total_ms * 1e-3) / 1e6
+    total_ms = env.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    kern_ms = env.max_over_ranks(float(np.mean(kernel_ms)))
+    return total_ms, kern_ms, phases, launches
 
-    # ---- end-to-end arm through the host-buffer ABI (pinned host memory) ----
-    h_verts = torch.from_numpy(verts).pin_memory()
-    h_tris = torch.from_numpy(tris.view(np.int32)).pin_memory()
-    h_out = torch.empty(slab_cells, dtype=torch.float32).pin_memory()
-    np_verts, np_tris, np_out = h_verts.numpy(), h_tris.numpy().view(np.uint32), h_out.numpy()
-    for _ in range(2):
-        ctx.grid_sdf_slab(np_verts, np_tris, grid, sign, x0, x1, np_out)
-    barrier()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        ctx.grid_sdf_slab(np_verts, np_tris, grid, sign, x0, x1, np_out)  # synchronous: returns with the slab on the host
-        e2e_s += time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    barrier()
-    e2e_value = total_cells * args.steps / float(e2e_t.item()) / 1e6
-    e2e_phase = ctx.timings()
-    checksum = float(np.abs(np_out[:: max(1, slab_cells // 4096)]).sum())
 
-    # ---- roofline of the dominant kernel (k_grid_nearest_run) ----
-    b_alg = 4 * slab_cells + 12 * len(verts) + 12 * len(tris)  # SURVEY §8d: output once + raw mesh once
-    kern_ms = float(kern.item())
+def timed_host_steps(env, call, steps, warmup=2):
+    """K synchronous host-buffer calls bracketed by barriers; returns seconds (max over ranks)."""
+    for _ in range(warmup):
+        call()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    s = time.perf_counter() - t0
+    s = env.max_over_ranks(s)
+    env.barrier()
+    return s
+
+
+def roofline_block(kernel, kern_ms, b_alg, traffic_key, note):
     peak, peak_src = measured_peak()
     achieved = b_alg / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "k_grid_nearest_run<Raycast, V=2>", "kernel_ms": kern_ms,
-                "algorithmic_bytes_per_launch": b_alg, "peak_source": peak_src,
-                "note": "exact nearest-triangle search is issue/L1-bound, not HBM-bound (see DESIGN.md, profiles/)"}
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(traffic_key), "kernel": kernel, "kernel_ms": kern_ms,
+            "algorithmic_bytes_per_launch": int(b_alg), "peak_source": peak_src, "note": note}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, verts, tris, grid, sign, world, args.scaling),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mvoxels/s", "h2d_bytes_per_step": int(12 * len(verts) + 12 * len(tris)),
-                "d2h_bytes_per_step": int(4 * slab_cells), "ms_per_step": float(e2e_t.item()) / args.steps * 1e3,
-                "api": "m2s_generate_grid_sdf_slab (host buffers, pinned; H2D copy of the mesh, the result written into the pinned destination by the kernel's own stores over PCIe)", "phases_ms_last": e2e_phase,
-                "checksum": checksum},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "phases_ms": phase,
+
+ISSUE_NOTE = ("exact nearest-triangle search is issue-bound, not HBM-bound: the instruction count per voxel, not "
+              "bytes, sets its time (DESIGN.md §3, profiles/)")
+
+
+def bench_grid_single(env, m2s, name, steps, warmup, want_cpu, cpu_planes, want_parity, host_steps=None):
+    """One grid config on ONE GPU: device-resident value, e2e through the facade's pageable buffers (+ pinned),
+    roofline, optional CPU baseline + parity numbers."""
+    torch = env.torch
+    verts, tris, pgrid, sign, diag = make_grid_workload(name)
+    grid = m2s.Grid(pgrid.first_cell, pgrid.cell_size, pgrid.cell_count)
+    nx, ny, nz = grid.cell_count
+    cells = nx * ny * nz
+    host_steps = host_steps or steps
+    ctx = m2s.Context([env.local_rank], stream=env.stream.cuda_stream)
+    d_verts = torch.from_numpy(verts).to(env.dev)
+    d_tris = torch.from_numpy(tris.view(np.int32)).to(env.dev)
+    d_out = torch.empty(cells, dtype=torch.float32, device=env.dev)
+
+    def step_device():
+        ctx.grid_sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), grid, sign, 0, nx,
+                            d_out.data_ptr())
+
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup)
+    clocks = sampler.stop()
+    value = cells * steps / (total_ms * 1e-3) / 1e6
+    del d_out
+
+    # ---- e2e: the facade call, pageable everything (what include/mesh_to_sdf.hpp / the Rust facade hand over) ----
+    topo = m2s.Topology.TriangleList(tris.reshape(-1))  # the caller's flat u32 index list
+    sign_m = m2s.SignMethod(sign)
+    result = {}
+
+    def call_facade():  # allocates its own result like the reference (generate/grid.rs:376 returns a fresh Vec)
+        result["sdf"] = m2s.generate_grid_sdf(verts, topo, grid, sign_m, ctx=ctx)
+
+    s_facade = timed_host_steps(env, call_facade, host_steps)
+    facade_phase = ctx.timings()
+    gpu_sdf = result["sdf"]
+    reuse = np.empty(cells, np.float32)
+    reuse[:] = 0
+
+    def call_reuse():  # the same pageable path into a destination the caller keeps across calls
+        ctx.grid_sdf(verts, tris, grid, sign, reuse)
+
+    s_reuse = timed_host_steps(env, call_reuse, host_steps)
+    pinned = m2s.host_alloc(cells)
+
+    def call_pinned():
+        ctx.grid_sdf(verts, tris, grid, sign, pinned.array)
+
+    s_pinned = timed_host_steps(env, call_pinned, host_steps)
+    pinned_phase = ctx.timings()
+    same = bool(np.array_equal(pinned.array.view(np.uint32), gpu_sdf.view(np.uint32)))
+    pinned.close()
+    h2d = int(12 * len(verts) + 12 * len(tris))
+    e2e = {
+        "value": cells * host_steps / s_facade / 1e6, "unit": "Mvoxels/s", "h2d_bytes_per_step": h2d,
+        "d2h_bytes_per_step": int(4 * cells), "ms_per_step": s_facade / host_steps * 1e3,
+        "api": "generate_grid_sdf(vertices, Topology::TriangleList(indices), grid, sign) -> fresh pageable array: "
+               "m2s_generate_grid_sdf with pageable inputs and destination (index expansion, allocation and the "
+               "first-touch page faults of the result inside the timed region)",
+        "host_path": facade_phase["host_path"], "phases_ms_last": facade_phase,
+        "reused_pageable_destination": {"value": cells * host_steps / s_reuse / 1e6,
+                                        "ms_per_step": s_reuse / host_steps * 1e3},
+        "pinned": {"value": cells * host_steps / s_pinned / 1e6, "ms_per_step": s_pinned / host_steps * 1e3,
+                   "host_path": pinned_phase["host_path"],
+                   "api": "m2s_generate_grid_sdf into an m2s_host_alloc destination (written in place by the "
+                          "kernel's stores over PCIe)"},
+        "pinned_equals_pageable_bitwise": same,
+        "checksum": float(np.abs(gpu_sdf[:: max(1, cells // 4096)]).sum()),
     }
-
-    # ---- CPU baseline beside it (rank 0, N == 1 only) ----
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    b_alg = 4 * cells + 12 * len(verts) + 12 * len(tris)  # SURVEY §8d: output once + raw mesh once
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": grid_config(name, verts, tris, grid, sign, 1),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline_block(f"k_grid_nearest_run<{'Raycast' if sign == 0 else 'Normal'}, V=2>", kern_ms, b_alg,
+                                   f"k_grid_nearest_dram_bytes_per_launch_{name}", ISSUE_NOTE),
+        "phases_ms": phases,
+    }
+    if want_cpu:
         import oracle
 
         oracle.build()
-        planes = args.cpu_planes
-        secs, vox = cpu_reference_step(oracle, verts, tris, grid, sign, planes)
+        secs, vox, faithful, fx0 = cpu_grid_sample(oracle, verts, tris, grid, sign, cpu_planes)
         line["cpu_baseline"] = {
             "value": vox / secs / 1e6, "unit": "Mvoxels/s", "cores": oracle.hardware_threads(), "kind": "port",
             "seconds": secs,
-            "sample": f"{min(planes, nx)} of {nx} x-planes ({vox} voxels, middle of the grid), full mesh, one run; "
+            "sample": f"{min(cpu_planes, nx)} of {nx} x-planes ({vox} voxels, middle of the grid), full mesh, one run; "
                       "faithful restatement of generate/grid.rs (restated C++, not rustc-built)"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+        if want_parity:
+            line["parity"] = grid_parity(oracle, verts, tris, grid, sign, diag, gpu_sdf, faithful, fx0)
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def bench_points_single(env, m2s, name, steps, warmup, want_cpu, cpu_queries):
+    torch = env.torch
+    verts, tris, queries, diag = make_point_workload(name)
+    nq = len(queries)
+    ctx = m2s.Context([env.local_rank], stream=env.stream.cuda_stream)
+    d_verts = torch.from_numpy(verts).to(env.dev)
+    d_tris = torch.from_numpy(tris.view(np.int32)).to(env.dev)
+    d_q = torch.from_numpy(queries).to(env.dev)
+    d_out = torch.empty(nq, dtype=torch.float32, device=env.dev)
+
+    def step_device():
+        ctx.sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), d_q.data_ptr(), nq,
+                       ACCEL_RTREE_BVH, RAYCAST, d_out.data_ptr())
+
+    total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup)
+    value = nq * steps / (total_ms * 1e-3) / 1e6
+    topo = m2s.Topology.TriangleList(tris.reshape(-1))
+    result = {}
+
+    def call_facade():
+        result["sdf"] = m2s.generate_sdf(verts, topo, queries, m2s.AccelerationMethod.RtreeBvh, ctx=ctx)
+
+    s_facade = timed_host_steps(env, call_facade, steps)
+    facade_phase = ctx.timings()
+    gpu = result["sdf"]
+    b_alg = 16 * nq + 12 * len(verts) + 12 * len(tris)  # SURVEY §8d: B_points
+    line = {
+        "metric": "Mqueries/s, generate_sdf 1M scattered queries x 500k triangles (RtreeBvh), 1 GPU vs ref CPU",
+        "value": value, "unit": "Mqueries/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "config": points_config(name, verts, tris, nq),
+        "e2e": {"value": nq * steps / s_facade / 1e6, "unit": "Mqueries/s",
+                "h2d_bytes_per_step": int(12 * len(verts) + 12 * len(tris) + 12 * nq), "d2h_bytes_per_step": int(4 * nq),
+                "ms_per_step": s_facade / steps * 1e3,
+                "api": "generate_sdf(vertices, Topology::TriangleList(indices), queries, RtreeBvh) -> fresh pageable "
+                       "array: m2s_generate_sdf with pageable inputs and destination",
+                "phases_ms_last": facade_phase, "checksum": float(np.abs(gpu[::97]).sum())},
+        "gpu_launches": int(launches),
+        "roofline": roofline_block("k_points_run<UNSIGNED, 3 axis rays>", kern_ms, b_alg,
+                                   "k_points_run_dram_bytes_per_launch_C4", ISSUE_NOTE),
+        "phases_ms": phases,
+    }
+    if want_cpu:
+        import oracle
+
+        oracle.build()
+        n = min(nq, cpu_queries)
+        t0 = time.perf_counter()
+        ref, ms = oracle.generate_sdf_tree(verts, tris, queries[:n], ACCEL_RTREE_BVH, RAYCAST, 0)
+        secs = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": n / secs / 1e6, "unit": "Mqueries/s", "cores": oracle.hardware_threads(), "kind": "port",
+            "seconds": secs, "build_ms": float(ms[0]), "query_ms": float(ms[1]),
+            "sample": f"the first {n} of {nq} queries, full mesh, trees built once; tree-accelerated restatement of "
+                      "generic/rtree_bvh.rs (restated C++, not rustc-built)"}
+        line["parity"] = {"cells": int(n), "bit_exact_vs_cpu_tree_restatement":
+                          bool(np.array_equal(ref.view(np.uint32), gpu[:n].view(np.uint32))),
+                          "max_abs": float(np.max(np.abs(ref - gpu[:n]))), "tolerance": 1e-4 * diag}
+    ctx.close()
+    return line
+
+
+class SharedHostBuffer:
+    """One host buffer that every rank maps (POSIX shared memory; a file under /tmp if /dev/shm is too small)."""
+
+    def __init__(self, env, nbytes: int, tag: str):
+        from multiprocessing import shared_memory
+
+        self.env, self.shm, self.mm, self.path = env, None, None, None
+        name = None
+        if env.rank == 0:
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                name = ("shm", self.shm.name)
+            except Exception:
+                self.path = f"/tmp/m2s_bench_{tag}_{os.getpid()}.bin"
+                with open(self.path, "wb") as f:
+                    f.truncate(nbytes)
+                name = ("file", self.path)
+        box = [name]
+        if env.world > 1:
+            env.dist.broadcast_object_list(box, src=0)
+        kind, ident = box[0]
+        if kind == "shm":
+            if env.rank != 0:
+                self.shm = shared_memory.SharedMemory(name=ident)
+            self.array = np.ndarray((nbytes // 4,), dtype=np.float32, buffer=self.shm.buf)
+        else:
+            self.mm = np.memmap(ident, dtype=np.float32, mode="r+", shape=(nbytes // 4,))
+            self.array = self.mm
+        self.kind = kind
+
+    def close(self):
+        self.array = None
+        self.env.barrier()
+        if self.shm is not None:
+            self.shm.close()
+            if self.env.rank == 0:
+                self.shm.unlink()
+        if self.mm is not None:
+            del self.mm
+        if self.path and self.env.rank == 0:
+            os.unlink(self.path)
+
+
+def bench_grid_multi(env, m2s, name, steps, warmup):
+    """Strong scaling of ONE grid over the ranks, assembled into one flat result."""
+    torch, dist = env.torch, env.dist
+    world, rank = env.world, env.rank
+    verts, tris, pgrid, sign, diag = make_grid_workload(name)
+    grid = m2s.Grid(pgrid.first_cell, pgrid.cell_size, pgrid.cell_count)
+    nx, ny, nz = grid.cell_count
+    plane, cells = ny * nz, nx * ny * nz
+    x0, x1 = slab_bounds(nx, world)[rank]
+    ctx = m2s.Context([env.local_rank], stream=env.stream.cuda_stream)
+    d_verts = torch.from_numpy(verts).to(env.dev)
+    d_tris = torch.from_numpy(tris.view(np.int32)).to(env.dev)
+
+    # rank 0 owns the flat device grid; the others map it (cudaIpc) and their kernels store into it over NVLink
+    base = ctx.device_alloc(4 * cells) if rank == 0 else 0
+    box = [ctx.ipc_export(base) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    mapped = base if rank == 0 else ctx.ipc_open(box[0])
+
+    def step_device():
+        ctx.grid_sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), grid, sign, x0, x1,
+                            mapped + 4 * x0 * plane)
+
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup)
+    clocks = sampler.stop()
+    value = cells * steps / (total_ms * 1e-3) / 1e6
+    rank_table = env.gather_list({"rank": rank, "x": [x0, x1], **{k: round(v, 4) for k, v in phases.items()}})
+    all_launches = sum(env.gather_list(int(launches)))
+
+    # the assembled device grid, checked on rank 0 against the same grid computed by rank 0 alone (also the strong-
+    # scaling base: the same workload on one GPU, in the same run)
+    single = None
+    if rank == 0:
+        d_ref = torch.empty(cells, dtype=torch.float32, device=env.dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = []
+        for k in range(3):
+            env.flush.fill_(k)
+            ev0.record(env.stream)
+            ctx.grid_sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), grid, sign, 0, nx,
+                                d_ref.data_ptr())
+            ev1.record(env.stream)
+            ctx.synchronize()
+            ms.append(ev0.elapsed_time(ev1))
+        try:
+            from cuda.bindings import runtime as cudart
+        except ImportError:
+            from cuda import cudart
+        assembled = torch.empty(cells, dtype=torch.float32, device=env.dev)
+        rc = cudart.cudaMemcpy(assembled.data_ptr(), base, 4 * cells, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+        assert int(rc[0]) == 0
+        single = {"ms_per_step": float(np.mean(ms[1:])), "value": cells / (float(np.mean(ms[1:])) * 1e-3) / 1e6,
+                  "unit": "Mvoxels/s", "what": "the same workload, whole grid, rank 0's GPU alone (device-resident)",
+                  "assembled_equals_single_gpu_bitwise": bool(torch.equal(assembled.view(torch.int32),
+                                                                          d_ref.view(torch.int32)))}
+        del d_ref, assembled
+    env.barrier()
+
+    # ---- e2e: pageable host inputs on every rank, ONE shared host buffer as the destination ----
+    shared = SharedHostBuffer(env, 4 * cells, "grid")
+    mine = shared.array[x0 * plane:x1 * plane]
+
+    def call_host():
+        ctx.grid_sdf_slab(verts, tris, grid, sign, x0, x1, mine)
+
+    s_pageable = timed_host_steps(env, call_host, steps)
+    path_pageable = ctx.timings()["host_path"]
+    checksum = float(np.abs(shared.array[:: max(1, cells // 4096)]).sum()) if rank == 0 else 0.0
+    m2s.host_register(mine)  # page-locked once: every rank's kernel then stores its slab in place
+    s_registered = timed_host_steps(env, call_host, steps)
+    path_registered = ctx.timings()["host_path"]
+    e2e_rank = env.gather_list({"rank": rank, **{k: (round(v, 4) if isinstance(v, float) else v)
+                                                 for k, v in ctx.timings().items()}})
+    m2s.host_unregister(mine)
+    del mine
+    shared.close()
+    h2d = int(12 * len(verts) + 12 * len(tris))
+    e2e = {
+        "value": cells * steps / s_pageable / 1e6, "unit": "Mvoxels/s", "h2d_bytes_per_step": h2d * world,
+        "d2h_bytes_per_step": int(4 * cells), "ms_per_step": s_pageable / steps * 1e3,
+        "api": f"m2s_generate_grid_sdf_slab on every rank: pageable mesh inputs, destination = the rank's slab of ONE "
+               f"pageable host buffer shared by the ranks ({shared.kind})",
+        "host_path": path_pageable,
+        "registered": {"value": cells * steps / s_registered / 1e6, "ms_per_step": s_registered / steps * 1e3,
+                       "host_path": path_registered,
+                       "api": "the same shared buffer page-locked once with m2s_host_register: written in place by "
+                              "the kernels' stores"},
+        "per_rank_phases_ms_last": e2e_rank, "checksum": checksum,
+    }
+    slab_cells = (x1 - x0) * plane
+    b_alg = 4 * slab_cells + 12 * len(verts) + 12 * len(tris)
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": grid_config(name, verts, tris, grid, sign, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(all_launches),
+        "roofline": roofline_block("k_grid_nearest_run<Raycast, V=2> (slowest rank's slab)", kern_ms, b_alg,
+                                   f"k_grid_nearest_dram_bytes_per_launch_{name}", ISSUE_NOTE),
+        "phases_ms": phases, "per_rank_phases_ms": rank_table, "single_gpu_same_workload": single,
+        "assembly": "device: every rank's distance kernel stores its x-slab into rank 0's flat buffer through a "
+                    "cudaIpc peer mapping (NVLink), no gather step; the LBVH is built on every rank (replicated: "
+                    "a broadcast cannot start before rank 0's build ends, DESIGN.md §6)",
+    }
+    if rank != 0:
+        ctx.ipc_close(mapped)
+    env.barrier()
+    if rank == 0:
+        ctx.device_free(base)
+    ctx.close()
+    return line
+
+
+def run_ours(args):
+    env = Env(args)
+    import mesh_to_sdf_b200 as m2s
+
+    warmup = max(args.warmup, 3)
+    if env.world > 1:
+        name = args.workload or "C5"
+        if name not in GRID_WORKLOADS:
+            raise SystemExit("multi-GPU runs take a grid workload (C2, C3, C5)")
+        line = bench_grid_multi(env, m2s, name, args.steps, warmup)
+    else:
+        name = args.workload or "C3"
+        cpu = not args.no_cpu_baseline
+        if name in POINT_WORKLOADS:
+            line = bench_points_single(env, m2s, name, args.steps, warmup, cpu, args.cpu_queries)
+        else:
+            planes = args.cpu_planes if name != "C5" else min(args.cpu_planes, 16)
+            line = bench_grid_single(env, m2s, name, args.steps, warmup, cpu, planes, cpu)
+        if not args.workload and not args.no_extra:
+            extras = []
+            extras.append(bench_grid_single(env, m2s, "C2", args.steps, warmup, cpu, 128, cpu))
+            extras.append(bench_points_single(env, m2s, "C4", args.steps, warmup, cpu, args.cpu_queries))
+            extras.append(bench_grid_single(env, m2s, "C5", max(3, args.steps // 3), warmup, cpu, 8, False,
+                                            host_steps=3))
+            line["extra_configs"] = extras
+    if env.rank == 0:
+        print(json.dumps(line), flush=True)
+    if env.world > 1:
+        env.dist.destroy_process_group()
     return 0
 
 
@@ -330,11 +754,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--workload", default=None, choices=sorted(GRID_WORKLOADS) + sorted(POINT_WORKLOADS),
+                    help="default: C3 on one GPU (+ C2, C4, C5 in extra_configs), C5 on several")
     ap.add_argument("--cpu-planes", type=int, default=256, help="x-planes of the CPU baseline sample (ours arm)")
+    ap.add_argument("--cpu-queries", type=int, default=200_000, help="queries of the C4 CPU baseline sample")
     ap.add_argument("--ref-planes", type=int, default=48, help="x-planes per step of the --impl reference arm")
+    ap.add_argument("--ref-queries", type=int, default=200_000, help="queries per step of the reference arm (C4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_configs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -69,16 +69,19 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     constexpr int NV = 32 * V;         // voxels per tile
     constexpr int QCAP = 32 + 2 * NV;  // < 32 items left over + at most 2 leaves x NV voxels appended by one node
     constexpr uint32_t BZR = 4u * V;   // brick extent in z
-    __shared__ uint2 s_stack[RUN_WARPS][PKT_STACK];
-    __shared__ uint2 s_queue[RUN_WARPS][QCAP];            // (triangle slot | degen, owner voxel = i * 32 + lane)
-    __shared__ unsigned long long s_best[RUN_WARPS][NV];  // per owner voxel: (d2 bits << 32) | [negative bit] | slot
-    __shared__ uint32_t s_pos[RUN_WARPS][SIGN == RUN_SIGN_NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
     constexpr bool NORMAL = SIGN == RUN_SIGN_NORMAL;
+    constexpr bool TREELETS = TREELET_MAX > 1u;
+    __shared__ uint2 s_stack[RUN_WARPS][PKT_STACK];
+    __shared__ uint2 s_queue[RUN_WARPS][QCAP];             // exact items: (triangle slot | degen, owner voxel = i * 32 + lane)
+    __shared__ uint2 s_tqueue[RUN_WARPS][TREELETS ? QCAP : 1];  // treelet items: (treelet ref, owner voxel)
+    __shared__ unsigned long long s_best[RUN_WARPS][NV];   // per owner voxel: (d2 bits << 32) | [negative bit] | slot
+    __shared__ uint32_t s_pos[RUN_WARPS][NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
     const unsigned full = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint2* const stack = s_stack[warp];
     uint2* const queue = s_queue[warp];
+    uint2* const tqueue = s_tqueue[warp];
     unsigned long long* const best = s_best[warp];
     uint32_t* const pos = s_pos[warp];
 
@@ -102,7 +105,9 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     // in mapped host memory (the host copies finished planes while the kernel runs, m2s_api.cu)
     auto signal_done = [&]() {
         if (progress.count == nullptr) return;
-        __threadfence_system();
+        // release at device scope per warp; the warp that completes the plane fences at system scope before it
+        // publishes the flag (cumulative: everything it observed through the counter is ordered before the flag)
+        __threadfence();
         __syncwarp();
         if (lane == 0) {
             const uint32_t done = atomicAdd(progress.count + bx, 1u) + 1u;
@@ -125,21 +130,19 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const float mag = fmaxf(scene_magnitude(st), grid_mag);
     const float eps = 4.0e-6f * mag;
     const float inv_s = pair_inv_scale(mag), inv_s2 = inv_s * inv_s;
-    // (dist + slack)^2, rounded up a little, in the squared units of the scaled nodes
-    auto bound_of = [&](float d2) {
+    // (dist + slack)^2, rounded up a little: the squared search radius in scene units
+    auto radius2_of = [&](float d2) {
         const float dist = sqrt_approx(d2);
         float r = dist + eps;
         if (NORMAL) r += fmaxf(1.0e-6f, dist * 2.4e-7f) * 1.5f;  // the near-tie window of compare_distances
-        return r * r * 1.000001f * inv_s2;
+        return r * r * 1.000001f;
     };
-    float best2[V], bnd[V];
-    uint32_t slot[V];            // NORMAL: | RUN_NEG_BIT if that triangle sees the voxel from behind
-    float pos2[NORMAL ? V : 1];  // NORMAL: squared distance of the nearest positive triangle
+    // the same in the squared units of the scaled nodes
+    auto bound_of = [&](float d2) { return radius2_of(d2) * inv_s2; };
+    // Per-voxel results live in shared memory (best / pos): any lane improves any voxel of the tile with atomicMin.
+    // Registers only keep what every node visit needs: the pruning bound of the lane's own voxels.
+    float bnd[V];
     bool nan = false;
-#pragma unroll
-    for (int i = 0; i < V; ++i) { best2[i] = INFINITY; slot[i] = 0u; }
-#pragma unroll
-    for (int i = 0; i < (NORMAL ? V : 1); ++i) pos2[i] = INFINITY;
 
     // Seed: the nearest triangle of the voxel with the same (y, z run) on the x-far face of the brick
     // `seed_planes` steps back in x, published by the warp that computed it.
@@ -165,19 +168,24 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     {
         const bool degen = (bvh.tri_id[nseed] & TRI_DEGEN_BIT) != 0u;
 #pragma unroll
-        for (int i = 0; i < V; ++i)
+        for (int i = 0; i < V; ++i) {
+            float d2 = INFINITY, p2 = INFINITY;
+            uint32_t sl = 0u;
             if (valid[i]) {
                 const f3 pi = {p0.x, p0.y, i == 0 ? p0.z : cell_center(g.fz, g.sz, z0 + i)};
                 bool neg = false;
-                best2[i] = exact_d2_sign<NORMAL>(bvh, nseed, degen, pi, &neg);
-                slot[i] = nseed | (NORMAL && neg ? RUN_NEG_BIT : 0u);
-                if (NORMAL && !neg) pos2[i] = best2[i];
-                if (NORMAL) nan |= !(best2[i] == best2[i]);
+                d2 = exact_d2_sign<NORMAL>(bvh, nseed, degen, pi, &neg);
+                sl = nseed | (NORMAL && neg ? RUN_NEG_BIT : 0u);
+                if (NORMAL && !neg) p2 = d2;
+                if (NORMAL) nan |= !(d2 == d2);
             }
+            best[lane + 32u * i] = pack_best(d2, sl);
+            if (NORMAL) pos[lane + 32u * i] = __float_as_uint(p2);
+            // voxels outside the grid never want a child or a triangle
+            bnd[i] = valid[i] ? bound_of(d2) : -1.0f;
+        }
     }
-    // voxels outside the grid never want a child or a triangle
-#pragma unroll
-    for (int i = 0; i < V; ++i) bnd[i] = valid[i] ? bound_of(best2[i]) : -1.0f;
+    __syncwarp();
     auto warp_max_b = [&]() {
         float m = 0.0f;
 #pragma unroll
@@ -186,28 +194,23 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     };
     float max_b = warp_max_b();
 
-    int qn = 0, sp = 0;  // warp-uniform
+    int qn = 0, qt = 0, sp = 0;  // warp-uniform
     int overflow = 0;
     [[maybe_unused]] uint32_t n_nodes = 0, n_leaves = 0;
 
-    // every lane calls it; w[i]: this lane's voxel i needs triangle `item`
-    auto enqueue = [&](const bool (&w)[V], uint32_t item) {
+    // every lane calls it; w[i]: this lane's voxel i needs `item` (a triangle for `q`, a treelet for the treelet queue)
+    auto enqueue = [&](uint2* q, int& n, const bool (&w)[V], uint32_t item) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const unsigned m = __ballot_sync(full, w[i]);
-            if (w[i]) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
-            qn += __popc(m);
+            if (w[i]) q[n + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
+            n += __popc(m);
         }
     };
     // exact arithmetic on the queued (triangle, voxel) items, 32 at a time, any lane for any voxel of the tile
     auto flush = [&](bool everything) {
         const int nb = everything ? (qn + 31) >> 5 : qn >> 5;
         if (nb == 0) return;
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            best[lane + 32u * i] = pack_best(best2[i], slot[i]);
-            if (NORMAL) pos[lane + 32u * i] = __float_as_uint(pos2[i]);
-        }
         __syncwarp();
         for (int b = 0; b < nb; ++b) {
             const int idx = b * 32 + (int)lane;
@@ -229,29 +232,66 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         __syncwarp();
         const int done = min(nb * 32, qn), rem = qn - done;
         const uint2 keep = (int)lane < rem ? queue[done + lane] : make_uint2(0u, 0u);
-        unsigned long long v[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            v[i] = best[lane + 32u * i];
-            if (NORMAL) pos2[i] = __uint_as_float(pos[lane + 32u * i]);
-        }
+        for (int i = 0; i < V; ++i)
+            if (valid[i]) bnd[i] = bound_of(__uint_as_float((unsigned)(best[lane + 32u * i] >> 32)));
         __syncwarp();
         if ((int)lane < rem) queue[lane] = keep;
         qn = rem;
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const float n2 = __uint_as_float((unsigned)(v[i] >> 32));
-            if (n2 < best2[i]) bnd[i] = bound_of(n2);
-            best2[i] = n2;  // the packed minimum: never larger than before; NORMAL: an equal d2 may have turned positive
-            slot[i] = (uint32_t)v[i];
-        }
         __syncwarp();
         max_b = warp_max_b();
+    };
+    // treelet items, 32 at a time: one lane tests the oriented boxes of ONE treelet's triangles for ONE voxel that
+    // wanted the treelet (with that voxel's current radius) and queues the survivors for the exact arithmetic
+    auto flush_treelets = [&](bool everything) {
+        const int nb = everything ? (qt + 31) >> 5 : qt >> 5;
+        if (nb == 0) return;
+        __syncwarp();
+        for (int b = 0; b < nb; ++b) {
+            const int idx = b * 32 + (int)lane;
+            const bool act = idx < qt;
+            const uint2 it = act ? tqueue[idx] : make_uint2(0u, lane);
+            const int ow = (int)(it.y & 31u);
+            const f3 po = {__shfl_sync(full, p0.x, ow), __shfl_sync(full, p0.y, ow),
+                           cell_center(g.fz, g.sz, __shfl_sync(full, z0, ow) + (it.y >> 5))};
+            const uint32_t first = it.x & TREELET_FIRST_MASK;
+            const uint32_t cnt = act ? ((it.x & TREELET_COUNT_MASK) >> TREELET_SHIFT) + 1u : 0u;
+            const uint32_t maxc = __reduce_max_sync(full, cnt);
+            for (uint32_t k = 0; k < maxc; ++k) {
+                bool pass = false;
+                uint32_t item = 0u;
+                if (k < cnt) {
+                    const uint32_t j = first + k;
+                    const float4* tb = bvh.tobb + 4 * (size_t)j;
+                    const float4 c = ldg4(tb), u = ldg4(tb + 1), v = ldg4(tb + 2), w = ldg4(tb + 3);
+                    // the owner's radius as it is NOW (other items of this flush may have shrunk it)
+                    const float r2 = radius2_of(__uint_as_float((unsigned)(best[it.y] >> 32)));
+                    pass = obb_dist2(po, c, u, v, w) <= r2;
+                    if (pass) item = j | (bvh.tri_id[j] & TRI_DEGEN_BIT);
+                }
+                const unsigned m = __ballot_sync(full, pass);
+                if (m) {
+                    PKT_COUNT(n_leaves);
+                    if (pass) queue[qn + __popc(m & lt_mask)] = make_uint2(item, it.y);
+                    qn += __popc(m);
+                    if (qn >= 32) flush(false);
+                }
+            }
+        }
+        __syncwarp();
+        const int done = min(nb * 32, qt), rem = qt - done;
+        const uint2 keep = (int)lane < rem ? tqueue[done + lane] : make_uint2(0u, 0u);
+        __syncwarp();
+        if ((int)lane < rem) tqueue[lane] = keep;
+        qt = rem;
+        __syncwarp();
     };
 
     uint32_t cur = 0u;  // the root: always an internal node; leaves are consumed at their parent
     for (;;) {
-        if (qn >= 32) flush(false);  // here, where the loop-carried state merges anyway
+        // here, where the loop-carried state merges anyway
+        if (TREELETS && qt >= 32) flush_treelets(false);
+        if (qn >= 32) flush(false);
         PKT_COUNT(n_nodes);
         const float4* nd = bvh.nodes_il + NODE_F4 * (size_t)cur;  // warp-uniform address
         const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
@@ -292,15 +332,23 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         if ((lref | rref) & LEAF_BIT) {
             if (lref & LEAF_BIT) {
                 if (bl) {
-                    enqueue(wl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                    PKT_COUNT(n_leaves);
+                    if (TREELETS && bvh.treelets && (lref & TREELET_COUNT_MASK)) {
+                        enqueue(tqueue, qt, wl, lref);
+                    } else {
+                        enqueue(queue, qn, wl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                        PKT_COUNT(n_leaves);
+                    }
                 }
                 bl = 0u;
             }
             if (rref & LEAF_BIT) {
                 if (br) {
-                    enqueue(wr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                    PKT_COUNT(n_leaves);
+                    if (TREELETS && bvh.treelets && (rref & TREELET_COUNT_MASK)) {
+                        enqueue(tqueue, qt, wr, rref);
+                    } else {
+                        enqueue(queue, qn, wr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                        PKT_COUNT(n_leaves);
+                    }
                 }
                 br = 0u;
             }
@@ -345,7 +393,17 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             cur = r;
         }
     }
+    if (TREELETS) flush_treelets(true);
     flush(true);
+
+    float best2[V];
+    uint32_t slot[V];  // NORMAL: | RUN_NEG_BIT if that triangle sees the voxel from behind
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const unsigned long long v = best[lane + 32u * i];
+        best2[i] = __uint_as_float((unsigned)(v >> 32));
+        slot[i] = (uint32_t)v;
+    }
 
     // publish the x-far voxels' nearest triangles for the bricks further in x
     if (tile_slot && lane >= 16u && (warp & 2u)) {
@@ -364,7 +422,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         for (int i = 0; i < V; ++i) {
             if (slot[i] & RUN_NEG_BIT) {
                 // lib.rs:242-254: an approximately equal positive distance beats the negative one
-                const float dp = __fsqrt_rn(pos2[NORMAL ? i : 0]);
+                const float dp = __fsqrt_rn(__uint_as_float(pos[lane + 32u * (NORMAL ? i : 0)]));
                 res[i] = approx_eq_abs(dp, res[i]) ? dp : -res[i];
             }
         }
@@ -657,7 +715,7 @@ cudaError_t launch_grid_nearest(Device& d, MeshDev& m, const GridParams& g, int 
     const uint32_t plane_bricks = cdiv(g.ny, BY) * cdiv(g.nz, BZR);
     const uint32_t resident = (uint32_t)d.sm_count * RUN_SEED_BLOCKS;
     const uint32_t planes = std::min(4u, std::max(1u, cdiv(resident * 5u / 4u, plane_bricks)));
-    CK(launch_nodes_interleave(d, m, mag, false));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
+    CK(launch_nodes_interleave(d, m, mag, false, TREELET_MAX));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
     Progress pr{nullptr, nullptr, 0u};
     if (progress) pr = *progress;
     Bvh bvh = m.bvh;

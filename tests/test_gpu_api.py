@@ -204,10 +204,13 @@ def test_other_processes_store_their_slabs_into_one_grid(m2s):
             r = subprocess.run([sys.executable, "-c", _IPC_CHILD, ROOT, handle.hex(), str(x0), str(x1)],
                                capture_output=True, text=True, timeout=300)
             assert r.returncode == 0 and "child ok" in r.stdout, r.stderr[-2000:]
-        import ctypes
         got = np.empty(n, np.float32)
-        rc = torch.cuda.cudart().cudaMemcpy(got.ctypes.data, base, 4 * n, 2)  # cudaMemcpyDeviceToHost
-        assert int(rc) == 0
+        try:
+            from cuda.bindings import runtime as cudart
+        except ImportError:
+            from cuda import cudart
+        rc = cudart.cudaMemcpy(got.ctypes.data, base, 4 * n, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        assert int(rc[0]) == 0
         c.device_free(base)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 

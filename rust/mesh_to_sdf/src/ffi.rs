@@ -1,9 +1,13 @@
-//! Raw declarations of include/m2s.h (ABI version 1). Plain pointers and sizes only.
+//! Raw declarations of include/m2s.h (ABI version 2). Plain pointers and sizes only.
 #![allow(non_camel_case_types, dead_code)]
 use core::ffi::{c_char, c_int, c_void};
 
 #[repr(C)]
 pub struct m2s_ctx {
+    _opaque: [u8; 0],
+}
+#[repr(C)]
+pub struct m2s_mesh {
     _opaque: [u8; 0],
 }
 
@@ -25,6 +29,7 @@ pub struct m2s_timings {
     pub d2h_ms: f32,
     pub total_ms: f32,
     pub seed_ms: f32,
+    pub host_path: c_int,
 }
 
 extern "C" {
@@ -33,7 +38,23 @@ extern "C" {
     pub fn m2s_create_on_stream(device: c_int, cuda_stream: *mut c_void, out: *mut *mut m2s_ctx) -> c_int;
     pub fn m2s_destroy(ctx: *mut m2s_ctx);
     pub fn m2s_last_error(ctx: *const m2s_ctx) -> *const c_char;
+    pub fn m2s_last_error_copy(ctx: *mut m2s_ctx, buf: *mut c_char, n: usize) -> c_int;
     pub fn m2s_last_timings(ctx: *const m2s_ctx, out: *mut m2s_timings) -> c_int;
+    pub fn m2s_set_option(ctx: *mut m2s_ctx, option: c_int, value: i64) -> c_int;
+    pub fn m2s_mesh_create(ctx: *mut m2s_ctx, verts_xyz: *const f32, nv: u64, tri_idx: *const u32, nt: u64, out: *mut *mut m2s_mesh) -> c_int;
+    pub fn m2s_mesh_destroy(mesh: *mut m2s_mesh);
+    pub fn m2s_mesh_grid_sdf(
+        ctx: *mut m2s_ctx, mesh: *mut m2s_mesh, first_cell: *const f32, cell_size: *const f32, cell_count: *const u64,
+        sign_method: c_int, x_begin: u64, x_end: u64, out_slab: *mut f32,
+    ) -> c_int;
+    pub fn m2s_mesh_sdf(
+        ctx: *mut m2s_ctx, mesh: *mut m2s_mesh, queries_xyz: *const f32, nq: u64, accel_method: c_int, sign_method: c_int,
+        out: *mut f32,
+    ) -> c_int;
+    pub fn m2s_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn m2s_host_free(p: *mut c_void);
+    pub fn m2s_host_register(p: *mut c_void, bytes: usize) -> c_int;
+    pub fn m2s_host_unregister(p: *mut c_void) -> c_int;
     pub fn m2s_launch_count(ctx: *const m2s_ctx) -> u64;
     pub fn m2s_device_count(ctx: *const m2s_ctx) -> c_int;
     pub fn m2s_synchronize(ctx: *mut m2s_ctx) -> c_int;

@@ -1,6 +1,8 @@
 //! `Grid` / `SnapResult`: host-side value types with the reference's getters. The flat output order of
 //! `generate_grid_sdf` is `get_cell_idx`: z fastest, x slowest.
 use crate::{ffi, Point};
+#[cfg(feature = "serde")]
+use serde::{de::DeserializeOwned, Deserialize, Serialize};
 
 #[derive(Debug, Clone, PartialEq, Eq, PartialOrd, Ord)]
 pub enum SnapResult {
@@ -8,7 +10,9 @@ pub enum SnapResult {
     Outside([usize; 3]),
 }
 
-#[derive(Debug, Clone, PartialEq, PartialOrd)]
+#[derive(Debug, Clone, PartialEq, PartialOrd, Eq, Ord)]
+#[cfg_attr(feature = "serde", derive(Serialize, Deserialize))]
+#[cfg_attr(feature = "serde", serde(bound = "V: Serialize + DeserializeOwned"))]
 pub struct Grid<V: Point> {
     first_cell: V,
     cell_size: V,

@@ -5,6 +5,8 @@
 mod ffi;
 mod grid;
 mod point;
+#[cfg(feature = "serde")]
+pub mod serde;
 
 pub use grid::{Grid, SnapResult};
 pub use point::Point;
@@ -18,14 +20,14 @@ pub enum Topology<'a, I: Into<u32>> {
     TriangleStrip(Option<&'a [I]>),
 }
 
-#[derive(Debug, Copy, Clone, Default, PartialEq, Eq)]
+#[derive(Debug, Clone, Copy, Default, PartialEq, Eq, PartialOrd, Ord, Hash)]
 pub enum SignMethod {
     #[default]
     Raycast,
     Normal,
 }
 
-#[derive(Debug, Copy, Clone, Default, PartialEq, Eq)]
+#[derive(Default, Debug, Clone, Copy, PartialEq, Eq, PartialOrd, Ord, Hash)]
 pub enum AccelerationMethod {
     None(SignMethod),
     Bvh(SignMethod),
@@ -53,7 +55,10 @@ fn ctx() -> &'static Mutex<Ctx> {
 
 fn check(c: &Ctx, rc: i32) {
     if rc != ffi::M2S_OK {
-        let msg = unsafe { std::ffi::CStr::from_ptr(ffi::m2s_last_error(c.0)) }.to_string_lossy().into_owned();
+        // copied while the context is still locked by this call (m2s_last_error_copy)
+        let mut buf = [0 as core::ffi::c_char; 512];
+        unsafe { ffi::m2s_last_error_copy(c.0, buf.as_mut_ptr(), buf.len()) };
+        let msg = unsafe { std::ffi::CStr::from_ptr(buf.as_ptr()) }.to_string_lossy().into_owned();
         match rc {
             ffi::M2S_ENAN => panic!("NaN distance ({msg})"),
             ffi::M2S_EINDEX => panic!("index out of bounds ({msg})"),
@@ -129,6 +134,116 @@ where
     };
     check(&c, rc);
     out
+}
+
+/// A `Vec<f32>`-like buffer in page-locked, mapped host memory (`m2s_host_alloc`). `generate_grid_sdf_into` has the
+/// distance kernel write it in place over PCIe: no staging buffer, no copy of the result. Derefs to `[f32]`.
+pub struct PinnedVec {
+    ptr: *mut f32,
+    len: usize,
+}
+unsafe impl Send for PinnedVec {}
+impl PinnedVec {
+    pub fn new(len: usize) -> Self {
+        let mut raw = core::ptr::null_mut();
+        let rc = unsafe { ffi::m2s_host_alloc(len.max(1) * 4, &mut raw) };
+        assert!(rc == ffi::M2S_OK, "mesh_to_sdf: m2s_host_alloc failed ({rc})");
+        Self { ptr: raw.cast(), len }
+    }
+}
+impl Drop for PinnedVec {
+    fn drop(&mut self) {
+        unsafe { ffi::m2s_host_free(self.ptr.cast()) }
+    }
+}
+impl core::ops::Deref for PinnedVec {
+    type Target = [f32];
+    fn deref(&self) -> &[f32] {
+        unsafe { core::slice::from_raw_parts(self.ptr, self.len) }
+    }
+}
+impl core::ops::DerefMut for PinnedVec {
+    fn deref_mut(&mut self) -> &mut [f32] {
+        unsafe { core::slice::from_raw_parts_mut(self.ptr, self.len) }
+    }
+}
+
+/// `generate_grid_sdf` into a caller-owned destination of `grid.get_total_cell_count()` floats. A `PinnedVec` is
+/// written in place by the kernel; any other slice is filled through the library's pinned ring while the kernel runs.
+pub fn generate_grid_sdf_into<V, I>(vertices: &[V], indices: Topology<I>, grid: &Grid<V>, sign_method: SignMethod, out: &mut [f32])
+where
+    V: Point + 'static,
+    I: Copy + Into<u32> + Sync + Send,
+{
+    assert_eq!(out.len(), grid.get_total_cell_count(), "destination length does not match the grid");
+    let tris = triangles(vertices.len(), indices);
+    let v = pack(vertices);
+    let (f, s, n) = (grid.get_first_cell(), grid.get_cell_size(), grid.get_cell_count());
+    let (first, size) = ([f.x(), f.y(), f.z()], [s.x(), s.y(), s.z()]);
+    let count = [n[0] as u64, n[1] as u64, n[2] as u64];
+    let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+    let rc = unsafe {
+        ffi::m2s_generate_grid_sdf(c.0, v.as_ptr(), vertices.len() as u64, tris.as_ptr(), (tris.len() / 3) as u64,
+                                   first.as_ptr(), size.as_ptr(), count.as_ptr(), sign_method as i32, out.as_mut_ptr())
+    };
+    check(&c, rc);
+}
+
+/// A mesh uploaded once with its LBVH kept on the GPU(s) (`m2s_mesh_create`): repeated `generate_*` calls on it pay
+/// neither the upload nor the build — the pattern of the reference's viewer, which regenerates the grid of one mesh
+/// on every parameter change (mesh_to_sdf_client/src/sdf_program.rs:679-721).
+pub struct Mesh {
+    raw: *mut ffi::m2s_mesh,
+    n_triangles: usize,
+}
+unsafe impl Send for Mesh {}
+impl Mesh {
+    pub fn new<V: Point, I: Copy + Into<u32>>(vertices: &[V], indices: Topology<I>) -> Self {
+        let tris = triangles(vertices.len(), indices);
+        let v = pack(vertices);
+        let mut raw = core::ptr::null_mut();
+        let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+        let rc = unsafe { ffi::m2s_mesh_create(c.0, v.as_ptr(), vertices.len() as u64, tris.as_ptr(), (tris.len() / 3) as u64, &mut raw) };
+        check(&c, rc);
+        Self { raw, n_triangles: tris.len() / 3 }
+    }
+
+    pub fn generate_grid_sdf<V: Point>(&self, grid: &Grid<V>, sign_method: SignMethod) -> Vec<f32> {
+        let (f, s, n) = (grid.get_first_cell(), grid.get_cell_size(), grid.get_cell_count());
+        let (first, size) = ([f.x(), f.y(), f.z()], [s.x(), s.y(), s.z()]);
+        let count = [n[0] as u64, n[1] as u64, n[2] as u64];
+        let mut out = vec![0f32; grid.get_total_cell_count()];
+        let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+        let rc = unsafe {
+            ffi::m2s_mesh_grid_sdf(c.0, self.raw, first.as_ptr(), size.as_ptr(), count.as_ptr(), sign_method as i32, 0, count[0],
+                                   out.as_mut_ptr())
+        };
+        check(&c, rc);
+        out
+    }
+
+    pub fn generate_sdf<V: Point>(&self, query_points: &[V], acceleration_method: AccelerationMethod) -> Vec<f32> {
+        if self.n_triangles == 0 && acceleration_method == AccelerationMethod::RtreeBvh {
+            return vec![];
+        }
+        let (accel, sign) = match acceleration_method {
+            AccelerationMethod::None(s) => (0, s as i32),
+            AccelerationMethod::Bvh(s) => (1, s as i32),
+            AccelerationMethod::Rtree => (2, 0),
+            AccelerationMethod::RtreeBvh => (3, 0),
+        };
+        let q = pack(query_points);
+        let mut out = vec![0f32; query_points.len()];
+        let c = ctx().lock().unwrap_or_else(|e| e.into_inner());
+        let rc = unsafe { ffi::m2s_mesh_sdf(c.0, self.raw, q.as_ptr(), query_points.len() as u64, accel, sign, out.as_mut_ptr()) };
+        check(&c, rc);
+        out
+    }
+}
+impl Drop for Mesh {
+    fn drop(&mut self) {
+        unsafe { ffi::m2s_mesh_destroy(self.raw) }
+    }
 }
 
 /// What the reference's in-repo caller does with the grid next (mesh_to_sdf_client/src/sdf.rs:62-68, :123):

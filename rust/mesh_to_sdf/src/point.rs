@@ -2,6 +2,11 @@
 //! (constructor, three getters, three mutable getters) so existing impls for user types keep compiling; the
 //! vector algebra the reference's CPU kernels used on it now lives on the device.
 pub trait Point: Sized + Copy + Sync + Send + core::fmt::Debug + PartialEq {
+    /// With the `serde` feature a point is serializable; implementors set `type Serde = Self;` (reference
+    /// `src/point.rs:22-40`).
+    #[cfg(feature = "serde")]
+    type Serde: serde::Serialize + serde::de::DeserializeOwned;
+
     fn new(x: f32, y: f32, z: f32) -> Self;
     fn x(&self) -> f32;
     fn y(&self) -> f32;
@@ -30,6 +35,8 @@ pub trait Point: Sized + Copy + Sync + Send + core::fmt::Debug + PartialEq {
 macro_rules! impl_point_fields {
     ($t:ty, $ctor:expr) => {
         impl Point for $t {
+            #[cfg(feature = "serde")]
+            type Serde = Self;
             fn new(x: f32, y: f32, z: f32) -> Self { $ctor(x, y, z) }
             fn x(&self) -> f32 { self.x }
             fn y(&self) -> f32 { self.y }
@@ -42,6 +49,8 @@ macro_rules! impl_point_fields {
 }
 
 impl Point for [f32; 3] {
+    #[cfg(feature = "serde")]
+    type Serde = Self;
     fn new(x: f32, y: f32, z: f32) -> Self { [x, y, z] }
     fn x(&self) -> f32 { self[0] }
     fn y(&self) -> f32 { self[1] }

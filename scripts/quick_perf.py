@@ -36,6 +36,12 @@ def run_grid(m2s, synth, name, nu, nv, n, sign, reps=3):
             dt = (time.perf_counter() - t0) * 1e3
         print(f"{name} handle    : wall {dt:7.2f} ms | " + " ".join(f"{k}={v:.3f}" if isinstance(v, float) else f"{k}={v}" for k, v in ctx.timings().items()), flush=True)
     print(f"  neg frac {np.mean(pinned.array < 0):.4f} checksum {float(np.abs(pinned.array[::4097]).sum()):.6f}")
+    if os.environ.get("M2S_STATS"):
+        ctx.debug_stats()
+        ctx.grid_sdf(verts, tris, grid, sign, pinned.array)
+        st = ctx.debug_stats()
+        if st[2]:
+            print(f"  stats per tile: nodes {st[0] / st[2]:.1f} leaves {st[1] / st[2]:.1f} tiles {st[2]} seedless {st[3] / st[2]:.3f}")
     pinned.close()
 
 

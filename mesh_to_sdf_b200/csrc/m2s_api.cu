@@ -6,6 +6,8 @@
 // Boundary replaced: the public free functions of the Rust crate, mesh_to_sdf/src/lib.rs:291-311
 // (generate_sdf) and src/generate/grid.rs:265-378 (generate_grid_sdf); their infallible signatures
 // panic where this ABI returns a status (lib.rs:257 "NaN distance", slice index panics, rtree.rs:117).
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
@@ -415,6 +417,20 @@ void mark_call_start(m2s_ctx* ctx, int nd, bool inputs_staged) {
     }
 }
 
+// A freshly allocated destination (the Vec<f32> a facade returns) takes its page faults inside the copy threads: with
+// transparent huge pages in "madvise" mode, asking for them first turns 512 faults per 2 MiB into one. Advisory only.
+void advise_huge_pages(void* p, size_t bytes) {
+#ifdef MADV_HUGEPAGE
+    const uintptr_t huge = 2u << 20;
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + huge - 1) & ~(huge - 1);
+    const uintptr_t b = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(huge - 1);
+    if (b > a) madvise(reinterpret_cast<void*>(a), b - a, MADV_HUGEPAGE);
+#else
+    (void)p;
+    (void)bytes;
+#endif
+}
+
 constexpr size_t PIPELINE_MIN_BYTES = 4u << 20;  // smaller slabs: one staged copy is cheaper than the flag protocol
 
 // ---- grid call, host destination -------------------------------------------------------------------------------
@@ -487,6 +503,7 @@ m2s_status grid_host(m2s_ctx* ctx, m2s_mesh* handle, const float* verts_xyz, uin
             // pageable destination: the kernel writes into the library's pinned ring and publishes a flag per brick
             // plane; host threads copy finished planes into the caller's memory while the kernel is still running
             sl.path = M2S_PATH_PIPELINED;
+            advise_huge_pages(sl.host_dst, bytes);
             CU(ctx, d.stage.ensure(bytes));
             CU(ctx, d.flags.ensure((size_t)sl.planes * 4));
             CU(ctx, d.progress.ensure((size_t)sl.planes * 4));

@@ -138,3 +138,86 @@ def test_gpu_sample_interpolates_the_distance_field(m2s, oracle):
     h = float(np.linalg.norm(grid.cell_size))
     assert np.max(np.abs(tri - exact)) <= h and np.max(np.abs(tet - exact)) <= h
     assert np.median(np.abs(tri - exact)) <= 0.05 * h
+
+
+# ---- hand-derived known answers for sdf_grid() (draw_raymarching.wgsl:118-200, :92-99, :585-650) -----------------
+# A 2x2x2 grid with first_cell = (0,0,0), cell_size = (1,1,1): cell_index == position, so the fractions are the
+# coordinates themselves. Corner values are powers of two and the fractions multiples of 1/4: every product and sum
+# below is exact in f32, so the expected numbers are worked out by hand from the shader's formulas, not by running
+# either implementation. d[x][y][z]:
+_KAT_D = {(0, 0, 0): 1.0, (1, 0, 0): 2.0, (0, 1, 0): 4.0, (0, 0, 1): 8.0,
+          (1, 1, 0): 16.0, (1, 0, 1): 32.0, (0, 1, 1): 64.0, (1, 1, 1): 128.0}
+# (position, expected tetrahedral value): one point strictly inside each of the six tetrahedra of :596-648
+_KAT_TETRA = [
+    # fG>=fB>=fR: (1-g) d000 + (g-b) d010 + (b-r) d011 + r d111
+    ((0.25, 0.75, 0.5), 0.25 * 1 + 0.25 * 4 + 0.25 * 64 + 0.25 * 128),      # 49.25
+    # fB>fR>fG: (1-b) d000 + (b-r) d001 + (r-g) d101 + g d111
+    ((0.5, 0.25, 0.75), 0.25 * 1 + 0.25 * 8 + 0.25 * 32 + 0.25 * 128),      # 42.25
+    # fB>fG>=fR: (1-b) d000 + (b-g) d001 + (g-r) d011 + r d111
+    ((0.25, 0.5, 0.75), 0.25 * 1 + 0.25 * 8 + 0.25 * 64 + 0.25 * 128),      # 50.25
+    # fR>=fG>fB: (1-r) d000 + (r-g) d100 + (g-b) d110 + b d111
+    ((0.75, 0.5, 0.25), 0.25 * 1 + 0.25 * 2 + 0.25 * 16 + 0.25 * 128),      # 36.75
+    # fG>fR>=fB: (1-g) d000 + (g-r) d010 + (r-b) d110 + b d111
+    ((0.5, 0.75, 0.25), 0.25 * 1 + 0.25 * 4 + 0.25 * 16 + 0.25 * 128),      # 37.25
+    # fR>=fB>=fG: (1-r) d000 + (r-b) d100 + (b-g) d101 + g d111
+    ((0.75, 0.25, 0.5), 0.25 * 1 + 0.25 * 2 + 0.25 * 32 + 0.25 * 128),      # 40.75
+    # the diagonal r = g = b = 1/2 takes the LAST matching branch (fR>=fB>=fG): 0.5 d000 + 0.5 d111
+    ((0.5, 0.5, 0.5), 0.5 * 1 + 0.5 * 128),                                  # 64.5
+]
+
+
+def _kat_grid():
+    sdf = np.zeros(8, np.float32)
+    for (x, y, z), v in _KAT_D.items():
+        sdf[z + 2 * y + 4 * x] = v  # Grid::get_cell_idx
+    return sdf, np.zeros(3, np.float32), np.ones(3, np.float32), [2, 2, 2]
+
+
+def _kat_cases():
+    pts, want = [], {0: [], 1: [], 2: []}
+    for p, tet in _KAT_TETRA:
+        x, y, z = p
+        pts.append(p)
+        # trilinear (:155-166): x first, then y, then z
+        c00 = _KAT_D[0, 0, 0] * (1 - x) + _KAT_D[1, 0, 0] * x
+        c01 = _KAT_D[0, 0, 1] * (1 - x) + _KAT_D[1, 0, 1] * x
+        c10 = _KAT_D[0, 1, 0] * (1 - x) + _KAT_D[1, 1, 0] * x
+        c11 = _KAT_D[0, 1, 1] * (1 - x) + _KAT_D[1, 1, 1] * x
+        want[1].append((c00 * (1 - y) + c10 * y) * (1 - z) + (c01 * (1 - y) + c11 * y) * z)
+        want[2].append(tet)
+        # snap (:126-134): floor((p - (first - size/2)) / size) = floor(p + 0.5)
+        want[0].append(_KAT_D[int(x + 0.5), int(y + 0.5), int(z + 0.5)])
+    # hand-checked spot values of the table above
+    assert want[2][0] == 49.25 and want[2][3] == 36.75 and want[2][6] == 64.5
+    assert want[1][6] == (1 + 2 + 4 + 8 + 16 + 32 + 64 + 128) / 8.0  # the centre is the mean of the corners
+    # outside [first_cell, get_last_cell()] = [0, 2]^3: 100.0 whatever the mode (:120-122); the upper border itself is
+    # inside and clamps to the last cell (:92-99): position (2, 2, 2) -> idx (2,2,2), fractions 0 -> d111
+    pts += [(-0.25, 0.5, 0.5), (0.5, 2.25, 0.5), (2.0, 2.0, 2.0), (1.5, 0.0, 0.0)]
+    for m in (0, 1, 2):
+        want[m] += [100.0, 100.0, 128.0]
+    # (1.5, 0, 0): idx (1,0,0) r = (0.5, 0, 0); x+1 clamps to the last cell: every x-neighbour is d1yz
+    want[0].append(_KAT_D[1, 0, 0])
+    want[1].append(_KAT_D[1, 0, 0])
+    want[2].append(0.5 * _KAT_D[1, 0, 0] + 0.5 * _KAT_D[1, 0, 0])  # fR>=fB>=fG: (1-r) d100 + (r-b) d(2->1)00
+    return np.asarray(pts, np.float32), {m: np.asarray(v, np.float32) for m, v in want.items()}
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_sample_known_answers_oracle(mode):
+    sdf, first, size, count = _kat_grid()
+    pts, want = _kat_cases()
+    got = post.sample_grid(sdf, first, size, count, pts, mode)
+    assert np.array_equal(got, want[mode]), (mode, got, want[mode])
+    # iso is subtracted from every fetched value, not from the interpolated result (:98): affine weights sum to 1
+    got_iso = post.sample_grid(sdf, first, size, count, pts[:7], mode, iso=0.5)
+    assert np.array_equal(got_iso, want[mode][:7] - np.float32(0.5))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_sample_known_answers_gpu(m2s, mode):
+    sdf, first, size, count = _kat_grid()
+    pts, want = _kat_cases()
+    grid = m2s.Grid(first, size, count)
+    got = m2s.default_context().sample_grid_sdf(sdf, grid, pts, mode)
+    assert np.array_equal(got, want[mode]), (mode, got, want[mode])

@@ -225,7 +225,6 @@ cudaError_t enqueue_mesh_pull(Device& d, MeshDev& m, const Device& sd, const Mes
     m.nv = src.nv;
     m.nt = nt;
     m.nodes_il_mag = -1.0f;
-    m.nodes_il_treelet = 0;
     if (nt == 0) return cudaSuccess;
     const size_t n_nodes = src.bvh.n_nodes;
     struct Item { DevBuf* dst; const DevBuf* s; size_t bytes; };
@@ -233,8 +232,6 @@ cudaError_t enqueue_mesh_pull(Device& d, MeshDev& m, const Device& sd, const Mes
                           {&m.tri_id_sorted, &src.tri_id_sorted, nt * 4},
                           {&m.nodes, &src.nodes, n_nodes * NODE_F4 * 16},
                           {&m.boxes, &src.boxes, n_nodes * BOX_F4 * 16},
-                          {&m.tobb, &src.tobb, nt * 64},
-                          {&m.node_range, &src.node_range, nt * 8},
                           {&m.status, &src.status, sizeof(BuildStatus)}};
     for (const Item& it : items) {
         if ((e = it.dst->ensure(it.bytes)) != cudaSuccess) return e;
@@ -246,8 +243,6 @@ cudaError_t enqueue_mesh_pull(Device& d, MeshDev& m, const Device& sd, const Mes
     m.bvh.tri_id = m.tri_id_sorted.as<uint32_t>();
     m.bvh.nodes = m.nodes.as<float4>();
     m.bvh.nodes_il = m.nodes_il.as<float4>();
-    m.bvh.node_range = m.node_range.as<uint2>();
-    m.bvh.tobb = m.tobb.as<float4>();
     m.bvh.nt = (uint32_t)nt;
     m.bvh.n_nodes = (uint32_t)n_nodes;
     return cudaSuccess;
@@ -285,7 +280,7 @@ cudaError_t enqueue_grid_query(Device& d, MeshDev& m, const float4* rows_rec, bo
     cudaEventRecord(d.ev[3], d.stream);
     const int mode = raycast ? MODE_UNSIGNED : MODE_NORMAL;
     // node frames in units of S = 2^k >= 4 x the largest |coordinate| (a no-op when current for this grid)
-    if ((e = launch_nodes_interleave(d, m, grid_magnitude(g), false, TREELET_MAX)) != cudaSuccess) return e;
+    if ((e = launch_nodes_interleave(d, m, grid_magnitude(g), false)) != cudaSuccess) return e;
     cudaEventRecord(d.ev[6], d.stream);
     e = launch_grid_nearest(d, m, g, mode, raycast ? &rb : nullptr, d_out, pr);
     cudaEventRecord(d.ev[4], d.stream);
@@ -773,7 +768,7 @@ m2s_status points_call(m2s_ctx* ctx, m2s_mesh* handle, bool host_io, const float
 void release_device(Device& d) {
     cudaSetDevice(d.ordinal);
     if (d.stream || !d.own_stream) cudaStreamSynchronize(d.stream);
-    DevBuf* bufs[] = {&d.verts, &d.tris, &d.rec_orig, &d.tri_lo, &d.tri_hi, &d.keys_in, &d.keys_out,
+    DevBuf* bufs[] = {&d.verts, &d.tris, &d.rec_orig, &d.tobb, &d.tri_lo, &d.tri_hi, &d.keys_in, &d.keys_out,
                       &d.vals_in, &d.vals_out, &d.cub_tmp, &d.leaf_parent, &d.node_parent, &d.node_flag,
                       &d.call_status, &d.rows[0], &d.rows[1], &d.rows[2], &d.big_list, &d.big_count, &d.stats,
                       &d.tile_slot, &d.progress, &d.queries, &d.q_sorted, &d.q_perm, &d.q_keys_in, &d.q_keys_out,

@@ -60,12 +60,11 @@ void PinBuf::release() {
 }
 
 void MeshDev::release() {
-    DevBuf* bufs[] = {&rec_sorted, &tri_id_sorted, &nodes, &nodes_il, &boxes, &status, &node_range, &tobb};
+    DevBuf* bufs[] = {&rec_sorted, &tri_id_sorted, &nodes, &nodes_il, &boxes, &status, &node_range};
     for (DevBuf* b : bufs) b->release();
     bvh = Bvh{};
     nv = nt = 0;
     nodes_il_mag = -1.0f;
-    nodes_il_treelet = 0;
 }
 
 namespace {
@@ -514,28 +513,14 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
 // keeps it a lower bound).
 __global__ void __launch_bounds__(256)
 k_nodes_interleave(const float4* __restrict__ nodes, uint32_t n_nodes, float4* __restrict__ il,
-                   const BuildStatus* __restrict__ st, float grid_mag, const uint2* __restrict__ node_range,
-                   uint32_t treelet_max) {
+                   const BuildStatus* __restrict__ st, float grid_mag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     const float inv_s = pair_inv_scale(fmaxf(scene_mag(st), grid_mag));
     const float4* nd = nodes + NODE_F4 * (size_t)i;
     float4* o = il + NODE_F4 * (size_t)i;
     {
-        float4 l = nd[0], r = nd[CHILD_F4];
-        if (treelet_max > 1u) {
-            // a child with a small subtree becomes a treelet ref: (count - 1, first leaf), see m2s_internal.h
-            uint32_t refs[2] = {__float_as_uint(l.w), __float_as_uint(r.w)};
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (refs[k] & LEAF_BIT) continue;
-                const uint2 rg = node_range[refs[k]];
-                const uint32_t cnt = rg.y - rg.x + 1u;
-                if (cnt <= treelet_max) refs[k] = LEAF_BIT | ((cnt - 1u) << TREELET_SHIFT) | rg.x;
-            }
-            l.w = __uint_as_float(refs[0]);
-            r.w = __uint_as_float(refs[1]);
-        }
+        const float4 l = nd[0], r = nd[CHILD_F4];
         o[0] = make_float4(l.x, r.x, l.y, r.y);
         o[1] = make_float4(l.z, r.z, l.w, r.w);
     }
@@ -705,7 +690,6 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
     m.nv = nv;
     m.nt = nt;
     m.nodes_il_mag = -1.0f;
-    m.nodes_il_treelet = 0;
     if (nt == 0) return cudaSuccess;
     CK(launch_mesh_status_reset(d, m));
     BuildStatus* st = m.status.as<BuildStatus>();
@@ -725,7 +709,7 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
     CK(m.nodes_il.ensure(n_nodes * NODE_F4 * 16));
     CK(m.boxes.ensure(n_nodes * BOX_F4 * 16));
     CK(m.node_range.ensure((size_t)nleaf * 8));
-    CK(m.tobb.ensure(nt * 64));
+    CK(d.tobb.ensure(nt * 64));
     CK(d.leaf_parent.ensure((size_t)nleaf * 4));
     CK(d.node_parent.ensure((size_t)nleaf * 4));
     CK(d.node_flag.ensure((size_t)nleaf * 4));
@@ -747,7 +731,7 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
     d.launches += 8;  // CUB onesweep: histogram + scan + 6 digit passes
     k_tri_permute<<<blocks_for(nt, bs), bs, 0, s>>>(d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
                                                     d.vals_out.as<uint32_t>(), (uint32_t)nt, st,
-                                                    m.rec_sorted.as<float4>(), m.tobb.as<float4>(),
+                                                    m.rec_sorted.as<float4>(), d.tobb.as<float4>(),
                                                     m.tri_id_sorted.as<uint32_t>());
     d.launches++;
     if (nleaf > 1) {
@@ -760,11 +744,11 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
                                                      m.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                      d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
         k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
-            m.rec_sorted.as<float4>(), m.tobb.as<float4>(), (uint32_t)nt, (int)nleaf, m.boxes.as<float4>(),
+            m.rec_sorted.as<float4>(), d.tobb.as<float4>(), (uint32_t)nt, (int)nleaf, m.boxes.as<float4>(),
             m.nodes.as<float4>(), m.node_range.as<uint2>(), st, 1.0f);
         d.launches += 3;
     } else {
-        k_single_root<<<1, 32, 0, s>>>(m.tobb.as<float4>(), d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),
+        k_single_root<<<1, 32, 0, s>>>(d.tobb.as<float4>(), d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),
                                        m.nodes.as<float4>(), m.boxes.as<float4>(), m.node_range.as<uint2>());
         d.launches++;
     }
@@ -776,8 +760,6 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
     m.bvh.nt = (uint32_t)nt;
     m.bvh.n_nodes = (uint32_t)n_nodes;
     m.bvh.node_range = m.node_range.as<uint2>();
-    m.bvh.tobb = m.tobb.as<float4>();
-    m.bvh.treelets = 0;
     m.bvh.stats = nullptr;
     return cudaGetLastError();
 }
@@ -785,19 +767,12 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
 // Writes Bvh::nodes_il in units of S = 2^k >= 4 x max(scene magnitude of the CALL's status block, mag_key).
 // Grids pass their host-known magnitude as the key (a no-op when it is current); point calls force it, because
 // the call's bounds include the queries, which only the device knows.
-cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool force, uint32_t treelet_max) {
-    if (m.bvh.n_nodes == 0) return cudaSuccess;
-    // treelet refs need 4 count bits above the first-leaf index
-    if (m.nt > (1ull << TREELET_SHIFT) || treelet_max < 1u) treelet_max = 1u;
-    if (treelet_max > 16u) treelet_max = 16u;
-    m.bvh.treelets = treelet_max > 1u ? 1u : 0u;
-    if (!force && m.nodes_il_mag == mag_key && m.nodes_il_treelet == treelet_max) return cudaSuccess;
+cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool force) {
+    if (m.bvh.n_nodes == 0 || (!force && m.nodes_il_mag == mag_key)) return cudaSuccess;
     k_nodes_interleave<<<blocks_for(m.bvh.n_nodes, 256), 256, 0, d.stream>>>(
-        m.nodes.as<float4>(), m.bvh.n_nodes, m.nodes_il.as<float4>(), d.call_status.as<BuildStatus>(), mag_key,
-        m.node_range.as<uint2>(), treelet_max);
+        m.nodes.as<float4>(), m.bvh.n_nodes, m.nodes_il.as<float4>(), d.call_status.as<BuildStatus>(), mag_key);
     d.launches++;
     m.nodes_il_mag = force ? -1.0f : mag_key;
-    m.nodes_il_treelet = treelet_max;
     return cudaGetLastError();
 }
 

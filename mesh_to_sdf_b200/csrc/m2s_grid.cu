@@ -70,10 +70,8 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     constexpr int QCAP = 32 + 2 * NV;  // < 32 items left over + at most 2 leaves x NV voxels appended by one node
     constexpr uint32_t BZR = 4u * V;   // brick extent in z
     constexpr bool NORMAL = SIGN == RUN_SIGN_NORMAL;
-    constexpr bool TREELETS = TREELET_MAX > 1u;
     __shared__ uint2 s_stack[RUN_WARPS][PKT_STACK];
     __shared__ uint2 s_queue[RUN_WARPS][QCAP];             // exact items: (triangle slot | degen, owner voxel = i * 32 + lane)
-    __shared__ uint2 s_tqueue[RUN_WARPS][TREELETS ? QCAP : 1];  // treelet items: (treelet ref, owner voxel)
     __shared__ unsigned long long s_best[RUN_WARPS][NV];   // per owner voxel: (d2 bits << 32) | [negative bit] | slot
     __shared__ uint32_t s_pos[RUN_WARPS][NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
     const unsigned full = 0xffffffffu;
@@ -81,7 +79,6 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const unsigned lt_mask = (1u << lane) - 1u;
     uint2* const stack = s_stack[warp];
     uint2* const queue = s_queue[warp];
-    uint2* const tqueue = s_tqueue[warp];
     unsigned long long* const best = s_best[warp];
     uint32_t* const pos = s_pos[warp];
 
@@ -159,10 +156,14 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 3, 1ull);
 #endif
     if (__any_sync(full, nseed >= bvh.nt)) {
-        // no neighbour result (first brick planes of a launch): one greedy descent for a voxel in the middle of
-        // the tile, the same on every lane (uniform loads, no divergence); its triangle seeds the lanes without one
+        // no neighbour result (first brick planes of a launch): the nearest triangle of a voxel in the middle of the
+        // tile, searched identically by every lane (uniform loads, no divergence), seeds the lanes without one
         const f3 pc = {__shfl_sync(full, p0.x, 13), __shfl_sync(full, p0.y, 13), __shfl_sync(full, p0.z, 13)};
+#ifdef M2S_GREEDY_SEED
         const uint32_t gl = greedy_leaf(bvh, pc);
+#else
+        const uint32_t gl = nearest_leaf_uniform(bvh, pc, stack);
+#endif
         if (nseed >= bvh.nt) nseed = gl;
     }
     {
@@ -194,17 +195,17 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     };
     float max_b = warp_max_b();
 
-    int qn = 0, qt = 0, sp = 0;  // warp-uniform
+    int qn = 0, sp = 0;  // warp-uniform
     int overflow = 0;
     [[maybe_unused]] uint32_t n_nodes = 0, n_leaves = 0;
 
-    // every lane calls it; w[i]: this lane's voxel i needs `item` (a triangle for `q`, a treelet for the treelet queue)
-    auto enqueue = [&](uint2* q, int& n, const bool (&w)[V], uint32_t item) {
+    // every lane calls it; w[i]: this lane's voxel i needs triangle `item`
+    auto enqueue = [&](const bool (&w)[V], uint32_t item) {
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             const unsigned m = __ballot_sync(full, w[i]);
-            if (w[i]) q[n + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
-            n += __popc(m);
+            if (w[i]) queue[qn + __popc(m & lt_mask)] = make_uint2(item, lane + 32u * i);
+            qn += __popc(m);
         }
     };
     // exact arithmetic on the queued (triangle, voxel) items, 32 at a time, any lane for any voxel of the tile
@@ -241,69 +242,14 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         __syncwarp();
         max_b = warp_max_b();
     };
-    // treelet items, 32 at a time: one lane tests the oriented boxes of ONE treelet's triangles for ONE voxel that
-    // wanted the treelet (with that voxel's current radius) and queues the survivors for the exact arithmetic
-    auto flush_treelets = [&](bool everything) {
-        const int nb = everything ? (qt + 31) >> 5 : qt >> 5;
-        if (nb == 0) return;
-        __syncwarp();
-        for (int b = 0; b < nb; ++b) {
-            const int idx = b * 32 + (int)lane;
-            const bool act = idx < qt;
-            const uint2 it = act ? tqueue[idx] : make_uint2(0u, lane);
-            const int ow = (int)(it.y & 31u);
-            const f3 po = {__shfl_sync(full, p0.x, ow), __shfl_sync(full, p0.y, ow),
-                           cell_center(g.fz, g.sz, __shfl_sync(full, z0, ow) + (it.y >> 5))};
-            const uint32_t first = it.x & TREELET_FIRST_MASK;
-            const uint32_t cnt = act ? ((it.x & TREELET_COUNT_MASK) >> TREELET_SHIFT) + 1u : 0u;
-            const uint32_t maxc = __reduce_max_sync(full, cnt);
-            for (uint32_t k = 0; k < maxc; ++k) {
-                bool pass = false;
-                uint32_t item = 0u;
-                if (k < cnt) {
-                    const uint32_t j = first + k;
-                    const float4* tb = bvh.tobb + 4 * (size_t)j;
-                    const float4 c = ldg4(tb), u = ldg4(tb + 1), v = ldg4(tb + 2), w = ldg4(tb + 3);
-                    // the owner's radius as it is NOW (other items of this flush may have shrunk it)
-                    const float r2 = radius2_of(__uint_as_float((unsigned)(best[it.y] >> 32)));
-                    pass = obb_dist2(po, c, u, v, w) <= r2;
-                    if (pass) item = j | (bvh.tri_id[j] & TRI_DEGEN_BIT);
-                }
-                const unsigned m = __ballot_sync(full, pass);
-                if (m) {
-                    PKT_COUNT(n_leaves);
-                    if (pass) queue[qn + __popc(m & lt_mask)] = make_uint2(item, it.y);
-                    qn += __popc(m);
-                    if (qn >= 32) flush(false);
-                }
-            }
-        }
-        __syncwarp();
-        const int done = min(nb * 32, qt), rem = qt - done;
-        const uint2 keep = (int)lane < rem ? tqueue[done + lane] : make_uint2(0u, 0u);
-        __syncwarp();
-        if ((int)lane < rem) tqueue[lane] = keep;
-        qt = rem;
-        __syncwarp();
-    };
-
-    uint32_t cur = 0u;  // the root: always an internal node; leaves are consumed at their parent
-    for (;;) {
-        // here, where the loop-carried state merges anyway
-        if (TREELETS && qt >= 32) flush_treelets(false);
-        if (qn >= 32) flush(false);
-        PKT_COUNT(n_nodes);
-        const float4* nd = bvh.nodes_il + NODE_F4 * (size_t)cur;  // warp-uniform address
+    // squared lower bounds of this lane's voxels against the two children of a node: low half of every packed
+    // operation = left child, high half = right child
+    auto pair_bounds = [&](const float4* nd, float2 (&dd)[V], uint32_t& lref, uint32_t& rref) {
         const float4 q0 = ldg4(nd), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
         const float4 q4 = ldg4(nd + 4), q5 = ldg4(nd + 5), q6 = ldg4(nd + 6), q7 = ldg4(nd + 7);
-        const uint32_t lref = __float_as_uint(q1.z), rref = __float_as_uint(q1.w);
-#ifdef M2S_PREFETCH
-        // both children's nodes on their way to L1 while this node's bounds are evaluated
-        if (!(lref & LEAF_BIT)) asm volatile("prefetch.global.L1 [%0];" ::"l"(bvh.nodes_il + NODE_F4 * (size_t)lref));
-        if (!(rref & LEAF_BIT)) asm volatile("prefetch.global.L1 [%0];" ::"l"(bvh.nodes_il + NODE_F4 * (size_t)rref));
-#endif
+        lref = __float_as_uint(q1.z);
+        rref = __float_as_uint(q1.w);
         const float2 m1 = make_float2(-1.0f, -1.0f);
-        // low half: left child, high half: right child
         const float2 dx = __ffma2_rn(f2lo(q0), m1, make_float2(p0.x, p0.x));
         const float2 dy = __ffma2_rn(f2hi(q0), m1, make_float2(p0.y, p0.y));
         const float2 dz = __ffma2_rn(f2lo(q1), m1, make_float2(p0.z, p0.z));
@@ -311,7 +257,6 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         const float2 tv = __ffma2_rn(dz, f2lo(q5), __ffma2_rn(dy, f2hi(q4), __fmul2_rn(dx, f2lo(q4))));
         const float2 tw = __ffma2_rn(dz, f2lo(q7), __ffma2_rn(dy, f2hi(q6), __fmul2_rn(dx, f2lo(q6))));
         const float2 eu = f2hi(q3), ev = f2hi(q5), ew = f2hi(q7);
-        float2 dd[V];  // squared lower bounds of voxel i: (left child, right child)
         dd[0] = sumsq2(excess2(tu, eu), excess2(tv, ev), excess2(tw, ew));
 #pragma unroll
         for (int i = 1; i < V; ++i) {
@@ -319,6 +264,14 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             dd[i] = sumsq2(excess2(__ffma2_rn(s2, f2lo(q3), tu), eu), excess2(__ffma2_rn(s2, f2lo(q5), tv), ev),
                            excess2(__ffma2_rn(s2, f2lo(q7), tw), ew));
         }
+    };
+    uint32_t cur = 0u;  // the root: always an internal node; leaves are consumed at their parent
+    for (;;) {
+        if (qn >= 32) flush(false);  // here, where the loop-carried state merges anyway
+        PKT_COUNT(n_nodes);
+        float2 dd[V];  // squared lower bounds of voxel i: (left child, right child)
+        uint32_t lref, rref;
+        pair_bounds(bvh.nodes_il + NODE_F4 * (size_t)cur, dd, lref, rref);  // warp-uniform address
         bool wl[V], wr[V];  // voxel i wants the left / right child
         bool any_l = false, any_r = false;
 #pragma unroll
@@ -332,23 +285,15 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         if ((lref | rref) & LEAF_BIT) {
             if (lref & LEAF_BIT) {
                 if (bl) {
-                    if (TREELETS && bvh.treelets && (lref & TREELET_COUNT_MASK)) {
-                        enqueue(tqueue, qt, wl, lref);
-                    } else {
-                        enqueue(queue, qn, wl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                        PKT_COUNT(n_leaves);
-                    }
+                    enqueue(wl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    PKT_COUNT(n_leaves);
                 }
                 bl = 0u;
             }
             if (rref & LEAF_BIT) {
                 if (br) {
-                    if (TREELETS && bvh.treelets && (rref & TREELET_COUNT_MASK)) {
-                        enqueue(tqueue, qt, wr, rref);
-                    } else {
-                        enqueue(queue, qn, wr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                        PKT_COUNT(n_leaves);
-                    }
+                    enqueue(wr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
+                    PKT_COUNT(n_leaves);
                 }
                 br = 0u;
             }
@@ -393,7 +338,6 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             cur = r;
         }
     }
-    if (TREELETS) flush_treelets(true);
     flush(true);
 
     float best2[V];
@@ -715,7 +659,7 @@ cudaError_t launch_grid_nearest(Device& d, MeshDev& m, const GridParams& g, int 
     const uint32_t plane_bricks = cdiv(g.ny, BY) * cdiv(g.nz, BZR);
     const uint32_t resident = (uint32_t)d.sm_count * RUN_SEED_BLOCKS;
     const uint32_t planes = std::min(4u, std::max(1u, cdiv(resident * 5u / 4u, plane_bricks)));
-    CK(launch_nodes_interleave(d, m, mag, false, TREELET_MAX));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
+    CK(launch_nodes_interleave(d, m, mag, false));  // node frames in units of S = 2^k >= 4 x the largest |coordinate|
     Progress pr{nullptr, nullptr, 0u};
     if (progress) pr = *progress;
     Bvh bvh = m.bvh;

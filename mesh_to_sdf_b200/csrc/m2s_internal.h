@@ -40,17 +40,6 @@ constexpr uint32_t LEAF_BIT = 0x80000000u;
 constexpr uint32_t LEAF_DEGEN_BIT = 0x40000000u;
 constexpr uint32_t LEAF_INDEX_MASK = 0x3fffffffu;
 constexpr uint32_t TRI_DEGEN_BIT = 0x80000000u;  // in tri_id_sorted
-// Treelets (interleaved nodes only, meshes of at most 2^26 triangles): a child whose subtree has 2..TREELET_MAX
-// leaves is stored as a leaf-like ref  LEAF_BIT | (count - 1) << 26 | first leaf  - the packet walk stops there and
-// the voxels that want it test the triangles' own oriented boxes (Bvh::tobb) one voxel per lane, instead of the
-// whole packet walking the last levels of the tree. A single-triangle leaf has count - 1 == 0.
-constexpr uint32_t TREELET_SHIFT = 26;
-constexpr uint32_t TREELET_COUNT_MASK = 0x3c000000u;
-constexpr uint32_t TREELET_FIRST_MASK = 0x03ffffffu;
-#ifndef M2S_TREELET
-#define M2S_TREELET 8
-#endif
-constexpr uint32_t TREELET_MAX = M2S_TREELET;  // 1 = off; at most 16
 
 // Status block, 64 B. One per mesh (written by the build: error flags of the mesh + its bounds) and one per
 // call (k_call_status_init copies the mesh's block, the query kernels add the query bounds and their own flags).
@@ -75,9 +64,7 @@ struct Bvh {
     uint32_t nt;              // triangles = leaves
     uint32_t n_nodes;         // internal nodes (>= 1 when nt >= 1)
     unsigned long long* stats; // optional traversal counters (-DM2S_STATS_BUILD + M2S_STATS=1): nodes, leaves, tiles
-    const uint2* node_range;   // per internal node: first / last leaf
-    const float4* tobb;        // leaf-order triangle oriented boxes (centre, 0) (u, eu) (v, ev) (w, ew): treelet tests
-    uint32_t treelets;         // 1 if nodes_il carries treelet refs (set by launch_nodes_interleave)
+    const uint2* node_range;   // per internal node: first / last leaf (box fitting, diagnostics)
 };
 
 struct GridParams {
@@ -143,11 +130,10 @@ struct PinBuf {
 // A mesh + its LBVH on one device: everything the query kernels read. Owned either by a Device (the scratch mesh
 // of the one-shot entry points, rebuilt per call) or by an m2s_mesh handle (built once, queried many times).
 struct MeshDev {
-    DevBuf rec_sorted, tri_id_sorted, nodes, nodes_il, boxes, status, node_range, tobb;
+    DevBuf rec_sorted, tri_id_sorted, nodes, nodes_il, boxes, status, node_range;
     Bvh bvh{};
     uint64_t nv = 0, nt = 0;
     float nodes_il_mag = -1.0f;  // magnitude key the interleaved nodes were last written for (< 0: stale)
-    uint32_t nodes_il_treelet = 0;  // treelet size they were written with
     void release();
 };
 
@@ -162,7 +148,7 @@ struct Device {
 
     DevBuf verts, tris;           // staging for the host entry points
     // build scratch (dead after launch_build)
-    DevBuf rec_orig, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
+    DevBuf rec_orig, tobb, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
     DevBuf leaf_parent, node_parent, node_flag;
     MeshDev scratch;              // the mesh of the one-shot entry points
     DevBuf call_status;           // per-call BuildStatus (mesh block + query bounds + this call's flags)
@@ -210,8 +196,7 @@ cudaError_t launch_call_status_init(Device& d, const MeshDev& m, bool clear_erro
 // after_records (optional) is recorded once the leaf-order triangle records exist (what the row kernels need)
 cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t nv, const uint32_t* d_tris, uint64_t nt,
                          cudaEvent_t after_records = nullptr);
-// treelet_max: 1 = every leaf is a single triangle (the point kernels), TREELET_MAX for the grid kernel
-cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool force, uint32_t treelet_max);
+cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool force);
 cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
 
 // rec: triangle records in any order (every triangle toggles its own rows)

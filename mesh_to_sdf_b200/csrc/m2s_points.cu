@@ -354,7 +354,7 @@ cudaError_t launch_points(Device& d, MeshDev& m, uint64_t nq, int mode, int sign
     BuildStatus* st = d.call_status.as<BuildStatus>();
     const uint32_t n = (uint32_t)nq;
     // after sort_queries: the call's scene bounds now include the queries, which only the device knows
-    CK(launch_nodes_interleave(d, m, 0.0f, true, 1u));
+    CK(launch_nodes_interleave(d, m, 0.0f, true));
     const unsigned nbr = (unsigned)((nq + 127) / 128);
     Bvh bvh = m.bvh;
 #ifdef M2S_STATS_BUILD

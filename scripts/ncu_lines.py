@@ -5,8 +5,10 @@ rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "mesh_to_sdf_b200", "libm2s.so")], cwd=tmp, capture_output=True)
-sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, "m2s_query.sm_100a.cubin")], capture_output=True, text=True).stdout
+lib = os.environ.get("M2S_LIB", os.path.join(root, "mesh_to_sdf_b200", "libm2s.so"))
+subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
+sass = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+               for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 kname = rows[0][1]
@@ -41,7 +43,7 @@ for a, c, t, s in data:
     tot += c; tott += t; tots += s
 print(f"warp instr {tot:.4g}  thread instr {tott:.4g}  avg active threads {tott / tot:.2f}")
 src = {}
-for name in ("m2s_query.cu", "m2s_geom.cuh"):
+for name in os.listdir(os.path.join(root, "mesh_to_sdf_b200", "csrc")):
     src[name] = open(os.path.join(root, "mesh_to_sdf_b200", "csrc", name)).read().splitlines()
 for ln, (c, t, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     text = ""

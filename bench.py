@@ -91,6 +91,28 @@ def slab_bounds(nx: int, world: int):
     return [(nx * r // world, nx * (r + 1) // world) for r in range(world)]
 
 
+def rebalance(bounds, times, align: int = 4):
+    """New slab boundaries from the measured time of every slab: the cost per x-plane is taken as uniform inside a
+    slab, the new cuts sit at equal shares of the cumulative cost, rounded to whole brick planes (`align` x-planes).
+    bounds: [(x0, x1)] per rank, times: seconds or ms per rank."""
+    world, nx = len(bounds), bounds[-1][1]
+    total = float(sum(times))
+    if world == 1 or total <= 0:
+        return list(bounds)
+    cuts, acc, r = [0], 0.0, 0
+    for k in range(1, world):
+        want = total * k / world
+        while r < world - 1 and acc + times[r] < want:
+            acc += times[r]
+            r += 1
+        x0, x1 = bounds[r]
+        x = x0 + (x1 - x0) * (want - acc) / max(times[r], 1e-12)
+        x = int(round(x / align)) * align
+        cuts.append(min(max(x, cuts[-1] + align), nx - align * (world - k)))
+    cuts.append(nx)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
 def grid_config(name, verts, tris, grid, sign, world):
     nu, nv = GRID_WORKLOADS[name][:2]
     return {
@@ -602,7 +624,7 @@ class SharedHostBuffer:
             os.unlink(self.path)
 
 
-def bench_grid_multi(env, m2s, name, steps, warmup):
+def bench_grid_multi(env, m2s, name, steps, warmup, balance=True):
     """Strong scaling of ONE grid over the ranks, assembled into one flat result."""
     torch, dist = env.torch, env.dist
     world, rank = env.world, env.rank
@@ -610,7 +632,7 @@ def bench_grid_multi(env, m2s, name, steps, warmup):
     grid = m2s.Grid(pgrid.first_cell, pgrid.cell_size, pgrid.cell_count)
     nx, ny, nz = grid.cell_count
     plane, cells = ny * nz, nx * ny * nz
-    x0, x1 = slab_bounds(nx, world)[rank]
+    bounds = slab_bounds(nx, world)
     ctx = m2s.Context([env.local_rank], stream=env.stream.cuda_stream)
     d_verts = torch.from_numpy(verts).to(env.dev)
     d_tris = torch.from_numpy(tris.view(np.int32)).to(env.dev)
@@ -620,10 +642,27 @@ def bench_grid_multi(env, m2s, name, steps, warmup):
     box = [ctx.ipc_export(base) if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     mapped = base if rank == 0 else ctx.ipc_open(box[0])
+    cut = {"x0": bounds[rank][0], "x1": bounds[rank][1]}
 
     def step_device():
-        ctx.grid_sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), grid, sign, x0, x1,
-                            mapped + 4 * x0 * plane)
+        ctx.grid_sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), grid, sign, cut["x0"],
+                            cut["x1"], mapped + 4 * cut["x0"] * plane)
+
+    # Equal-width slabs are uneven in cost (profiles/r2b_c5_slab_balance.log: 0.86 at 8 slabs). A service that
+    # regenerates grids keeps the split of its last call: the cuts are moved to equal shares of the measured kernel
+    # time during UNTIMED steps, then frozen for the warm-up and the timed steps.
+    balance_log = [[list(b) for b in bounds]]
+    if balance:
+        for _ in range(4):
+            env.flush.fill_(3)
+            step_device()
+            ctx.synchronize()
+            times = env.gather_list(float(ctx.timings()["dist_ms"]))
+            bounds = rebalance(bounds, times)
+            cut["x0"], cut["x1"] = bounds[rank]
+            balance_log.append([list(b) for b in bounds])
+        env.barrier()
+    x0, x1 = cut["x0"], cut["x1"]
 
     sampler = ClockSampler(env.local_rank)
     sampler.start()
@@ -703,6 +742,9 @@ def bench_grid_multi(env, m2s, name, steps, warmup):
         "roofline": roofline_block("k_grid_nearest_run<Raycast, V=2> (slowest rank's slab)", kern_ms, b_alg,
                                    f"k_grid_nearest_dram_bytes_per_launch_{name}", ISSUE_NOTE),
         "phases_ms": phases, "per_rank_phases_ms": rank_table, "single_gpu_same_workload": single,
+        "slab_cuts": {"method": "equal shares of the measured per-slab kernel time of 4 untimed steps, frozen before "
+                                "the warm-up" if balance else "equal widths",
+                      "history": balance_log},
         "assembly": "device: every rank's distance kernel stores its x-slab into rank 0's flat buffer through a "
                     "cudaIpc peer mapping (NVLink), no gather step; the LBVH is built on every rank (replicated: "
                     "a broadcast cannot start before rank 0's build ends, DESIGN.md §6)",
@@ -725,7 +767,7 @@ def run_ours(args):
         name = args.workload or "C5"
         if name not in GRID_WORKLOADS:
             raise SystemExit("multi-GPU runs take a grid workload (C2, C3, C5)")
-        line = bench_grid_multi(env, m2s, name, args.steps, warmup)
+        line = bench_grid_multi(env, m2s, name, args.steps, warmup, balance=not args.equal_slabs)
     else:
         name = args.workload or "C3"
         cpu = not args.no_cpu_baseline
@@ -762,6 +804,7 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=200_000, help="queries per step of the reference arm (C4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_configs")
+    ap.add_argument("--equal-slabs", action="store_true", help="N > 1: equal-width x-slabs instead of balanced cuts")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -156,14 +156,11 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 3, 1ull);
 #endif
     if (__any_sync(full, nseed >= bvh.nt)) {
-        // no neighbour result (first brick planes of a launch): the nearest triangle of a voxel in the middle of the
-        // tile, searched identically by every lane (uniform loads, no divergence), seeds the lanes without one
+        // no neighbour result (first brick planes of a launch): one greedy descent for a voxel in the middle of
+        // the tile, the same on every lane (uniform loads, no divergence); its triangle seeds the lanes without one
+        // (an exact uniform search for that voxel instead measured no better: profiles/r2d, r2e)
         const f3 pc = {__shfl_sync(full, p0.x, 13), __shfl_sync(full, p0.y, 13), __shfl_sync(full, p0.z, 13)};
-#ifdef M2S_GREEDY_SEED
         const uint32_t gl = greedy_leaf(bvh, pc);
-#else
-        const uint32_t gl = nearest_leaf_uniform(bvh, pc, stack);
-#endif
         if (nseed >= bvh.nt) nseed = gl;
     }
     {

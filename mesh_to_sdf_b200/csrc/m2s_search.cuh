@@ -60,73 +60,6 @@ __device__ __forceinline__ uint32_t greedy_leaf(const Bvh& bvh, const f3 p) {
     return (cur & LEAF_BIT) ? (cur & LEAF_INDEX_MASK) : 0u;
 }
 
-// forward declaration (defined below)
-template <bool WANT_SIGN>
-__device__ __forceinline__ float exact_d2_sign(const Bvh& bvh, uint32_t j, bool degen, const f3 p, bool* negative);
-
-// Seed for a tile that has no neighbour result: THE nearest triangle of one point (the tile's middle voxel), found by
-// an ordered depth-first walk that every lane of the warp executes identically (uniform loads, no divergence; the
-// stack is the warp's shared-memory stack, written by lane 0). A greedy descent alone lands on a triangle that can be
-// several triangles away from the nearest one, and in the far field every extra bit of start radius costs hundreds
-// of candidates for all 64 voxels of the tile; the true nearest triangle of the middle voxel is as good a seed as a
-// neighbour tile's result. Only a seed: plain compares, no conservative slack needed.
-__device__ __forceinline__ uint32_t nearest_leaf_uniform(const Bvh& bvh, const f3 p, uint2* stack) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t cur = 0u, bestj = 0u;
-    float best2 = INFINITY;
-    int sp = 0;
-    __syncwarp();
-    for (int guard = 0; guard < 4096; ++guard) {
-        const float4* nd = bvh.nodes + NODE_F4 * (size_t)cur;
-        const float4 l0 = ldg4(nd), l1 = ldg4(nd + 1), l2 = ldg4(nd + 2), l3 = ldg4(nd + 3);
-        const float4 r0 = ldg4(nd + 4), r1 = ldg4(nd + 5), r2 = ldg4(nd + 6), r3 = ldg4(nd + 7);
-        float dl = obb_dist2(p, l0, l1, l2, l3), dr = obb_dist2(p, r0, r1, r2, r3);
-        const uint32_t lref = __float_as_uint(l0.w), rref = __float_as_uint(r0.w);
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const uint32_t ref = side ? rref : lref;
-            if (!(ref & LEAF_BIT)) continue;
-            if ((side ? dr : dl) < best2) {
-                const uint32_t j = ref & LEAF_INDEX_MASK;
-                bool neg;
-                const float d2 = exact_d2_sign<false>(bvh, j, (ref & LEAF_DEGEN_BIT) != 0u, p, &neg);
-                if (d2 < best2) {
-                    best2 = d2;
-                    bestj = j;
-                }
-            }
-            if (side) dr = INFINITY; else dl = INFINITY;  // consumed
-        }
-        const bool go_l = dl < best2, go_r = dr < best2;
-        if (go_l && go_r) {
-            const bool left_first = dl <= dr;
-            if (sp < PKT_STACK) {
-                if (lane == 0) stack[sp] = make_uint2(left_first ? rref : lref, __float_as_uint(left_first ? dr : dl));
-                ++sp;
-                __syncwarp();
-            }
-            cur = left_first ? lref : rref;
-        } else if (go_l) {
-            cur = lref;
-        } else if (go_r) {
-            cur = rref;
-        } else {
-            uint32_t r = TRAVERSAL_DONE;
-            while (sp > 0) {
-                const uint2 e = stack[--sp];
-                if (__uint_as_float(e.y) < best2) {
-                    r = e.x;
-                    break;
-                }
-            }
-            __syncwarp();
-            if (r == TRAVERSAL_DONE) break;
-            cur = r;
-        }
-    }
-    return bestj;
-}
-
 // Exact squared distance from p to triangle slot j (geo.rs:70-138 + Point::dist2, un-fused) and, on request, the
 // sign test of geo.rs:43-56: dot(p - nearest, ab x ac) > 0 is positive.
 template <bool WANT_SIGN>

@@ -63,14 +63,21 @@ wr = num("dram__bytes_write.sum") * scale.get(m["dram__bytes_write.sum"][1], 1)
 lines = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_lines.py"), rep, kern, "30"], capture_output=True, text=True).stdout
 with open(os.path.join(prof, f"{tag}_{kern.split('IL')[0]}_ncu_full.md"), "w") as f:
     f.write(f"# ncu --set full: {r[2][h.index('Kernel Name')][:160] if 'Kernel Name' in h else kern} ({tag})\n\n"
-            f"Captured with `ncu --set full --clock-control none --import-source on -k regex:k_grid_nearest -c 1` around "
-            f"`{os.environ.get('PROFILE_CMD', 'python bench.py')}` (workload C3, the whole 256^3 grid in one launch). "
+            f"Captured with `ncu --set full --clock-control none --import-source on -k regex:{kern} -c 1` around "
+            f"`{os.environ.get('PROFILE_CMD', 'python scripts/ncu_case.py')}` ({os.environ.get('PROFILE_DESC', 'workload C3, the whole 256^3 grid in one launch')}). "
             f"Numbers under a profiler are not bench values.\n\n| metric | value | unit |\n|---|---:|---|\n")
     for k in keys:
         if k in m:
             f.write(f"| `{k}` | {m[k][0]} | {m[k][1]} |\n")
     f.write(f"\nDRAM traffic per launch: read {rd/1e6:.1f} MB + write {wr/1e6:.1f} MB = {(rd+wr)/1e6:.1f} MB "
-            f"(algorithmic bytes: 68.9 MB = 64 MiB output + 1.8 MB mesh).\n\n## Hot source lines (SASS joined with -lineinfo)\n\n```\n{lines}```\n")
-json.dump({"k_grid_nearest_dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": f"profiles/{tag}_*_ncu_full.md"},
-          open(os.path.join(prof, "roofline_traffic.json"), "w"), indent=1)
+            f"({os.environ.get('PROFILE_ALG', 'algorithmic bytes: 68.9 MB = 64 MiB output + 1.8 MB mesh')}).\n\n## Hot source lines (SASS joined with -lineinfo)\n\n```\n{lines}```\n")
+# bench.py reads roofline.traffic from here: one key per (kernel, workload)
+tj = os.path.join(prof, "roofline_traffic.json")
+try:
+    traffic = json.load(open(tj))
+except Exception:
+    traffic = {}
+traffic[os.environ.get("PROFILE_KEY", "k_grid_nearest_dram_bytes_per_launch_C3")] = rd + wr
+traffic.setdefault("sources", {})[os.environ.get("PROFILE_KEY", "k_grid_nearest_dram_bytes_per_launch_C3")] = f"profiles/{tag}_{kern.split('IL')[0]}_ncu_full.md"
+json.dump(traffic, open(tj, "w"), indent=1)
 print("ok", rd, wr)

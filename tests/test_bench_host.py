@@ -82,3 +82,22 @@ def test_shared_host_buffer_world2_gloo():
     for rank, p in enumerate(procs):
         out, err = p.communicate(timeout=300)
         assert p.returncode == 0 and f"rank {rank} ok" in out, err[-2000:]
+
+
+def test_rebalance_moves_cuts_towards_equal_cost():
+    # slab costs measured on C5 at 8 equal slabs (profiles/r2b_c5_slab_balance.log)
+    bounds = bench.slab_bounds(512, 8)
+    times = [6.67, 7.15, 8.42, 8.41, 8.82, 8.02, 6.74, 6.58]
+    new = bench.rebalance(bounds, times)
+    assert new[0][0] == 0 and new[-1][1] == 512
+    assert all(a[1] == b[0] for a, b in zip(new, new[1:])) and all(x1 > x0 for x0, x1 in new)
+    assert all(x0 % 4 == 0 for x0, _ in new)  # whole brick planes
+    dens = np.concatenate([[t / (x1 - x0)] * (x1 - x0) for t, (x0, x1) in zip(times, bounds)])
+    est = [float(dens[x0:x1].sum()) for x0, x1 in new]
+    assert max(est) / (sum(est) / 8) < max(times) / (sum(times) / 8)  # better than the equal split
+    assert max(est) / (sum(est) / 8) < 1.06
+    # degenerate inputs keep a valid partition
+    for t in ([0.0] * 8, [1.0] + [0.0] * 7, [1e-9] * 7 + [5.0]):
+        nb = bench.rebalance(bounds, t)
+        assert nb[0][0] == 0 and nb[-1][1] == 512 and all(x1 - x0 >= 4 for x0, x1 in nb)
+    assert bench.rebalance([(0, 100)], [3.0]) == [(0, 100)]

@@ -605,6 +605,11 @@ class SharedHostBuffer:
         if kind == "shm":
             if env.rank != 0:
                 self.shm = shared_memory.SharedMemory(name=ident)
+                try:  # only the creating rank owns the segment (Python < 3.13 would unlink it from every process)
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
             self.array = np.ndarray((nbytes // 4,), dtype=np.float32, buffer=self.shm.buf)
         else:
             self.mm = np.memmap(ident, dtype=np.float32, mode="r+", shape=(nbytes // 4,))

@@ -394,62 +394,44 @@ k_tri_permute(const float4* __restrict__ rec, const float4* __restrict__ tri_lo,
 }
 
 // K4d: search node of every internal node: per child either the padded box (for big / strongly curved
-// subtrees) or an oriented box fitted to the child's contiguous leaf-order triangle range. One warp
-// per child slot, three strided passes: normal sum -> lateral covariance -> extents.
+// subtrees) or an oriented box fitted to the child's contiguous leaf-order triangle range. A group of G lanes
+// per child slot, three strided passes: normal sum -> lateral covariance -> extents. Most slots are tiny (half of
+// all internal children have two or three triangles), so the first launch gives every slot 8 lanes and leaves the
+// slots with more than SMALL_SLOT_TRIS triangles to a second, warp-per-slot launch over a compacted list.
 #ifndef M2S_OBB_MAX_TRIS
 #define M2S_OBB_MAX_TRIS 512  // one warp fits a slot serially: 4096 left a 128-iteration tail (build 0.45 -> 0.37 ms, same walk)
 #endif
 constexpr uint32_t OBB_MAX_TRIS = M2S_OBB_MAX_TRIS;
+constexpr uint32_t SMALL_SLOT_TRIS = 32;
 
-__global__ void __launch_bounds__(256)
-k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__ tobb, uint32_t nt,
-               int nleaf, const float4* __restrict__ boxes, float4* __restrict__ nodes,
-               const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st, float obb_bias) {
-    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (slot >= 2u * (uint32_t)(nleaf - 1)) return;
-    const float4* bx = boxes + BOX_F4 * (size_t)(slot >> 1) + 2 * (slot & 1u);
-    float4* ch = nodes + NODE_F4 * (size_t)(slot >> 1) + CHILD_F4 * (slot & 1u);
-    const float4 c0 = bx[0], c1 = bx[1];
-    const uint32_t ref = __float_as_uint(c0.w);
-    uint32_t l0, l1;
-    if (ref & LEAF_BIT) {
-        // single-triangle leaf: its oriented box was already fitted by k_tri_permute
-        l0 = ref & LEAF_INDEX_MASK;
-        if (lane < 4) {
-            float4 v = tobb[4 * (size_t)l0 + lane];
-            if (lane == 0) v.w = __uint_as_float(ref);
-            ch[lane] = v;
-        }
-        return;
-    } else {
-        const uint2 r = node_range[ref];
-        l0 = r.x;
-        l1 = r.y;
-    }
-    const uint32_t b = l0, e = min(nt, l1 + 1);
+// fits child slot `slot` with the G lanes of the calling group (G = 8 or 32; all G lanes call it together)
+template <int G>
+__device__ __forceinline__ void fit_child_slot(const uint32_t slot, const uint32_t gl, const unsigned gmask, const uint32_t b,
+                                               const uint32_t e, const float4 c0, const float4 c1, const uint32_t ref,
+                                               const float4* __restrict__ rec_sorted, float4* __restrict__ ch,
+                                               const BuildStatus* __restrict__ st, const float obb_bias) {
     const float3 origin = make_float3(0.5f * (c0.x + c1.x), 0.5f * (c0.y + c1.y), 0.5f * (c0.z + c1.z));
-    const unsigned full = 0xffffffffu;
     bool use_obb = (e - b) <= OBB_MAX_TRIS;
     Frame F;
     Extent E;
     if (use_obb) {
         float3 ns = make_float3(0.f, 0.f, 0.f);
-        for (uint32_t j = b + lane; j < e; j += 32) {
+        for (uint32_t j = b + gl; j < e; j += G) {
             const float4 r2 = rec_sorted[3 * (size_t)j + 2];
             ns.x += r2.y; ns.y += r2.z; ns.z += r2.w;
         }
-        for (int o = 16; o; o >>= 1) {
-            ns.x += __shfl_xor_sync(full, ns.x, o);
-            ns.y += __shfl_xor_sync(full, ns.y, o);
-            ns.z += __shfl_xor_sync(full, ns.z, o);
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) {
+            ns.x += __shfl_xor_sync(gmask, ns.x, o);
+            ns.y += __shfl_xor_sync(gmask, ns.y, o);
+            ns.z += __shfl_xor_sync(gmask, ns.z, o);
         }
         use_obb = frame_from_normal(ns, &F);  // identical on all lanes (xor-butterfly sums are bitwise equal)
     }
     if (use_obb) {
         // lateral covariance of the vertices in the (v, w) plane
         float sa = 0.f, sb = 0.f, saa = 0.f, sab = 0.f, sbb = 0.f, cnt = 0.f;
-        for (uint32_t j = b + lane; j < e; j += 32) {
+        for (uint32_t j = b + gl; j < e; j += G) {
             const float4 r0 = rec_sorted[3 * (size_t)j], r1 = rec_sorted[3 * (size_t)j + 1],
                          r2 = rec_sorted[3 * (size_t)j + 2];
             const float3 p3[3] = {make_float3(r0.x, r0.y, r0.z), make_float3(r0.w, r1.x, r1.y),
@@ -460,26 +442,28 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
                 sa += pa; sb += pb; saa += pa * pa; sab += pa * pb; sbb += pb * pb; cnt += 1.0f;
             }
         }
-        for (int o = 16; o; o >>= 1) {
-            sa += __shfl_xor_sync(full, sa, o); sb += __shfl_xor_sync(full, sb, o);
-            saa += __shfl_xor_sync(full, saa, o); sab += __shfl_xor_sync(full, sab, o);
-            sbb += __shfl_xor_sync(full, sbb, o); cnt += __shfl_xor_sync(full, cnt, o);
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) {
+            sa += __shfl_xor_sync(gmask, sa, o); sb += __shfl_xor_sync(gmask, sb, o);
+            saa += __shfl_xor_sync(gmask, saa, o); sab += __shfl_xor_sync(gmask, sab, o);
+            sbb += __shfl_xor_sync(gmask, sbb, o); cnt += __shfl_xor_sync(gmask, cnt, o);
         }
         const float inv = 1.0f / fmaxf(cnt, 1.0f);
         const float ma = sa * inv, mb = sb * inv;
         frame_align(&F, saa * inv - ma * ma, sab * inv - ma * mb, sbb * inv - mb * mb);
         E.reset();
-        for (uint32_t j = b + lane; j < e; j += 32) {
+        for (uint32_t j = b + gl; j < e; j += G) {
             const float4 r0 = rec_sorted[3 * (size_t)j], r1 = rec_sorted[3 * (size_t)j + 1],
                          r2 = rec_sorted[3 * (size_t)j + 2];
             E.add(F, f3sub(make_float3(r0.x, r0.y, r0.z), origin));
             E.add(F, f3sub(make_float3(r0.w, r1.x, r1.y), origin));
             E.add(F, f3sub(make_float3(r1.z, r1.w, r2.x), origin));
         }
-        for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1)
             for (int k = 0; k < 3; ++k) {
-                E.lo[k] = fminf(E.lo[k], __shfl_xor_sync(full, E.lo[k], o));
-                E.hi[k] = fmaxf(E.hi[k], __shfl_xor_sync(full, E.hi[k], o));
+                E.lo[k] = fminf(E.lo[k], __shfl_xor_sync(gmask, E.lo[k], o));
+                E.hi[k] = fmaxf(E.hi[k], __shfl_xor_sync(gmask, E.hi[k], o));
             }
         // keep the oriented box only where it is the smaller volume (top-level, curved subtrees are
         // better served by the axis-aligned box, which is also cheaper to test)
@@ -487,7 +471,7 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
         const float va = (c1.x - c0.x) * (c1.y - c0.y) * (c1.z - c0.z);
         use_obb = vo > 0.0f && isfinite(vo) && vo <= obb_bias * va;  // NaN / overflowed fits fall back to the padded box
     }
-    if (lane == 0) {
+    if (gl == 0) {
         if (use_obb) {
             write_obb(ch, origin, F, E, scene_mag(st), __uint_as_float(ref));
         } else {
@@ -499,6 +483,59 @@ k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__
             ch[2] = make_float4(0.f, 1.f, 0.f, fmaxf(c1.y - origin.y, origin.y - c0.y) + slack);
             ch[3] = make_float4(0.f, 0.f, 1.f, fmaxf(c1.z - origin.z, origin.z - c0.z) + slack);
         }
+    }
+    (void)slot;
+}
+
+// first launch: 8 lanes per child slot; leaves copy their triangle's box, small subtrees are fitted here, the
+// others are listed for k_search_nodes_big
+__global__ void __launch_bounds__(256)
+k_search_nodes(const float4* __restrict__ rec_sorted, const float4* __restrict__ tobb, uint32_t nt,
+               int nleaf, const float4* __restrict__ boxes, float4* __restrict__ nodes,
+               const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st, float obb_bias,
+               uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
+    constexpr int G = 8;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t slot = tid / G, gl = threadIdx.x & (G - 1);
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
+    if (slot >= 2u * (uint32_t)(nleaf - 1)) return;  // whole groups leave together (256 % G == 0)
+    const float4* bx = boxes + BOX_F4 * (size_t)(slot >> 1) + 2 * (slot & 1u);
+    float4* ch = nodes + NODE_F4 * (size_t)(slot >> 1) + CHILD_F4 * (slot & 1u);
+    const float4 c0 = bx[0], c1 = bx[1];
+    const uint32_t ref = __float_as_uint(c0.w);
+    if (ref & LEAF_BIT) {
+        // single-triangle leaf: its oriented box was already fitted by k_tri_permute
+        if (gl < 4) {
+            float4 v = tobb[4 * (size_t)(ref & LEAF_INDEX_MASK) + gl];
+            if (gl == 0) v.w = __uint_as_float(ref);
+            ch[gl] = v;
+        }
+        return;
+    }
+    const uint2 r = node_range[ref];
+    const uint32_t b = r.x, e = min(nt, r.y + 1);
+    if (e - b > SMALL_SLOT_TRIS) {
+        if (gl == 0) big_list[atomicAdd(big_count, 1u)] = slot;
+        return;
+    }
+    fit_child_slot<G>(slot, gl, gmask, b, e, c0, c1, ref, rec_sorted, ch, st, obb_bias);
+}
+
+// second launch: one warp per listed slot (subtrees of more than SMALL_SLOT_TRIS triangles)
+__global__ void __launch_bounds__(256)
+k_search_nodes_big(const float4* __restrict__ rec_sorted, uint32_t nt, const float4* __restrict__ boxes,
+                   float4* __restrict__ nodes, const uint2* __restrict__ node_range, const BuildStatus* __restrict__ st,
+                   float obb_bias, const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_count) {
+    const uint32_t n = *big_count, lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const uint32_t slot = big_list[i];
+        const float4* bx = boxes + BOX_F4 * (size_t)(slot >> 1) + 2 * (slot & 1u);
+        float4* ch = nodes + NODE_F4 * (size_t)(slot >> 1) + CHILD_F4 * (slot & 1u);
+        const float4 c0 = bx[0], c1 = bx[1];
+        const uint32_t ref = __float_as_uint(c0.w);
+        const uint2 r = node_range[ref];
+        fit_child_slot<32>(slot, lane, 0xffffffffu, r.x, min(nt, r.y + 1), c0, c1, ref, rec_sorted, ch, st, obb_bias);
     }
 }
 
@@ -743,9 +780,18 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
                                                      d.vals_out.as<uint32_t>(), (int)nleaf,
                                                      m.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                      d.node_parent.as<uint32_t>(), d.node_flag.as<uint32_t>());
-        k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 32, bs), bs, 0, s>>>(
+        // child-slot boxes: small subtrees with 8 lanes each, the rest through a compacted list with a warp each
+        CK(d.slot_list.ensure((size_t)nleaf * 2 * 4));
+        CK(d.slot_count.ensure(4));
+        CK(cudaMemsetAsync(d.slot_count.p, 0, 4, s));
+        k_search_nodes<<<blocks_for((uint64_t)2 * (nleaf - 1) * 8, bs), bs, 0, s>>>(
             m.rec_sorted.as<float4>(), d.tobb.as<float4>(), (uint32_t)nt, (int)nleaf, m.boxes.as<float4>(),
-            m.nodes.as<float4>(), m.node_range.as<uint2>(), st, 1.0f);
+            m.nodes.as<float4>(), m.node_range.as<uint2>(), st, 1.0f, d.slot_list.as<uint32_t>(),
+            d.slot_count.as<uint32_t>());
+        k_search_nodes_big<<<d.sm_count * 8, bs, 0, s>>>(
+            m.rec_sorted.as<float4>(), (uint32_t)nt, m.boxes.as<float4>(), m.nodes.as<float4>(),
+            m.node_range.as<uint2>(), st, 1.0f, d.slot_list.as<uint32_t>(), d.slot_count.as<uint32_t>());
+        d.launches++;
         d.launches += 3;
     } else {
         k_single_root<<<1, 32, 0, s>>>(d.tobb.as<float4>(), d.tri_lo.as<float4>(), d.tri_hi.as<float4>(),

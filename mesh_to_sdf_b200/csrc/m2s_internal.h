@@ -150,6 +150,7 @@ struct Device {
     // build scratch (dead after launch_build)
     DevBuf rec_orig, tobb, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
     DevBuf leaf_parent, node_parent, node_flag;
+    DevBuf slot_list, slot_count; // child slots whose box is fitted by a whole warp (k_search_nodes_big)
     MeshDev scratch;              // the mesh of the one-shot entry points
     DevBuf call_status;           // per-call BuildStatus (mesh block + query bounds + this call's flags)
     DevBuf rows[3], big_list, big_count;

@@ -181,7 +181,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_ready(self, timeout: float = 8.0):
+        """nvidia-smi takes a second or two to deliver its first sample on an 8-GPU box: wait for it, so that a
+        short timed region is not left without samples."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Start of the timed region: only samples from here on are reported."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -193,7 +204,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        timed = [l for t, l in self.lines if t >= t_mark] or [l for _, l in self.lines[-3:]]
+        for l in timed:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -368,7 +381,8 @@ class Env:
         return out
 
 
-def timed_device_steps(env, ctx, step, steps, warmup, phase_keys=("build_ms", "sign_ms", "seed_ms", "dist_ms")):
+def timed_device_steps(env, ctx, step, steps, warmup, phase_keys=("build_ms", "sign_ms", "seed_ms", "dist_ms"),
+                       sampler=None):
     """W untimed + K timed steps of `step()` (enqueue only) with an L2 flush before each, CUDA events on the launching
     stream. Returns (sum of step ms [max over ranks], mean kernel ms [max over ranks], phases of this rank, launches)."""
     torch = env.torch
@@ -376,7 +390,11 @@ def timed_device_steps(env, ctx, step, steps, warmup, phase_keys=("build_ms", "s
         env.flush.fill_(1)
         step()
     ctx.synchronize()
+    if sampler is not None:
+        sampler.wait_ready()
     env.barrier()
+    if sampler is not None:
+        sampler.mark()
     launches0 = ctx.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     phases = {k: 0.0 for k in phase_keys}
@@ -444,7 +462,7 @@ def bench_grid_single(env, m2s, name, steps, warmup, want_cpu, cpu_planes, want_
 
     sampler = ClockSampler(env.local_rank)
     sampler.start()
-    total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup)
+    total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup, sampler=sampler)
     clocks = sampler.stop()
     value = cells * steps / (total_ms * 1e-3) / 1e6
     del d_out
@@ -648,6 +666,8 @@ def bench_grid_multi(env, m2s, name, steps, warmup, balance=True):
     dist.broadcast_object_list(box, src=0)
     mapped = base if rank == 0 else ctx.ipc_open(box[0])
     cut = {"x0": bounds[rank][0], "x1": bounds[rank][1]}
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
 
     def step_device():
         ctx.grid_sdf_device(d_verts.data_ptr(), len(verts), d_tris.data_ptr(), len(tris), grid, sign, cut["x0"],
@@ -669,9 +689,7 @@ def bench_grid_multi(env, m2s, name, steps, warmup, balance=True):
         env.barrier()
     x0, x1 = cut["x0"], cut["x1"]
 
-    sampler = ClockSampler(env.local_rank)
-    sampler.start()
-    total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup)
+    total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup, sampler=sampler)
     clocks = sampler.stop()
     value = cells * steps / (total_ms * 1e-3) / 1e6
     rank_table = env.gather_list({"rank": rank, "x": [x0, x1], **{k: round(v, 4) for k, v in phases.items()}})

@@ -225,6 +225,7 @@ cudaError_t enqueue_mesh_pull(Device& d, MeshDev& m, const Device& sd, const Mes
     m.nv = src.nv;
     m.nt = nt;
     m.nodes_il_mag = -1.0f;
+    m.bins_built = false;
     if (nt == 0) return cudaSuccess;
     const size_t n_nodes = src.bvh.n_nodes;
     struct Item { DevBuf* dst; const DevBuf* s; size_t bytes; };
@@ -997,6 +998,10 @@ m2s_status m2s_set_option(m2s_ctx* ctx, int option, int64_t value) {
         case M2S_OPT_COPY_THREADS:
             if (value < 1 || value > 64) return fail(ctx, M2S_EINVAL, "copy threads out of range");
             ctx->copy_threads = (int)value;
+            return M2S_OK;
+        case M2S_OPT_RAY_BINS:
+            if (value != 0 && value != 1) return fail(ctx, M2S_EINVAL, "ray bins: 0 or 1");
+            for (int i = 0; i < ctx->n_devices; ++i) ctx->dev[i].no_ray_bins = value == 0;
             return M2S_OK;
         default:
             return fail(ctx, M2S_EINVAL, "unknown option");

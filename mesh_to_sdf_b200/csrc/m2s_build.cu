@@ -5,8 +5,11 @@
 // (mesh_to_sdf/src/generate/grid.rs:95-111, generic/bvh.rs:62-74, generic/rtree_bvh.rs:108-116) and
 // rstar::RTree::bulk_load (generic/rtree.rs:111, generic/rtree_bvh.rs:118). Leaf boxes are the
 // reference's padded triangle boxes (geo::triangle_bounding_box, src/geo.rs:4-22).
+#include <algorithm>
+
 #include <cuda/atomic>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "m2s_geom.cuh"
 #include "m2s_internal.h"
@@ -60,11 +63,13 @@ void PinBuf::release() {
 }
 
 void MeshDev::release() {
-    DevBuf* bufs[] = {&rec_sorted, &tri_id_sorted, &nodes, &nodes_il, &boxes, &status, &node_range};
+    DevBuf* bufs[] = {&rec_sorted, &tri_id_sorted, &nodes, &nodes_il, &boxes, &status, &node_range,
+                      &bin_offsets, &bin_cursor, &bin_items, &bin_big, &bin_meta};
     for (DevBuf* b : bufs) b->release();
     bvh = Bvh{};
     nv = nt = 0;
     nodes_il_mag = -1.0f;
+    bins_built = false;
 }
 
 namespace {
@@ -569,6 +574,83 @@ k_nodes_interleave(const float4* __restrict__ nodes, uint32_t n_nodes, float4* _
     }
 }
 
+// ---- ray bins (see RayBins, m2s_internal.h) -----------------------------------------------------------------------
+// cell of an in-plane coordinate: monotone in v (subtract, multiply by a positive constant, floor), so
+// lo <= v <= hi  =>  cell(lo) <= cell(v) <= cell(hi): a query inside a triangle's padded box is inside its cell range
+__device__ __forceinline__ uint32_t raybin_cell(float v, float lo, float inv, uint32_t R) {
+    const float c = floorf((v - lo) * inv);
+    if (!(c > 0.0f)) return 0u;
+    return c >= (float)R ? R - 1u : (uint32_t)c;
+}
+
+struct BinRange {
+    uint32_t j0, j1, k0, k1;
+};
+
+// padded box of leaf-order triangle t in the projection of `axis`: cells [j0, j1] x [k0, k1]
+__device__ __forceinline__ BinRange raybin_range(const float4* __restrict__ rec, uint32_t t, int axis,
+                                                 const BuildStatus* __restrict__ st, uint32_t R) {
+    const float4 r0 = rec[3 * (size_t)t], r1 = rec[3 * (size_t)t + 1], r2 = rec[3 * (size_t)t + 2];
+    const float a[3] = {r0.x, r0.y, r0.z}, b[3] = {r0.w, r1.x, r1.y}, c[3] = {r1.z, r1.w, r2.x};
+    const int iy = (axis + 1) % 3, iz = (axis + 2) % 3;
+    const float EPS = 0.0001f;  // geo.rs:5,20-21
+    BinRange g;
+    {
+        const float lo = ord2f(st->lo[iy]), hi = ord2f(st->hi[iy]);
+        const float inv = hi > lo ? (float)R / (hi - lo) : 0.0f;
+        g.j0 = raybin_cell(fsub(fminf(a[iy], fminf(b[iy], c[iy])), EPS), lo, inv, R);
+        g.j1 = raybin_cell(fadd(fmaxf(a[iy], fmaxf(b[iy], c[iy])), EPS), lo, inv, R);
+    }
+    {
+        const float lo = ord2f(st->lo[iz]), hi = ord2f(st->hi[iz]);
+        const float inv = hi > lo ? (float)R / (hi - lo) : 0.0f;
+        g.k0 = raybin_cell(fsub(fminf(a[iz], fminf(b[iz], c[iz])), EPS), lo, inv, R);
+        g.k1 = raybin_cell(fadd(fmaxf(a[iz], fmaxf(b[iz], c[iz])), EPS), lo, inv, R);
+    }
+    return g;
+}
+
+// pass 0: count the items of every cell, list the big triangles; pass 1: scatter the items
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_raybins(const float4* __restrict__ rec, uint32_t nt, const BuildStatus* __restrict__ st, uint32_t R,
+          uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ items,
+          uint32_t* __restrict__ big, uint32_t* __restrict__ meta, uint32_t capacity) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    if (PASS == 1 && meta[4] == 0u) return;  // over budget: the queries walk the box tree instead
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis) {
+        const BinRange g = raybin_range(rec, t, axis, st, R);
+        const uint32_t ncell = (g.j1 - g.j0 + 1u) * (g.k1 - g.k0 + 1u);
+        if (ncell > RAYBIN_BIG_CELLS) {
+            if (PASS == 0) {
+                const uint32_t i = atomicAdd(meta + axis, 1u);
+                if (i < RAYBIN_MAX_BIG) big[axis * RAYBIN_MAX_BIG + i] = t;
+            }
+            continue;
+        }
+        uint32_t* cnt = counts + (size_t)axis * R * R;
+        for (uint32_t k = g.k0; k <= g.k1; ++k)
+            for (uint32_t j = g.j0; j <= g.j1; ++j) {
+                const uint32_t cell = k * R + j;
+                const uint32_t i = atomicAdd(cnt + cell, 1u);
+                if (PASS == 1) {
+                    const uint32_t at = offsets[(size_t)axis * R * R + cell] + i;
+                    if (at < capacity) items[at] = t;
+                }
+            }
+        if (PASS == 0) atomicAdd(meta + 3, ncell);
+    }
+}
+
+// after the count pass: do the totals fit the budgets?
+__global__ void k_raybins_verdict(uint32_t* meta, uint32_t capacity) {
+    if (threadIdx.x == 0)
+        meta[4] = (meta[0] <= RAYBIN_MAX_BIG && meta[1] <= RAYBIN_MAX_BIG && meta[2] <= RAYBIN_MAX_BIG &&
+                   meta[3] <= capacity) ? 1u : 0u;
+}
+
 // Karras 2012 delta over the leaf keys (leaf l = sorted triangle l; equal keys are ordered by index).
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int nleaf, int i, int j) {
     if (j < 0 || j >= nleaf) return -1;
@@ -727,6 +809,7 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
     m.nv = nv;
     m.nt = nt;
     m.nodes_il_mag = -1.0f;
+    m.bins_built = false;
     if (nt == 0) return cudaSuccess;
     CK(launch_mesh_status_reset(d, m));
     BuildStatus* st = m.status.as<BuildStatus>();
@@ -819,6 +902,45 @@ cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool f
         m.nodes.as<float4>(), m.bvh.n_nodes, m.nodes_il.as<float4>(), d.call_status.as<BuildStatus>(), mag_key);
     d.launches++;
     m.nodes_il_mag = force ? -1.0f : mag_key;
+    return cudaGetLastError();
+}
+
+// Ray bins of a built mesh (RayBins, m2s_internal.h): count -> verdict -> exclusive scan -> scatter, all enqueued.
+cudaError_t launch_ray_bins(Device& d, MeshDev& m) {
+    if (m.bins_built || m.nt == 0) return cudaSuccess;
+    cudaStream_t s = d.stream;
+    const uint32_t nt = (uint32_t)m.nt;
+    // about one triangle per cell of a projection: R = 2^round(log2(sqrt(nt))), 16 .. 2048
+    uint32_t R = 16;
+    while (R < 2048u && (double)R * R * 2.0 < (double)nt) R <<= 1;
+    const size_t cells = (size_t)3 * R * R;
+    const uint64_t cap64 = (uint64_t)RAYBIN_ITEMS_PER_TRI * 3u * nt + 1024u;
+    const uint32_t capacity = (uint32_t)std::min<uint64_t>(cap64, 0xfffffff0ull);
+    CK(m.bin_offsets.ensure((cells + 1) * 4));
+    CK(m.bin_cursor.ensure((cells + 1) * 4));
+    CK(m.bin_items.ensure((size_t)capacity * 4));
+    CK(m.bin_big.ensure((size_t)3 * RAYBIN_MAX_BIG * 4));
+    CK(m.bin_meta.ensure(32));
+    CK(cudaMemsetAsync(m.bin_cursor.p, 0, (cells + 1) * 4, s));
+    CK(cudaMemsetAsync(m.bin_meta.p, 0, 32, s));
+    const float4* rec = m.rec_sorted.as<float4>();
+    const BuildStatus* st = m.status.as<BuildStatus>();
+    uint32_t* cursor = m.bin_cursor.as<uint32_t>();
+    uint32_t* offsets = m.bin_offsets.as<uint32_t>();
+    uint32_t* meta = m.bin_meta.as<uint32_t>();
+    k_raybins<0><<<blocks_for(nt, 256), 256, 0, s>>>(rec, nt, st, R, cursor, nullptr, nullptr, m.bin_big.as<uint32_t>(),
+                                                     meta, capacity);
+    k_raybins_verdict<<<1, 32, 0, s>>>(meta, capacity);
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cursor, offsets, (int)(cells + 1), s));
+    CK(d.cub_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceScan::ExclusiveSum(d.cub_tmp.p, tmp_bytes, cursor, offsets, (int)(cells + 1), s));
+    CK(cudaMemsetAsync(m.bin_cursor.p, 0, (cells + 1) * 4, s));
+    k_raybins<1><<<blocks_for(nt, 256), 256, 0, s>>>(rec, nt, st, R, cursor, offsets, m.bin_items.as<uint32_t>(),
+                                                     m.bin_big.as<uint32_t>(), meta, capacity);
+    d.launches += 5;  // two bin passes, the verdict, the scan's two kernels
+    m.bvh.bins = RayBins{R, offsets, m.bin_items.as<uint32_t>(), m.bin_big.as<uint32_t>(), meta, st};
+    m.bins_built = true;
     return cudaGetLastError();
 }
 

@@ -55,6 +55,24 @@ struct BuildStatus {
 };
 static_assert(sizeof(BuildStatus) == 64, "BuildStatus must be 64 bytes");
 
+// Ray bins (scattered queries, Raycast sign rules): per axis A a uniform R x R grid over the two other coordinates
+// of the mesh's bounds; a cell lists the triangles whose PADDED box (geo.rs:4-22, the bvh crate's filter) overlaps it
+// in that projection. The axis-aligned ray of a query only has to test the triangles of its own cell - what
+// bvh.traverse returns for that ray, found without a tree walk. Triangles that cover more than RAYBIN_BIG_CELLS cells
+// go to a short per-axis list every query scans. `ok` == 0 (too many items / big triangles for the budgets: a mesh of
+// huge overlapping triangles) makes the query kernel fall back to the packet walk of the box tree.
+constexpr uint32_t RAYBIN_BIG_CELLS = 64;
+constexpr uint32_t RAYBIN_MAX_BIG = 256;       // per axis
+constexpr uint32_t RAYBIN_ITEMS_PER_TRI = 12;  // item capacity per axis = this x nt
+struct RayBins {
+    uint32_t R;               // cells per in-plane axis (power of two)
+    const uint32_t* offsets;  // [3][R*R] + 1: exclusive prefix of the cell counts (axis-major, cell = k * R + j)
+    const uint32_t* items;    // leaf-order triangle slots
+    const uint32_t* big;      // [3][RAYBIN_MAX_BIG]
+    const uint32_t* meta;     // [0..2] big count per axis, [3] total items, [4] ok flag
+    const BuildStatus* mesh;  // the mesh's bounds (lo / hi of the padded boxes)
+};
+
 struct Bvh {
     const float4* rec;        // leaf-order triangle records
     const float4* boxes;      // box nodes (ray walks)
@@ -65,6 +83,7 @@ struct Bvh {
     uint32_t n_nodes;         // internal nodes (>= 1 when nt >= 1)
     unsigned long long* stats; // optional traversal counters (-DM2S_STATS_BUILD + M2S_STATS=1): nodes, leaves, tiles
     const uint2* node_range;   // per internal node: first / last leaf (box fitting, diagnostics)
+    RayBins bins;              // valid after launch_ray_bins (point calls with a Raycast sign rule)
 };
 
 struct GridParams {
@@ -131,6 +150,8 @@ struct PinBuf {
 // of the one-shot entry points, rebuilt per call) or by an m2s_mesh handle (built once, queried many times).
 struct MeshDev {
     DevBuf rec_sorted, tri_id_sorted, nodes, nodes_il, boxes, status, node_range;
+    DevBuf bin_offsets, bin_cursor, bin_items, bin_big, bin_meta;  // ray bins, built at the first point call that needs them
+    bool bins_built = false;
     Bvh bvh{};
     uint64_t nv = 0, nt = 0;
     float nodes_il_mag = -1.0f;  // magnitude key the interleaved nodes were last written for (< 0: stale)
@@ -156,6 +177,7 @@ struct Device {
     DevBuf rows[3], big_list, big_count;
     DevBuf stats;                 // traversal counters (stats builds only)
     bool want_stats = false;
+    bool no_ray_bins = false;     // M2S_OPT_RAY_BINS = 0: ray parities always through the box tree (tests, A/B)
     DevBuf tile_slot;             // per-tile nearest-triangle slots published by the distance kernel
     DevBuf progress;              // per brick plane completion counters (pipelined host copies)
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
@@ -199,6 +221,7 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
                          cudaEvent_t after_records = nullptr);
 cudaError_t launch_nodes_interleave(Device& d, MeshDev& m, float mag_key, bool force);
 cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq);
+cudaError_t launch_ray_bins(Device& d, MeshDev& m);  // no-op when the mesh already has them
 
 // rec: triangle records in any order (every triangle toggles its own rows)
 cudaError_t launch_grid_rows(Device& d, const float4* rec, uint32_t nt, const GridParams& g, RowBits* rb, cudaStream_t stream);

@@ -118,6 +118,77 @@ __device__ __forceinline__ uint32_t ray_parities_packet(const Bvh& bvh, const f3
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Ray parities through the ray bins (RayBins, m2s_internal.h): per axis the query looks up the cell of its two
+// in-plane coordinates and tests the triangles listed there - exactly the triangles whose padded box its ray can
+// touch (plus the few big ones) - with the same box filter and the same geo.rs:165-216 arithmetic as the packet walk
+// above, so both give the same parities. One lane per query; no tree, no stack, ~5 candidates per axis on a mesh
+// whose triangles are about a cell wide.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ord2f_b(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+template <int AXIS>
+__device__ __forceinline__ uint32_t ray_hit_padded(const Bvh& bvh, uint32_t t, const f3 o) {
+    const float4 r0 = ldg4(bvh.rec + 3 * (size_t)t), r1 = ldg4(bvh.rec + 3 * (size_t)t + 1),
+                 r2 = ldg4(bvh.rec + 3 * (size_t)t + 2);
+    const f3 a = {r0.x, r0.y, r0.z}, b = {r0.w, r1.x, r1.y}, c = {r1.z, r1.w, r2.x};
+    // the padded box of geo.rs:4-22, as the refit wrote it into the box tree (fsub / fadd of 1e-4 on min / max)
+    const float EPS = 0.0001f;
+    const float4 lo = make_float4(fsub(fminf(a.x, fminf(b.x, c.x)), EPS), fsub(fminf(a.y, fminf(b.y, c.y)), EPS),
+                                  fsub(fminf(a.z, fminf(b.z, c.z)), EPS), 0.f);
+    const float4 hi = make_float4(fadd(fmaxf(a.x, fmaxf(b.x, c.x)), EPS), fadd(fmaxf(a.y, fmaxf(b.y, c.y)), EPS),
+                                  fadd(fmaxf(a.z, fmaxf(b.z, c.z)), EPS), 0.f);
+    if (!(ray_box_mask<3>(o, lo, hi) & (1u << AXIS))) return 0u;
+    float t_hit;
+    return ray_aligned<AXIS>(o, a, b, c, &t_hit) ? (1u << AXIS) : 0u;
+}
+
+template <int AXIS>
+__device__ __forceinline__ uint32_t ray_parity_bins_axis(const Bvh& bvh, const f3 o, const bool valid) {
+    const RayBins& B = bvh.bins;
+    constexpr int IY = (AXIS + 1) % 3, IZ = (AXIS + 2) % 3;
+    const float oc[3] = {o.x, o.y, o.z};
+    const float lo_y = ord2f_b(B.mesh->lo[IY]), hi_y = ord2f_b(B.mesh->hi[IY]);
+    const float lo_z = ord2f_b(B.mesh->lo[IZ]), hi_z = ord2f_b(B.mesh->hi[IZ]);
+    uint32_t parity = 0u;
+    // outside the mesh's (padded) bounds in the projection: the ray touches no box
+    const bool in = valid && oc[IY] >= lo_y && oc[IY] <= hi_y && oc[IZ] >= lo_z && oc[IZ] <= hi_z;
+    uint32_t beg = 0u, end = 0u;
+    if (in) {
+        const float inv_y = hi_y > lo_y ? (float)B.R / (hi_y - lo_y) : 0.0f;
+        const float inv_z = hi_z > lo_z ? (float)B.R / (hi_z - lo_z) : 0.0f;
+        const float cy = floorf((oc[IY] - lo_y) * inv_y), cz = floorf((oc[IZ] - lo_z) * inv_z);
+        const uint32_t j = !(cy > 0.0f) ? 0u : (cy >= (float)B.R ? B.R - 1u : (uint32_t)cy);
+        const uint32_t k = !(cz > 0.0f) ? 0u : (cz >= (float)B.R ? B.R - 1u : (uint32_t)cz);
+        const uint32_t* off = B.offsets + (size_t)AXIS * B.R * B.R + (size_t)k * B.R + j;
+        beg = off[0];
+        end = off[1];
+    }
+    for (uint32_t i = beg; i < end; ++i) parity ^= ray_hit_padded<AXIS>(bvh, B.items[i], o);
+    const uint32_t nbig = B.meta[AXIS];
+    if (in)
+        for (uint32_t i = 0; i < nbig; ++i) parity ^= ray_hit_padded<AXIS>(bvh, B.big[AXIS * RAYBIN_MAX_BIG + i], o);
+    return parity;
+}
+
+template <int NAX>
+__device__ __forceinline__ uint32_t ray_parities_bins(const Bvh& bvh, const f3 o, const bool valid) {
+    uint32_t parity = ray_parity_bins_axis<0>(bvh, o, valid);
+    if (NAX == 3) {
+        parity |= ray_parity_bins_axis<1>(bvh, o, valid);
+        parity |= ray_parity_bins_axis<2>(bvh, o, valid);
+    }
+    return parity;
+}
+
+// the sign rules' parities: through the bins when the mesh fits their budgets, else the packet walk of the box tree
+template <int NAX>
+__device__ __forceinline__ uint32_t ray_parities(const Bvh& bvh, const f3 o, const bool valid, uint2* stack,
+                                                 int* overflow) {
+    if (bvh.bins.meta != nullptr && bvh.bins.meta[4] != 0u) return ray_parities_bins<NAX>(bvh, o, valid);
+    return ray_parities_packet<NAX>(bvh, o, valid, stack, overflow);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Run kernel for scattered queries: the packet walk of k_grid_nearest_run (m2s_grid.cu) for 32 consecutive
 // Morton-sorted queries per warp - both children of a node per packed-fp32 instruction (interleaved, pre-scaled
 // nodes, FADD.SAT excess), one warp-shared queue of (triangle, query) items for the exact arithmetic. The queries
@@ -322,9 +393,9 @@ k_points_run(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, fl
         }
     }
     if (SIGN == 1) {
-        if (ray_parities_packet<1>(bvh, p, valid, stack, &overflow) & 1u) d = -d;
+        if (ray_parities<1>(bvh, p, valid, stack, &overflow) & 1u) d = -d;
     } else if (SIGN == 3) {
-        if (__popc(ray_parities_packet<3>(bvh, p, valid, stack, &overflow)) > 1) d = -d;
+        if (__popc(ray_parities<3>(bvh, p, valid, stack, &overflow)) > 1) d = -d;
     }
     if (valid) out[orig] = d;
     if (NORMAL && __any_sync(full, nan) && lane == 0) atomicExch(&st->nan_distance, 1);
@@ -355,8 +426,10 @@ cudaError_t launch_points(Device& d, MeshDev& m, uint64_t nq, int mode, int sign
     const uint32_t n = (uint32_t)nq;
     // after sort_queries: the call's scene bounds now include the queries, which only the device knows
     CK(launch_nodes_interleave(d, m, 0.0f, true));
+    if (sign_rule != 0 && !d.no_ray_bins) CK(launch_ray_bins(d, m));
     const unsigned nbr = (unsigned)((nq + 127) / 128);
     Bvh bvh = m.bvh;
+    if (d.no_ray_bins) bvh.bins = RayBins{};
 #ifdef M2S_STATS_BUILD
     bvh.stats = d.want_stats ? d.stats.as<unsigned long long>() : nullptr;
 #endif

@@ -175,3 +175,50 @@ def test_query_order_preserved(m2s, oracle):
     a = m2s.default_context().sdf(verts, tris, q, 3, 0)
     b = m2s.default_context().sdf(verts, tris, q[perm], 3, 0)
     assert np.array_equal(a[perm], b)
+
+
+def _raycast_methods():
+    return [(0, 0), (1, 0), (3, 0)]  # None(Raycast): +X parity; Bvh(Raycast), RtreeBvh: best of three axes
+
+
+def test_ray_bins_equal_the_box_tree_walk_and_the_oracle(m2s, oracle):
+    # the axis-ray parities come from per-axis 2-D triangle bins by default and from the packet walk of the box tree
+    # with M2S_OPT_RAY_BINS = 0: same candidate filter (padded boxes, geo.rs:4-22), same predicates -> same bits
+    rng = np.random.default_rng(11)
+    cases = []
+    verts, tris = synth.bumpy_torus(96, 64)
+    mn, mx = synth.padded_grid_box(verts)
+    cases.append(("torus", verts, tris, synth.splitmix64_points(20000, mn, mx)))
+    # a few big triangles (a box around everything: every one covers far more than 64 cells) + the small ones
+    bmn, bmx = mn - 0.1, mx + 0.1
+    c = np.array([[bmn[0], bmn[1], bmn[2]], [bmx[0], bmn[1], bmn[2]], [bmx[0], bmx[1], bmn[2]], [bmn[0], bmx[1], bmn[2]],
+                  [bmn[0], bmn[1], bmx[2]], [bmx[0], bmn[1], bmx[2]], [bmx[0], bmx[1], bmx[2]], [bmn[0], bmx[1], bmx[2]]],
+                 np.float32)
+    f = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5],
+                  [0, 4, 7], [0, 7, 3]], np.uint32)
+    v2 = np.concatenate([verts, c]).astype(np.float32)
+    t2 = np.concatenate([tris, f + len(verts)]).astype(np.uint32)
+    q2 = synth.splitmix64_points(8000, bmn - 0.2, bmx + 0.2)
+    cases.append(("torus in a box (12 big triangles)", v2, t2, q2))
+    # more big overlapping triangles than the per-axis budget: the library falls back to the tree walk by itself
+    fan_v = (rng.uniform(-1.0, 1.0, (900, 3)) * np.array([3.0, 3.0, 1.0])).astype(np.float32)
+    fan_t = np.arange(900, dtype=np.uint32).reshape(-1, 3)
+    cases.append(("300 big random triangles (over budget)", fan_v, fan_t, synth.splitmix64_points(3000, [-3, -3, -1], [3, 3, 1])))
+    with m2s.Context() as c:
+        for name, v, t, q in cases:
+            for accel, sign in _raycast_methods():
+                c.set_option(m2s.OPT_RAY_BINS, 1)
+                a = c.sdf(v, t, q, accel, sign)
+                c.set_option(m2s.OPT_RAY_BINS, 0)
+                b = c.sdf(v, t, q, accel, sign)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, accel)
+                want = oracle.generate_sdf(v, t, q, accel, sign)
+                assert np.array_equal(a.view(np.uint32), want.view(np.uint32)), (name, accel)
+        # a mesh handle builds its bins once and keeps them
+        c.set_option(m2s.OPT_RAY_BINS, 1)
+        name, v, t, q = cases[1]
+        with c.mesh(v, t) as mesh:
+            first = mesh.sdf(q, 3)
+            again = mesh.sdf(q[::-1].copy(), 3)
+            assert np.array_equal(first.view(np.uint32), again[::-1].view(np.uint32))
+            assert np.array_equal(first.view(np.uint32), oracle.generate_sdf(v, t, q, 3, 0).view(np.uint32))

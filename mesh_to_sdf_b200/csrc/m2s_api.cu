@@ -330,6 +330,86 @@ float* pinned_device_alias(const void* host_ptr, size_t bytes) {
     return static_cast<float*>(a.devicePointer);
 }
 
+CopyPool* ensure_pool(m2s_ctx* ctx) {
+    if (!ctx->pool || ctx->pool->threads() != ctx->copy_threads) {
+        delete ctx->pool;
+        ctx->pool = new CopyPool(ctx->copy_threads);
+    }
+    return ctx->pool;
+}
+
+// Host -> device copies of caller memory. A cudaMemcpyAsync from pageable memory is staged by the driver through its
+// own bounce buffer by the calling thread (measured 11 GB/s: 1.6 ms for the 18 MB mesh of C5); from page-locked memory
+// it is one DMA. Large pageable inputs therefore go through the library's pinned staging buffer: the context's host
+// threads copy 1 MiB chunks into it and each enqueues the DMA of its chunk right away, so the memcpy of one chunk runs
+// beside the DMA of another. `parts` are copied back to back into `stage`.
+constexpr size_t H2D_STAGE_MIN_BYTES = 4u << 20, H2D_CHUNK = 1u << 20;
+struct H2DPart {
+    void* dst;
+    const void* src;
+    size_t bytes;
+};
+bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+cudaError_t upload_inputs(m2s_ctx* ctx, Device& d, PinBuf& stage, const H2DPart* parts, int n_parts) {
+    size_t total = 0;
+    bool pageable = false;
+    for (int i = 0; i < n_parts; ++i) {
+        total += parts[i].bytes;
+        if (parts[i].bytes && !host_is_pinned(parts[i].src)) pageable = true;
+    }
+    if (!pageable || total < H2D_STAGE_MIN_BYTES || ctx->host_path == M2S_HOST_STAGED) {
+        for (int i = 0; i < n_parts; ++i)
+            if (parts[i].bytes) {
+                cudaError_t e = cudaMemcpyAsync(parts[i].dst, parts[i].src, parts[i].bytes, cudaMemcpyHostToDevice, d.stream);
+                if (e != cudaSuccess) return e;
+            }
+        return cudaSuccess;
+    }
+    // the previous call's DMAs out of this buffer have completed: host-buffer calls return synchronised
+    cudaError_t e = stage.ensure(total);
+    if (e != cudaSuccess) return e;
+    struct Chunk {
+        char* dst;
+        const char* src;
+        char* pin;
+        size_t bytes;
+    };
+    std::vector<Chunk> chunks;
+    size_t off = 0;
+    for (int i = 0; i < n_parts; ++i)
+        for (size_t o = 0; o < parts[i].bytes; o += H2D_CHUNK) {
+            const size_t n = std::min(H2D_CHUNK, parts[i].bytes - o);
+            chunks.push_back(Chunk{static_cast<char*>(parts[i].dst) + o, static_cast<const char*>(parts[i].src) + o,
+                                   static_cast<char*>(stage.p) + off, n});
+            off += n;
+        }
+    std::atomic<int> failed{0};
+    const int ordinal = d.ordinal;
+    cudaStream_t stream = d.stream;
+    std::function<void(int)> job = [&](int k) {
+        const Chunk& c = chunks[(size_t)k];
+        std::memcpy(c.pin, c.src, c.bytes);
+        if (cudaSetDevice(ordinal) != cudaSuccess ||
+            cudaMemcpyAsync(c.dst, c.pin, c.bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess)
+            failed.store(1);
+    };
+    CopyPool* pool = ensure_pool(ctx);
+    pool->start(&job, (int)chunks.size());
+    pool->wait();
+    if (failed.load()) {
+        const cudaError_t err = cudaGetLastError();
+        return err != cudaSuccess ? err : cudaErrorUnknown;
+    }
+    return cudaSuccess;
+}
+
 // Upload (host inputs) or fan out (device inputs on the first device) the mesh of a call to every device that takes
 // part: the first device gets it from the caller, the others pull it from the first device over NVLink when peer
 // access exists (one PCIe upload instead of n), else from the host again.
@@ -348,8 +428,8 @@ m2s_status stage_mesh_inputs(m2s_ctx* ctx, int nd, bool host_inputs, const float
     if (host_inputs) {
         CU(ctx, d0.verts.ensure(nv * 12));
         CU(ctx, d0.tris.ensure(nt * 12));
-        CU(ctx, cudaMemcpyAsync(d0.verts.p, verts, nv * 12, cudaMemcpyHostToDevice, d0.stream));
-        CU(ctx, cudaMemcpyAsync(d0.tris.p, tris, nt * 12, cudaMemcpyHostToDevice, d0.stream));
+        const H2DPart parts[2] = {{d0.verts.p, verts, nv * 12}, {d0.tris.p, tris, nt * 12}};
+        CU(ctx, upload_inputs(ctx, d0, d0.in_mesh, parts, 2));
         in_dev[0] = MeshInputs{d0.verts.as<float>(), d0.tris.as<uint32_t>()};
     } else {
         in_dev[0] = MeshInputs{verts, tris};
@@ -427,6 +507,61 @@ void advise_huge_pages(void* p, size_t bytes) {
 #endif
 }
 
+// ---- slab cuts over the devices of a context ---------------------------------------------------------------------
+// cuts[i] .. cuts[i + 1] = the x range of device i
+std::vector<uint64_t> slab_cuts(m2s_ctx* ctx, int nd, uint64_t xa, uint64_t xb, const GridArgs& ga, uint64_t nt) {
+    SlabBalance& b = ctx->balance;
+    const bool same = b.valid && b.nd == nd && b.xa == xa && b.xb == xb && b.ny == ga.g.ny && b.nz == ga.g.nz && b.nt == nt;
+    if (!(ctx->balance_slabs && same)) {
+        b.cuts.resize((size_t)nd + 1);
+        for (int i = 0; i <= nd; ++i) b.cuts[(size_t)i] = xa + (xb - xa) * (uint64_t)i / (uint64_t)nd;
+    }
+    b.xa = xa; b.xb = xb; b.ny = ga.g.ny; b.nz = ga.g.nz; b.nt = nt; b.nd = nd;
+    b.valid = false;
+    b.pending = nd > 1 && ctx->balance_slabs;
+    return b.cuts;
+}
+
+// Called once the timings of the call that used ctx->balance.cuts are known: the cost per x-plane is taken as
+// uniform inside a slab, the new cuts sit at equal shares of the cumulative cost, on whole brick planes.
+void update_slab_balance(m2s_ctx* ctx) {
+    SlabBalance& b = ctx->balance;
+    if (!b.pending) return;
+    b.pending = false;
+    const int nd = b.nd;
+    std::vector<double> t((size_t)nd);
+    double total = 0.0;
+    for (int i = 0; i < nd; ++i) {
+        const m2s_timings& tm = ctx->dev[i].timings;
+        t[(size_t)i] = std::max(0.0, (double)tm.dist_ms + (double)tm.sign_ms);
+        total += t[(size_t)i];
+    }
+    const uint64_t align = GRID_BRICK_X, span = b.xb - b.xa;
+    if (!(total > 0.0) || !std::isfinite(total) || span < align * (uint64_t)nd) return;  // keep the cuts, not "valid"
+    const double tmax = *std::max_element(t.begin(), t.end()), tmin = *std::min_element(t.begin(), t.end());
+    if (tmax <= 1.03 * tmin) {  // balanced within the noise of the measurement: keep the cuts
+        b.valid = true;
+        return;
+    }
+    std::vector<uint64_t> cuts((size_t)nd + 1);
+    cuts[0] = b.xa;
+    double acc = 0.0;
+    int r = 0;
+    for (int k = 1; k < nd; ++k) {
+        const double want = total * k / nd;
+        while (r < nd - 1 && acc + t[(size_t)r] < want) acc += t[(size_t)r++];
+        const double x0 = (double)b.cuts[(size_t)r], x1 = (double)b.cuts[(size_t)r + 1];
+        double x = x0 + (x1 - x0) * (want - acc) / std::max(t[(size_t)r], 1e-12);
+        x = 0.5 * (x + (double)b.cuts[(size_t)k]);  // damped: one odd measurement moves a cut half-way at most
+        uint64_t xi = b.xa + (uint64_t)std::llround(std::max(0.0, x - (double)b.xa) / (double)align) * align;
+        const uint64_t lo = cuts[(size_t)k - 1] + align, hi = b.xb - align * (uint64_t)(nd - k);
+        cuts[(size_t)k] = std::min(std::max(xi, lo), hi);
+    }
+    cuts[(size_t)nd] = b.xb;
+    b.cuts = cuts;
+    b.valid = true;
+}
+
 constexpr size_t PIPELINE_MIN_BYTES = 4u << 20;  // smaller slabs: one staged copy is cheaper than the flag protocol
 
 // ---- grid call, host destination -------------------------------------------------------------------------------
@@ -465,12 +600,13 @@ m2s_status grid_host(m2s_ctx* ctx, m2s_mesh* handle, const float* verts_xyz, uin
         bool registered;
     };
     std::vector<Slab> slabs(nd);
+    const std::vector<uint64_t> cuts = slab_cuts(ctx, nd, xa, xb, ga, nt);
     for (int i = 0; i < nd; ++i) {
         Device& d = ctx->dev[i];
         Slab& sl = slabs[i];
         sl.g = ga.g;
-        sl.g.x0 = (uint32_t)(xa + span * i / nd);
-        sl.g.x1 = (uint32_t)(xa + span * (i + 1) / nd);
+        sl.g.x0 = (uint32_t)cuts[(size_t)i];
+        sl.g.x1 = (uint32_t)cuts[(size_t)i + 1];
         sl.cells = (uint64_t)(sl.g.x1 - sl.g.x0) * plane;
         sl.host_dst = out + (uint64_t)(sl.g.x0 - xa) * plane;
         sl.stage = nullptr;
@@ -576,11 +712,7 @@ m2s_status grid_host(m2s_ctx* ctx, m2s_mesh* handle, const float* verts_xyz, uin
     };
     const bool pipelined = !chunks.empty();
     if (pipelined) {
-        if (!ctx->pool || ctx->pool->threads() != ctx->copy_threads) {
-            delete ctx->pool;
-            ctx->pool = new CopyPool(ctx->copy_threads);
-        }
-        ctx->pool->start(&job, (int)chunks.size());
+        ensure_pool(ctx)->start(&job, (int)chunks.size());
     }
     m2s_status result = M2S_OK;
     cudaError_t sync_error = cudaSuccess;
@@ -611,6 +743,7 @@ m2s_status grid_host(m2s_ctx* ctx, m2s_mesh* handle, const float* verts_xyz, uin
             d.timings.total_ms += tail;
         }
     }
+    update_slab_balance(ctx);
     return result;
 }
 
@@ -636,6 +769,7 @@ m2s_status grid_device(m2s_ctx* ctx, m2s_mesh* handle, const float* d_verts, uin
         m2s_status s = stage_meshes(ctx, nd, handle, in_dev, nv, nt, raycast, meshes);
         if (s != M2S_OK) return s;
     }
+    const std::vector<uint64_t> cuts = slab_cuts(ctx, nd, xa, xb, ga, nt);
     Device& d0 = ctx->dev[0];
     if (nd > 1) {
         // the destination may still be in use by earlier work on the first device's stream
@@ -646,8 +780,8 @@ m2s_status grid_device(m2s_ctx* ctx, m2s_mesh* handle, const float* d_verts, uin
         Device& d = ctx->dev[i];
         CU(ctx, cudaSetDevice(d.ordinal));
         GridParams g = ga.g;
-        g.x0 = (uint32_t)(xa + span * i / nd);
-        g.x1 = (uint32_t)(xa + span * (i + 1) / nd);
+        g.x0 = (uint32_t)cuts[(size_t)i];
+        g.x1 = (uint32_t)cuts[(size_t)i + 1];
         const uint64_t cells = (uint64_t)(g.x1 - g.x0) * plane;
         float* dst = d_out + (uint64_t)(g.x0 - xa) * plane;
         // peers store their slab straight into the first device's buffer (peer-mapped pointer, NVLink): the
@@ -710,7 +844,8 @@ m2s_status points_call(m2s_ctx* ctx, m2s_mesh* handle, bool host_io, const float
         if (host_io) {
             CU(ctx, d.queries.ensure(n * 12));
             CU(ctx, d.out.ensure(n * 4));
-            CU(ctx, cudaMemcpyAsync(d.queries.p, queries + 3 * q0, n * 12, cudaMemcpyHostToDevice, d.stream));
+            const H2DPart part{d.queries.p, queries + 3 * q0, n * 12};
+            CU(ctx, upload_inputs(ctx, d, d.in_queries, &part, 1));
             dq = d.queries.as<float>();
             target = d.out.as<float>();
         } else if (i == 0) {
@@ -779,6 +914,8 @@ void release_device(Device& d) {
     d.scratch.release();
     d.stage.release();
     d.flags.release();
+    d.in_mesh.release();
+    d.in_queries.release();
     if (d.h_status) cudaFreeHost(d.h_status);
     for (int k = 0; k < 8; ++k)
         if (d.ev[k]) cudaEventDestroy(d.ev[k]);
@@ -999,6 +1136,11 @@ m2s_status m2s_set_option(m2s_ctx* ctx, int option, int64_t value) {
             if (value < 1 || value > 64) return fail(ctx, M2S_EINVAL, "copy threads out of range");
             ctx->copy_threads = (int)value;
             return M2S_OK;
+        case M2S_OPT_BALANCE:
+            if (value != 0 && value != 1) return fail(ctx, M2S_EINVAL, "balance: 0 or 1");
+            ctx->balance_slabs = value != 0;
+            ctx->balance = SlabBalance{};
+            return M2S_OK;
         case M2S_OPT_RAY_BINS:
             if (value != 0 && value != 1) return fail(ctx, M2S_EINVAL, "ray bins: 0 or 1");
             for (int i = 0; i < ctx->n_devices; ++i) ctx->dev[i].no_ray_bins = value == 0;
@@ -1148,6 +1290,7 @@ m2s_status m2s_synchronize(m2s_ctx* ctx) {
             CU(ctx, cudaStreamSynchronize(d.stream));
         }
     }
+    update_slab_balance(ctx);  // the timings of an enqueued multi-device grid call are in now
     return result;
 }
 

@@ -183,6 +183,7 @@ struct Device {
     DevBuf queries, q_sorted, q_perm, q_keys_in, q_keys_out, q_vals_in, out;
     DevBuf post_keys, post_idx, post_mm, post_in, post_pts, post_out;  // post-passes (m2s_post.cu) and their host staging
     PinBuf stage;                 // pinned staging ring: pageable destinations are filled from here by host threads
+    PinBuf in_mesh, in_queries;   // pinned staging of pageable INPUTS (host threads copy chunks in, each followed by its H2D)
     PinBuf flags;                 // mapped completion flags of the pipelined path
     uint32_t epoch = 0;
     BuildStatus* h_status = nullptr;  // pinned
@@ -250,6 +251,17 @@ struct m2s_mesh {
     uint64_t nv = 0, nt = 0;
 };
 
+// Slab cuts of the last multi-device grid call and, once its timings are in, the cuts the next call on the same grid
+// shape will use: equal-width x-slabs are uneven in cost (the slabs through the middle of a mesh do more work), so
+// the cuts move to equal shares of the measured per-slab kernel time. Results do not depend on the cuts.
+struct SlabBalance {
+    uint64_t xa = 0, xb = 0, ny = 0, nz = 0, nt = 0;
+    int nd = 0;
+    std::vector<uint64_t> cuts;  // nd + 1 entries, cuts[0] = xa, cuts[nd] = xb
+    bool valid = false;          // cuts hold a measured split for the key above
+    bool pending = false;        // a call with these cuts is in flight / finished and its timings were not used yet
+};
+
 struct m2s_ctx {
     int n_devices = 0;
     m2s::Device* dev = nullptr;
@@ -257,6 +269,8 @@ struct m2s_ctx {
     int build_mode = M2S_BUILD_REPLICATED;
     int host_path = M2S_HOST_AUTO;
     int copy_threads = 4;
+    bool balance_slabs = true;     // M2S_OPT_BALANCE
+    SlabBalance balance;
     m2s::CopyPool* pool = nullptr;
     std::mutex mu;  // a context serves one call at a time
 };

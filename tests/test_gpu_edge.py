@@ -232,3 +232,34 @@ def test_pinned_destination_is_written_in_place(m2s):
         c.grid_sdf(verts, tris, grid, 0, pinned.numpy())
         assert c.timings()["host_path"] == "staged"
         assert np.array_equal(pinned.numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_multi_device_slab_balance_keeps_the_bits(m2s):
+    # a multi-device context moves its slab cuts to equal shares of the previous call's measured kernel times
+    # (M2S_OPT_BALANCE, default on): the cuts change from call to call on a lopsided grid, the result never does
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    verts, tris = synth.bumpy_torus(96, 64)
+    mn, mx = synth.padded_grid_box(verts)
+    mx = mx.copy()
+    mx[0] += 3.0  # the mesh sits in the low-x third of the box: equal-width slabs are far from equal cost
+    grid = m2s.Grid.from_bounding_box(mn, mx, [160, 48, 40])
+    one = m2s.default_context().grid_sdf(verts, tris, grid, RAYCAST)
+    with m2s.Context([0, 1]) as c2:
+        times = []
+        for _ in range(4):
+            two = c2.grid_sdf(verts, tris, grid, RAYCAST)
+            assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
+            times.append((c2.timings(0)["dist_ms"], c2.timings(1)["dist_ms"]))
+        # the imbalance of the first (equal-width) call shrinks once the cuts follow the measured times
+        ratio = [max(a, b) / max(min(a, b), 1e-6) for a, b in times]
+        assert ratio[-1] < ratio[0] or ratio[0] < 1.15, (times, ratio)
+        c2.set_option(m2s.OPT_BALANCE, 0)
+        assert np.array_equal(one.view(np.uint32), c2.grid_sdf(verts, tris, grid, RAYCAST).view(np.uint32))
+        c2.set_option(m2s.OPT_BALANCE, 1)
+        # a slab of the grid through a handle, twice (the key of the balance includes the x range)
+        with c2.mesh(verts, tris) as mesh:
+            for _ in range(2):
+                part = mesh.grid_sdf(grid, RAYCAST, 16, 120)
+                assert np.array_equal(part.view(np.uint32), one[16 * 48 * 40:120 * 48 * 40].view(np.uint32))

@@ -9,6 +9,7 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -692,7 +693,36 @@ m2s_status grid_host(m2s_ctx* ctx, m2s_mesh* handle, const float* verts_xyz, uin
     std::vector<std::atomic<int>> stream_done(nd);
     for (int i = 0; i < nd; ++i) stream_done[i].store(0);
     std::atomic<int> copy_failed{0};
-    std::function<void(int)> job = [&](int k) {
+    // A fresh destination (the Vec<f32> a facade has just allocated) takes its first-touch page faults in these
+    // threads. They are taken EARLY, while the GPU is still uploading and building: the first tasks populate the
+    // destination 2 MiB at a time (MADV_POPULATE_WRITE leaves present pages and their contents alone, so it cannot
+    // race with a copy), the copies that follow find their pages there.
+    struct Block {
+        char* p;
+        size_t bytes;
+    };
+    std::vector<Block> blocks;
+#ifdef MADV_POPULATE_WRITE
+    static std::atomic<int> populate_ok{1};
+    if (populate_ok.load(std::memory_order_relaxed))
+        for (int i = 0; i < nd; ++i) {
+            if (slabs[i].path != M2S_PATH_PIPELINED) continue;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(slabs[i].host_dst) & ~(uintptr_t)4095;
+            const uintptr_t b = (reinterpret_cast<uintptr_t>(slabs[i].host_dst) + slabs[i].cells * 4 + 4095) & ~(uintptr_t)4095;
+            for (uintptr_t o = a; o < b; o += (2u << 20))
+                blocks.push_back(Block{reinterpret_cast<char*>(o), (size_t)std::min<uintptr_t>(2u << 20, b - o)});
+        }
+#endif
+    const int n_blocks = (int)blocks.size();
+    std::function<void(int)> job = [&](int task) {
+        if (task < n_blocks) {
+#ifdef MADV_POPULATE_WRITE
+            if (madvise(blocks[(size_t)task].p, blocks[(size_t)task].bytes, MADV_POPULATE_WRITE) != 0 && errno == EINVAL)
+                populate_ok.store(0, std::memory_order_relaxed);  // kernel older than 5.14: faults happen in the copies
+#endif
+            return;
+        }
+        const int k = task - n_blocks;
         const Chunk c = chunks[(size_t)k];
         const Slab& sl = slabs[c.dev];
         const volatile uint32_t* flag = static_cast<const volatile uint32_t*>(ctx->dev[c.dev].flags.p) + c.plane;
@@ -712,7 +742,7 @@ m2s_status grid_host(m2s_ctx* ctx, m2s_mesh* handle, const float* verts_xyz, uin
     };
     const bool pipelined = !chunks.empty();
     if (pipelined) {
-        ensure_pool(ctx)->start(&job, (int)chunks.size());
+        ensure_pool(ctx)->start(&job, n_blocks + (int)chunks.size());
     }
     m2s_status result = M2S_OK;
     cudaError_t sync_error = cudaSuccess;
@@ -946,6 +976,14 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
     m2s_ctx* ctx = new (std::nothrow) m2s_ctx();
     if (!ctx) return M2S_EINVAL;
     ctx->n_devices = (int)ids.size();
+    {
+        // host copy threads of the pipelined paths: a fresh destination (the Vec<f32> a facade returns) takes its page
+        // faults inside them. Measured on this pool's hosts (scripts/host_fault_bench.cpp, 64 MiB, huge pages
+        // advised): 4 threads fill 14.9 GB/s, 8 threads 23.8 GB/s; the C3 kernel produces 13.8 GB/s. Half of the
+        // host's threads divided by the visible GPUs (one process per GPU shares the host), 4..8.
+        const int hw = (int)std::thread::hardware_concurrency();
+        ctx->copy_threads = std::min(8, std::max(4, hw / (2 * std::max(1, visible))));
+    }
     ctx->dev = new (std::nothrow) Device[ids.size()];
     if (!ctx->dev) { delete ctx; return M2S_EINVAL; }
     for (size_t i = 0; i < ids.size(); ++i) {

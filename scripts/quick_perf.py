@@ -57,6 +57,12 @@ def run_points(m2s, synth, name, nu, nv, nq, accel, sign, reps=3):
         t = ctx.timings()
         print(f"{name} rep{r}: wall {dt*1e3:.2f} ms | " + " ".join(f"{k}={v:.3f}" if isinstance(v, float) else f"{k}={v}" for k, v in t.items()), flush=True)
     print(f"  neg frac {np.mean(out<0):.4f} checksum {float(np.abs(out[::97]).sum()):.6f}")
+    if os.environ.get("M2S_STATS"):
+        ctx.debug_stats()
+        ctx.sdf(verts, tris, q, accel, sign)
+        st = ctx.debug_stats()
+        if st[2]:
+            print(f"  stats per packet: nodes {st[0] / st[2]:.1f} leaves {st[1] / st[2]:.1f} packets {st[2]}")
 
 
 def main(which):

@@ -90,12 +90,13 @@ typedef enum m2s_host_path_taken {
 typedef enum m2s_option {
     M2S_OPT_BUILD_MODE = 1,  /* multi-device contexts: m2s_build_mode                                           */
     M2S_OPT_HOST_PATH = 2,   /* how pageable host destinations are filled: m2s_host_path                        */
-    M2S_OPT_COPY_THREADS = 3, /* host threads of the pipelined paths (1..64; default 4..8 by host size)                        */
+    M2S_OPT_COPY_THREADS = 3, /* host threads of the pipelined paths (1..64; default 4..8 by host size)         */
     M2S_OPT_RAY_BINS = 4,     /* generate_sdf Raycast sign rules: 1 (default) = axis-ray parities through per-axis
                                  2-D triangle bins, 0 = always through the packet walk of the box tree (same results) */
-    M2S_OPT_BALANCE = 5       /* multi-device contexts: 1 (default) = a grid call on the same grid shape as the previous
+    M2S_OPT_BALANCE = 5,      /* multi-device contexts: 1 (default) = a grid call on the same grid shape as the previous
                                  one cuts its x-slabs at equal shares of that call's measured per-slab kernel time,
                                  0 = always equal-width slabs (same results either way)                              */
+    M2S_OPT_RUN_LENGTH = 6    /* voxels per lane of the grid kernel: 0 (default) = chosen by mesh size, 2 or 4         */
 } m2s_option;
 typedef enum m2s_build_mode {
     M2S_BUILD_REPLICATED = 0, /* every device builds its own LBVH from the mesh (default: measured faster)      */

@@ -60,7 +60,7 @@ class Timings(C.Structure):
 # m2s_host_path_taken (m2s.h): how the result of the last call reached its host destination
 HOST_PATH_NAMES = {0: "device", 1: "zerocopy", 2: "pipelined", 3: "staged", 4: "registered"}
 # m2s_set_option keys / values (m2s.h)
-OPT_BUILD_MODE, OPT_HOST_PATH, OPT_COPY_THREADS, OPT_RAY_BINS, OPT_BALANCE = 1, 2, 3, 4, 5
+OPT_BUILD_MODE, OPT_HOST_PATH, OPT_COPY_THREADS, OPT_RAY_BINS, OPT_BALANCE, OPT_RUN_LENGTH = 1, 2, 3, 4, 5, 6
 BUILD_REPLICATED, BUILD_BROADCAST = 0, 1
 HOST_AUTO, HOST_STAGED, HOST_PIPELINED, HOST_REGISTER = 0, 1, 2, 3
 

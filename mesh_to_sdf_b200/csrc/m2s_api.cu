@@ -1179,6 +1179,10 @@ m2s_status m2s_set_option(m2s_ctx* ctx, int option, int64_t value) {
             ctx->balance_slabs = value != 0;
             ctx->balance = SlabBalance{};
             return M2S_OK;
+        case M2S_OPT_RUN_LENGTH:
+            if (value != 0 && value != 2 && value != 4) return fail(ctx, M2S_EINVAL, "run length: 0, 2 or 4");
+            for (int i = 0; i < ctx->n_devices; ++i) ctx->dev[i].run_v = (uint32_t)value;
+            return M2S_OK;
         case M2S_OPT_RAY_BINS:
             if (value != 0 && value != 1) return fail(ctx, M2S_EINVAL, "ray bins: 0 or 1");
             for (int i = 0; i < ctx->n_devices; ++i) ctx->dev[i].no_ray_bins = value == 0;

@@ -637,10 +637,11 @@ float grid_magnitude(const GridParams& g) {
 uint32_t grid_brick_planes(const GridParams& g) { return cdiv(g.x1 - g.x0, (uint32_t)BX); }
 
 // The distance kernel over the slab [g.x0, g.x1). progress (optional): completion flags per brick plane.
-cudaError_t launch_grid_nearest(Device& d, MeshDev& m, const GridParams& g, int mode, const RowBits* rb, float* d_out,
-                                const Progress* progress) {
+template <int V>
+static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams& g, int mode, const RowBits* rb,
+                                         float* d_out, const Progress* progress) {
     cudaStream_t s = d.stream;
-    constexpr uint32_t V = 2u, BZR = 4u * V;
+    constexpr uint32_t BZR = 4u * V;
     const uint64_t nrun = (uint64_t)cdiv(g.x1 - g.x0, BX) * cdiv(g.ny, BY) * cdiv(g.nz, BZR);
     if (nrun == 0) return cudaSuccess;
     if (nrun > 0x7fffffffull) return cudaErrorInvalidConfiguration;
@@ -664,16 +665,38 @@ cudaError_t launch_grid_nearest(Device& d, MeshDev& m, const GridParams& g, int 
     bvh.stats = d.want_stats ? d.stats.as<unsigned long long>() : nullptr;
 #endif
     if (rb)
-        k_grid_nearest_run<RUN_SIGN_RAYCAST, 2><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_RAYCAST, V><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                               tile_slot, planes, pr);
     else if (mode == MODE_NORMAL)
-        k_grid_nearest_run<RUN_SIGN_NORMAL, 2><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_NORMAL, V><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                              tile_slot, planes, pr);
     else
-        k_grid_nearest_run<RUN_SIGN_NONE, 2><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_NONE, V><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                            tile_slot, planes, pr);
     d.launches++;
     return cudaGetLastError();
+}
+
+// Voxels per lane (the run along z). 4 amortises a node visit over 128 voxels instead of 64 but needs more registers
+// (24 instead of 28 resident warps) and a tile twice as long in z. Measured over mesh sizes, grid sizes and cell shapes
+// (profiles/r2m_run_length.md): it wins on large grids that are fine relative to the mesh and whose cells are thin in
+// z - 0.65x .. 0.97x the kernel time at 256^3 for 5k .. 100k triangles, 0.91x on C5 - and loses 3 .. 20 % on cubic
+// cells, on small grids and where the mesh is as fine as the grid.
+uint32_t grid_run_length(const Device& d, const MeshDev& m, const GridParams& g) {
+    if (d.run_v == 2u || d.run_v == 4u) return d.run_v;  // M2S_OPT_RUN_LENGTH
+    const double cells = (double)g.nx * g.ny * g.nz;
+    const double sx = fabs((double)g.sx), sy = fabs((double)g.sy), sz = fabs((double)g.sz);
+    const bool big_grid = cells >= 8.0e6;
+    const bool fine_grid = cells >= 64.0 * (double)m.nt;                   // voxels per triangle
+    const bool thin_z = 16.0 * sz <= 1.5 * std::max(2.0 * sx, 4.0 * sy);   // the 2 x 4 x 16 tile stays compact
+    return big_grid && fine_grid && thin_z ? 4u : 2u;
+}
+
+// The distance kernel over the slab [g.x0, g.x1). progress (optional): completion flags per brick plane.
+cudaError_t launch_grid_nearest(Device& d, MeshDev& m, const GridParams& g, int mode, const RowBits* rb, float* d_out,
+                                const Progress* progress) {
+    return grid_run_length(d, m, g) == 4u ? launch_grid_nearest_v<4>(d, m, g, mode, rb, d_out, progress)
+                                          : launch_grid_nearest_v<2>(d, m, g, mode, rb, d_out, progress);
 }
 
 cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value, const Progress* progress, uint32_t planes) {

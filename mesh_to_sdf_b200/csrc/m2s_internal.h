@@ -177,6 +177,7 @@ struct Device {
     DevBuf rows[3], big_list, big_count;
     DevBuf stats;                 // traversal counters (stats builds only)
     bool want_stats = false;
+    uint32_t run_v = 0;           // M2S_OPT_RUN_LENGTH: 0 = by mesh size, 2 / 4 = voxels per lane of the grid kernel
     bool no_ray_bins = false;     // M2S_OPT_RAY_BINS = 0: ray parities always through the box tree (tests, A/B)
     DevBuf tile_slot;             // per-tile nearest-triangle slots published by the distance kernel
     DevBuf progress;              // per brick plane completion counters (pipelined host copies)

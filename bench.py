@@ -675,14 +675,16 @@ def bench_grid_multi(env, m2s, name, steps, warmup, balance=True):
 
     # Equal-width slabs are uneven in cost (profiles/r2b_c5_slab_balance.log: 0.86 at 8 slabs). A service that
     # regenerates grids keeps the split of its last call: the cuts are moved to equal shares of the measured kernel
-    # time during UNTIMED steps, then frozen for the warm-up and the timed steps.
+    # time during up to 8 UNTIMED steps, then frozen for the warm-up and the timed steps.
     balance_log = [[list(b) for b in bounds]]
     if balance:
-        for _ in range(4):
+        for _ in range(8):
             env.flush.fill_(3)
             step_device()
             ctx.synchronize()
             times = env.gather_list(float(ctx.timings()["dist_ms"]))
+            if max(times) <= 1.02 * min(times):
+                break
             bounds = rebalance(bounds, times)
             cut["x0"], cut["x1"] = bounds[rank]
             balance_log.append([list(b) for b in bounds])
@@ -765,7 +767,7 @@ def bench_grid_multi(env, m2s, name, steps, warmup, balance=True):
         "roofline": roofline_block("k_grid_nearest_run<Raycast, V=2> (slowest rank's slab)", kern_ms, b_alg,
                                    f"k_grid_nearest_dram_bytes_per_launch_{name}", ISSUE_NOTE),
         "phases_ms": phases, "per_rank_phases_ms": rank_table, "single_gpu_same_workload": single,
-        "slab_cuts": {"method": "equal shares of the measured per-slab kernel time of 4 untimed steps, frozen before "
+        "slab_cuts": {"method": "equal shares of the measured per-slab kernel time over up to 8 untimed steps, frozen before "
                                 "the warm-up" if balance else "equal widths",
                       "history": balance_log},
         "assembly": "device: every rank's distance kernel stores its x-slab into rank 0's flat buffer through a "

@@ -1180,7 +1180,8 @@ m2s_status m2s_set_option(m2s_ctx* ctx, int option, int64_t value) {
             ctx->balance = SlabBalance{};
             return M2S_OK;
         case M2S_OPT_RUN_LENGTH:
-            if (value != 0 && value != 2 && value != 4) return fail(ctx, M2S_EINVAL, "run length: 0, 2 or 4");
+            if (value != 0 && value != 2 && value != 4 && value != 18 && value != 20)
+                return fail(ctx, M2S_EINVAL, "run length: 0, 2, 4 (+16: the 4 x 4 x 2V lane layout)");
             for (int i = 0; i < ctx->n_devices; ++i) ctx->dev[i].run_v = (uint32_t)value;
             return M2S_OK;
         case M2S_OPT_RAY_BINS:

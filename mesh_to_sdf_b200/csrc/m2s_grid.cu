@@ -60,7 +60,7 @@ constexpr int RUN_WARPS = 4;
 
 enum : int { RUN_SIGN_NONE = 0, RUN_SIGN_RAYCAST = 1, RUN_SIGN_NORMAL = 2 };
 
-template <int SIGN, int V>
+template <int SIGN, int V, int LAYOUT>
 __global__ void __launch_bounds__(32 * RUN_WARPS, RUN_MIN_BLOCKS)
 k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
                    const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
@@ -88,10 +88,12 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const uint32_t bz = bid % nbz;
     bid /= nbz;
     const uint32_t by = bid % nby, bx = bid / nby;
-    // warp (wx, wy), lane (lx:2, ly:4, run:4): first voxel of this lane's run (x relative to the slab start)
-    const uint32_t xr = bx * BX + ((warp >> 1) & 1u) * 2u + (lane >> 4);
-    const uint32_t y = by * BY + (warp & 1u) * 4u + ((lane >> 2) & 3u);
-    const uint32_t z0 = bz * BZR + (lane & 3u) * V;
+    // first voxel of this lane's run (x relative to the slab start); a block of 4 warps covers a 4 x 8 x 4V brick
+    //   LAYOUT 0: warp tile 2 x 4 x 4V - warps (wx, wy), lanes (lx:2, ly:4, run:4): compact where cells are thin in z
+    //   LAYOUT 1: warp tile 4 x 4 x 2V - warps (wy, wz), lanes (lx:4, ly:4, run:2): compact where cells are cubic
+    const uint32_t xr = bx * BX + (LAYOUT == 0 ? ((warp >> 1) & 1u) * 2u + (lane >> 4) : (lane >> 3));
+    const uint32_t y = by * BY + (warp & 1u) * 4u + (LAYOUT == 0 ? ((lane >> 2) & 3u) : ((lane >> 1) & 3u));
+    const uint32_t z0 = bz * BZR + (LAYOUT == 0 ? (lane & 3u) * V : (warp >> 1) * 2u * V + (lane & 1u) * V);
     const uint32_t x = g.x0 + xr;
     const bool valid_xy = x < g.x1 && y < g.ny;
     bool valid[V];
@@ -145,7 +147,9 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     // `seed_planes` steps back in x, published by the warp that computed it.
     uint32_t nseed = 0xffffffffu;
     const uint32_t back = seed_planes * nby * nbz;  // dispatch distance of that brick
-    const uint32_t src_warp = warp | 2u, src_idx = lane & 15u;
+    // the x-far voxels of a brick: LAYOUT 0 lanes 16..31 of the warps with wx = 1, LAYOUT 1 lanes 24..31 of every warp
+    const uint32_t src_warp = LAYOUT == 0 ? (warp | 2u) : warp, src_idx = LAYOUT == 0 ? (lane & 15u) : (lane & 7u);
+    const bool publishes = LAYOUT == 0 ? (lane >= 16u && (warp & 2u)) : ((lane >> 3) == 3u);
     if (tile_slot && blockIdx.x >= back) {
         nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - back) * RUN_WARPS + src_warp) * 16u + src_idx);
         // a straggler: the brick twice as far back has certainly finished (still a good radius)
@@ -347,7 +351,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     }
 
     // publish the x-far voxels' nearest triangles for the bricks further in x
-    if (tile_slot && lane >= 16u && (warp & 2u)) {
+    if (tile_slot && publishes) {
         // the middle voxel of the run (the first one where the run is cut by the grid's end)
         if (valid[0])
             __stcg(tile_slot + ((size_t)blockIdx.x * RUN_WARPS + warp) * 16u + src_idx,
@@ -637,7 +641,7 @@ float grid_magnitude(const GridParams& g) {
 uint32_t grid_brick_planes(const GridParams& g) { return cdiv(g.x1 - g.x0, (uint32_t)BX); }
 
 // The distance kernel over the slab [g.x0, g.x1). progress (optional): completion flags per brick plane.
-template <int V>
+template <int V, int LAYOUT>
 static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams& g, int mode, const RowBits* rb,
                                          float* d_out, const Progress* progress) {
     cudaStream_t s = d.stream;
@@ -665,13 +669,13 @@ static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams
     bvh.stats = d.want_stats ? d.stats.as<unsigned long long>() : nullptr;
 #endif
     if (rb)
-        k_grid_nearest_run<RUN_SIGN_RAYCAST, V><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_RAYCAST, V, LAYOUT><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                               tile_slot, planes, pr);
     else if (mode == MODE_NORMAL)
-        k_grid_nearest_run<RUN_SIGN_NORMAL, V><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_NORMAL, V, LAYOUT><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                              tile_slot, planes, pr);
     else
-        k_grid_nearest_run<RUN_SIGN_NONE, V><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_NONE, V, LAYOUT><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                            tile_slot, planes, pr);
     d.launches++;
     return cudaGetLastError();
@@ -681,22 +685,30 @@ static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams
 // (24 instead of 28 resident warps) and a tile twice as long in z. Measured over mesh sizes, grid sizes and cell shapes
 // (profiles/r2m_run_length.md): it wins on large grids that are fine relative to the mesh and whose cells are thin in
 // z - 0.65x .. 0.97x the kernel time at 256^3 for 5k .. 100k triangles, 0.91x on C5 - and loses 3 .. 20 % on cubic
-// cells, on small grids and where the mesh is as fine as the grid.
+// cells, on small grids and where the mesh is as fine as the grid. Return value: V (+ 16 for lane layout 1).
 uint32_t grid_run_length(const Device& d, const MeshDev& m, const GridParams& g) {
-    if (d.run_v == 2u || d.run_v == 4u) return d.run_v;  // M2S_OPT_RUN_LENGTH
+    if (d.run_v != 0u) return d.run_v;  // M2S_OPT_RUN_LENGTH: 2, 4 (layout 0), 18, 20 (layout 1)
     const double cells = (double)g.nx * g.ny * g.nz;
     const double sx = fabs((double)g.sx), sy = fabs((double)g.sy), sz = fabs((double)g.sz);
     const bool big_grid = cells >= 8.0e6;
     const bool fine_grid = cells >= 64.0 * (double)m.nt;                   // voxels per triangle
     const bool thin_z = 16.0 * sz <= 1.5 * std::max(2.0 * sx, 4.0 * sy);   // the 2 x 4 x 16 tile stays compact
-    return big_grid && fine_grid && thin_z ? 4u : 2u;
+    if (big_grid && fine_grid && thin_z) return 4u;
+    // cells about as wide as deep and a mesh about as fine as the grid: the 4 x 4 x 4 warp tile of layout 1 is the
+    // compact one (0.94 .. 0.96x at 100k .. 1M triangles on cubic cells; slower everywhere else)
+    if (!thin_z && !fine_grid) return 18u;
+    return 2u;
 }
 
 // The distance kernel over the slab [g.x0, g.x1). progress (optional): completion flags per brick plane.
 cudaError_t launch_grid_nearest(Device& d, MeshDev& m, const GridParams& g, int mode, const RowBits* rb, float* d_out,
                                 const Progress* progress) {
-    return grid_run_length(d, m, g) == 4u ? launch_grid_nearest_v<4>(d, m, g, mode, rb, d_out, progress)
-                                          : launch_grid_nearest_v<2>(d, m, g, mode, rb, d_out, progress);
+    switch (grid_run_length(d, m, g)) {
+        case 4u: return launch_grid_nearest_v<4, 0>(d, m, g, mode, rb, d_out, progress);
+        case 18u: return launch_grid_nearest_v<2, 1>(d, m, g, mode, rb, d_out, progress);
+        case 20u: return launch_grid_nearest_v<4, 1>(d, m, g, mode, rb, d_out, progress);
+        default: return launch_grid_nearest_v<2, 0>(d, m, g, mode, rb, d_out, progress);
+    }
 }
 
 cudaError_t launch_fill(Device& d, float* d_out, uint64_t n, float value, const Progress* progress, uint32_t planes) {

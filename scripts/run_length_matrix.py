@@ -7,7 +7,7 @@ import mesh_to_sdf_b200 as m2s
 from mesh_to_sdf_b200 import synth
 
 ctx = m2s.default_context()
-print("| mesh | triangles | grid | cells | sign | V=2 ms | V=4 ms | V=4 / V=2 |\n|---|---:|---|---|---|---:|---:|---:|")
+print("| mesh | triangles | grid | cells | sign | V=2 ms | V=4 ms | V=2 B ms | V=4 B ms | best |\n|---|---:|---|---|---|---:|---:|---:|---:|---|")
 for nu, nv in ((64, 40), (100, 64), (128, 98), (180, 140), (256, 196), (512, 392), (1024, 490)):
     verts, tris = synth.bumpy_torus(nu, nv)
     mn, mx = synth.padded_grid_box(verts)
@@ -23,9 +23,9 @@ for nu, nv in ((64, 40), (100, 64), (128, 98), (180, 140), (256, 196), (512, 392
                     cnt = [max(8, int(np.ceil((mx[i] - mn[i]) / cs))) for i in range(3)]
                     grid = m2s.Grid(mn + 0.5 * cs, [cs, cs, cs], cnt)
                 out = m2s.host_alloc(grid.get_total_cell_count())
-                for sign in (0, 1):
+                for sign in (0,):
                     t = {}
-                    for v in (2, 4):
+                    for v in (2, 4, 18, 20):
                         ctx.set_option(m2s.OPT_RUN_LENGTH, v)
                         best = 1e9
                         for _ in range(3):
@@ -33,6 +33,7 @@ for nu, nv in ((64, 40), (100, 64), (128, 98), (180, 140), (256, 196), (512, 392
                             best = min(best, ctx.timings()["dist_ms"])
                         t[v] = best
                     print(f"| T({nu},{nv}) | {len(tris)} | {'x'.join(map(str, grid.cell_count))} | {shape} | "
-                          f"{'Raycast' if sign == 0 else 'Normal'} | {t[2]:.3f} | {t[4]:.3f} | {t[4] / t[2]:.3f} |", flush=True)
+                          f"{'Raycast' if sign == 0 else 'Normal'} | {t[2]:.3f} | {t[4]:.3f} | {t[18]:.3f} | {t[20]:.3f} | "
+                          f"{min(t, key=t.get)} ({min(t.values()) / t[2]:.3f}) |", flush=True)
                 out.close()
 ctx.set_option(m2s.OPT_RUN_LENGTH, 0)

@@ -165,6 +165,31 @@ def test_ragged_grids_and_slabs_bit_exact(m2s, oracle, dims):
         assert np.array_equal(out.cpu().numpy().view(np.uint32), want[x0 * plane:x1 * plane].view(np.uint32))
 
 
+@pytest.mark.parametrize("run_length", [2, 4, 18, 20])
+@pytest.mark.parametrize("dims", [(37, 21, 30), (5, 9, 131), (48, 40, 33)])
+def test_every_run_length_and_lane_layout_bit_exact(m2s, oracle, run_length, dims):
+    # the grid kernel exists with runs of 2 and 4 voxels per lane and two lane layouts (M2S_OPT_RUN_LENGTH: 2, 4,
+    # +16 = the 4 x 4 x 2V layout); the library picks one by grid / mesh shape. Every variant must give the exact
+    # oracle's bits on ragged grids and slabs, with both sign methods, through the pipelined host path too
+    verts, tris = synth.bumpy_torus(40, 24)
+    grid = _grid_for(m2s, verts, list(dims))
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, RAYCAST)
+    want_n = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, NORMAL)
+    with m2s.Context() as c:
+        c.set_option(m2s.OPT_RUN_LENGTH, run_length)
+        got = c.grid_sdf(verts, tris, grid, RAYCAST)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        got_n = c.grid_sdf(verts, tris, grid, NORMAL)
+        assert np.max(np.abs(np.abs(got_n) - np.abs(want_n))) <= 4e-6
+        assert np.array_equal(np.signbit(got_n), np.signbit(want_n))
+        c.set_option(m2s.OPT_HOST_PATH, m2s.HOST_PIPELINED)
+        assert np.array_equal(c.grid_sdf(verts, tris, grid, RAYCAST).view(np.uint32), want.view(np.uint32))
+        plane = dims[1] * dims[2]
+        x0, x1 = dims[0] // 3, dims[0] - 2
+        part = c.grid_sdf_slab(verts, tris, grid, RAYCAST, x0, x1)
+        assert np.array_equal(part.view(np.uint32), want[x0 * plane:x1 * plane].view(np.uint32))
+
+
 def test_normal_sign_near_ties_positive_wins(m2s, oracle):
     # lib.rs:242-254: approximately equal |d| (2 ulps / 1e-6) -> the positive one wins. Queries in the mid-plane of
     # a thin slab see two faces at (almost) the same distance from opposite sides; queries straight above a shared

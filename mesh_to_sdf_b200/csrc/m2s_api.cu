@@ -981,8 +981,10 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
         // faults inside them. Measured on this pool's hosts (scripts/host_fault_bench.cpp, 64 MiB, huge pages
         // advised): 4 threads fill 14.9 GB/s, 8 threads 23.8 GB/s; the C3 kernel produces 13.8 GB/s. Half of the
         // host's threads divided by the visible GPUs (one process per GPU shares the host), 4..8.
+        // A context that drives several GPUs itself gets that share for each of them (up to 16 threads).
         const int hw = (int)std::thread::hardware_concurrency();
-        ctx->copy_threads = std::min(8, std::max(4, hw / (2 * std::max(1, visible))));
+        const int share = std::max(1, hw / (2 * std::max(1, visible)));
+        ctx->copy_threads = std::min(ctx->n_devices > 1 ? 16 : 8, std::max(4, share * ctx->n_devices));
     }
     ctx->dev = new (std::nothrow) Device[ids.size()];
     if (!ctx->dev) { delete ctx; return M2S_EINVAL; }

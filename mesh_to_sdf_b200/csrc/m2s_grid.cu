@@ -100,17 +100,18 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
 #pragma unroll
     for (int i = 0; i < V; ++i) valid[i] = valid_xy && z0 + i < g.nz;
 
-    // every warp reports the completion of its stores; the last warp of a brick plane publishes the plane's flag
-    // in mapped host memory (the host copies finished planes while the kernel runs, m2s_api.cu)
+    // every BLOCK reports the completion of its stores; the last block of a brick plane publishes the plane's flag
+    // in mapped host memory (the host copies finished planes while the kernel runs, m2s_api.cu). All four warps meet
+    // at a barrier (a block keeps its resources until its last warp exits anyway), then one thread releases the
+    // block's stores at device scope - cumulative over what the barrier made visible to it - and bumps the plane's
+    // counter; the block that completes the plane fences at system scope before it publishes the flag.
     auto signal_done = [&]() {
         if (progress.count == nullptr) return;
-        // release at device scope per warp; the warp that completes the plane fences at system scope before it
-        // publishes the flag (cumulative: everything it observed through the counter is ordered before the flag)
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
             const uint32_t done = atomicAdd(progress.count + bx, 1u) + 1u;
-            if (done == nby * nbz * (uint32_t)RUN_WARPS) {
+            if (done == nby * nbz) {
                 __threadfence_system();
                 progress.flag[bx] = progress.epoch;
             }

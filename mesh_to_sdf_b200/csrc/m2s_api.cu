@@ -358,7 +358,8 @@ bool host_is_pinned(const void* p) {
     }
     return a.type == cudaMemoryTypeHost;
 }
-cudaError_t upload_inputs(m2s_ctx* ctx, Device& d, PinBuf& stage, const H2DPart* parts, int n_parts) {
+cudaError_t upload_inputs(m2s_ctx* ctx, Device& d, PinBuf& stage, const H2DPart* parts, int n_parts,
+                          cudaStream_t stream) {
     size_t total = 0;
     bool pageable = false;
     for (int i = 0; i < n_parts; ++i) {
@@ -368,7 +369,7 @@ cudaError_t upload_inputs(m2s_ctx* ctx, Device& d, PinBuf& stage, const H2DPart*
     if (!pageable || total < H2D_STAGE_MIN_BYTES || ctx->host_path == M2S_HOST_STAGED) {
         for (int i = 0; i < n_parts; ++i)
             if (parts[i].bytes) {
-                cudaError_t e = cudaMemcpyAsync(parts[i].dst, parts[i].src, parts[i].bytes, cudaMemcpyHostToDevice, d.stream);
+                cudaError_t e = cudaMemcpyAsync(parts[i].dst, parts[i].src, parts[i].bytes, cudaMemcpyHostToDevice, stream);
                 if (e != cudaSuccess) return e;
             }
         return cudaSuccess;
@@ -393,7 +394,6 @@ cudaError_t upload_inputs(m2s_ctx* ctx, Device& d, PinBuf& stage, const H2DPart*
         }
     std::atomic<int> failed{0};
     const int ordinal = d.ordinal;
-    cudaStream_t stream = d.stream;
     std::function<void(int)> job = [&](int k) {
         const Chunk& c = chunks[(size_t)k];
         std::memcpy(c.pin, c.src, c.bytes);
@@ -430,7 +430,7 @@ m2s_status stage_mesh_inputs(m2s_ctx* ctx, int nd, bool host_inputs, const float
         CU(ctx, d0.verts.ensure(nv * 12));
         CU(ctx, d0.tris.ensure(nt * 12));
         const H2DPart parts[2] = {{d0.verts.p, verts, nv * 12}, {d0.tris.p, tris, nt * 12}};
-        CU(ctx, upload_inputs(ctx, d0, d0.in_mesh, parts, 2));
+        CU(ctx, upload_inputs(ctx, d0, d0.in_mesh, parts, 2, d0.stream));
         in_dev[0] = MeshInputs{d0.verts.as<float>(), d0.tris.as<uint32_t>()};
     } else {
         in_dev[0] = MeshInputs{verts, tris};
@@ -874,8 +874,11 @@ m2s_status points_call(m2s_ctx* ctx, m2s_mesh* handle, bool host_io, const float
         if (host_io) {
             CU(ctx, d.queries.ensure(n * 12));
             CU(ctx, d.out.ensure(n * 4));
+            // the queries travel on the side stream while the main stream builds the tree
             const H2DPart part{d.queries.p, queries + 3 * q0, n * 12};
-            CU(ctx, upload_inputs(ctx, d, d.in_queries, &part, 1));
+            CU(ctx, upload_inputs(ctx, d, d.in_queries, &part, 1, d.aux_stream));
+            CU(ctx, cudaEventRecord(d.ev_rows, d.aux_stream));
+            CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_rows, 0));
             dq = d.queries.as<float>();
             target = d.out.as<float>();
         } else if (i == 0) {

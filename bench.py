@@ -442,7 +442,8 @@ ISSUE_NOTE = ("exact nearest-triangle search is issue-bound, not HBM-bound: the 
               "bytes, sets its time (DESIGN.md §3, profiles/)")
 
 
-def bench_grid_single(env, m2s, name, steps, warmup, want_cpu, cpu_planes, want_parity, host_steps=None):
+def bench_grid_single(env, m2s, name, steps, warmup, want_cpu, cpu_planes, want_parity, host_steps=None,
+                      want_post=False):
     """One grid config on ONE GPU: device-resident value, e2e through the facade's pageable buffers (+ pinned),
     roofline, optional CPU baseline + parity numbers."""
     torch = env.torch
@@ -465,6 +466,7 @@ def bench_grid_single(env, m2s, name, steps, warmup, want_cpu, cpu_planes, want_
     total_ms, kern_ms, phases, launches = timed_device_steps(env, ctx, step_device, steps, warmup, sampler=sampler)
     clocks = sampler.stop()
     value = cells * steps / (total_ms * 1e-3) / 1e6
+    post = bench_post_passes(env, ctx, m2s, grid, d_out, cells) if want_post else None
     del d_out
 
     # ---- e2e: the facade call, pageable everything (what include/mesh_to_sdf.hpp / the Rust facade hand over) ----
@@ -521,6 +523,8 @@ def bench_grid_single(env, m2s, name, steps, warmup, want_cpu, cpu_planes, want_
                                    f"k_grid_nearest_dram_bytes_per_launch_{name}", ISSUE_NOTE),
         "phases_ms": phases,
     }
+    if post is not None:
+        line["post_passes"] = post
     if want_cpu:
         import oracle
 
@@ -535,6 +539,54 @@ def bench_grid_single(env, m2s, name, steps, warmup, want_cpu, cpu_planes, want_
             line["parity"] = grid_parity(oracle, verts, tris, grid, sign, diag, gpu_sdf, faithful, fx0)
     ctx.close()
     return line
+
+
+def bench_post_passes(env, ctx, m2s, grid, d_sdf, cells, reps=10):
+    """What the reference's in-repo caller does with the grid next, on the device-resident grid:
+    render order + iso limits (mesh_to_sdf_client/src/sdf.rs:65-68, :123) and sampling with interpolation
+    (shaders/draw_raymarching.wgsl:118-200). HBM-bound passes: algorithmic bytes over the measured copy peak."""
+    torch = env.torch
+    peak, _ = measured_peak()
+    out = {}
+    d_order = torch.empty(cells, dtype=torch.int32, device=env.dev)
+    d_mm = torch.empty(2, dtype=torch.float32, device=env.dev)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ctx.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = []
+        for _ in range(reps):
+            env.flush.fill_(7)
+            ev0.record(env.stream)
+            fn()
+            ev1.record(env.stream)
+            ctx.synchronize()
+            ms.append(ev0.elapsed_time(ev1))
+        return float(np.median(ms))
+
+    ms = timed(lambda: ctx.grid_order_device(d_sdf.data_ptr(), cells, d_order.data_ptr(), d_mm.data_ptr()))
+    b = 8 * cells + 8  # the grid read once, the order written once, (min, max)
+    out["grid_order"] = {"ms": ms, "Mcells_per_s": cells / ms / 1e3, "algorithmic_bytes": int(b),
+                         "roofline_frac_hbm": b / (ms * 1e-3) / 1e9 / peak,
+                         "what": "m2s_grid_order_device: total-order keys -> cub::DeviceRadixSort::SortPairs (library) -> "
+                                 "min / max; the radix passes over (key, index) pairs are the sort's own traffic"}
+    n_pts = 4_000_000
+    lo = torch.tensor(np.asarray(grid.first_cell), device=env.dev)
+    hi = torch.tensor(np.asarray(grid.get_last_cell(), np.float32), device=env.dev)
+    gen = torch.Generator(device=env.dev)
+    gen.manual_seed(1234)
+    pts = (lo + (hi - lo) * torch.rand((n_pts, 3), device=env.dev, generator=gen)).contiguous()
+    d_val = torch.empty(n_pts, dtype=torch.float32, device=env.dev)
+    for mode, mname in ((1, "trilinear"), (2, "tetrahedral")):
+        ms = timed(lambda: ctx.sample_grid_sdf_device(d_sdf.data_ptr(), grid, pts.data_ptr(), n_pts, mode, 0.0,
+                                                      d_val.data_ptr()))
+        b = 16 * n_pts  # 12 B point + 4 B result; the gathered corners hit L2 (the grid is 64 MiB)
+        out["sample_" + mname] = {"ms": ms, "Msamples_per_s": n_pts / ms / 1e3, "algorithmic_bytes": int(b),
+                                  "roofline_frac_hbm": b / (ms * 1e-3) / 1e9 / peak,
+                                  "what": f"m2s_sample_grid_sdf_device, {n_pts} uniform points, {mname} on the dual grid"}
+    return out
 
 
 def bench_points_single(env, m2s, name, steps, warmup, want_cpu, cpu_queries):
@@ -800,7 +852,7 @@ def run_ours(args):
             line = bench_points_single(env, m2s, name, args.steps, warmup, cpu, args.cpu_queries)
         else:
             planes = args.cpu_planes if name != "C5" else min(args.cpu_planes, 16)
-            line = bench_grid_single(env, m2s, name, args.steps, warmup, cpu, planes, cpu)
+            line = bench_grid_single(env, m2s, name, args.steps, warmup, cpu, planes, cpu, want_post=name == "C3")
         if not args.workload and not args.no_extra:
             extras = []
             extras.append(bench_grid_single(env, m2s, "C2", args.steps, warmup, cpu, 128, cpu))

@@ -111,7 +111,8 @@ typedef enum m2s_host_path {
 
 /* ---- context ------------------------------------------------------------------------------------ */
 
-/* Create a context on `n_devices` CUDA devices (`devices == NULL || n_devices == 0` -> device 0).
+/* Create a context on `n_devices` CUDA devices (`devices == NULL || n_devices == 0` -> device 0; an ordinal may be
+ * listed more than once: every entry gets its own streams, arenas and slab).
  * With more than one device, m2s_generate_grid_sdf shards the grid by slabs along x (the slowest
  * axis of get_cell_idx) and m2s_generate_sdf shards the queries by contiguous ranges. */
 M2S_API m2s_status m2s_create(const int* devices, int n_devices, m2s_ctx** out);

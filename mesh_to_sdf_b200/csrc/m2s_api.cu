@@ -971,11 +971,11 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
     std::vector<int> ids;
     if (!devices || n <= 0) ids.push_back(0);
     else ids.assign(devices, devices + n);
-    for (size_t i = 0; i < ids.size(); ++i) {
+    // An ordinal may be listed more than once: every entry is a "device" of the context with its own streams, arenas
+    // and slab (several slabs in flight on one GPU; also how the multi-device paths are exercised on a one-GPU box).
+    if (ids.size() > 64) return M2S_EINVAL;
+    for (size_t i = 0; i < ids.size(); ++i)
         if (ids[i] < 0 || ids[i] >= visible) return M2S_ENODEV;
-        for (size_t j = 0; j < i; ++j)
-            if (ids[j] == ids[i]) return M2S_EINVAL;
-    }
     m2s_ctx* ctx = new (std::nothrow) m2s_ctx();
     if (!ctx) return M2S_EINVAL;
     ctx->n_devices = (int)ids.size();
@@ -1032,6 +1032,10 @@ m2s_status create_common(const int* devices, int n, void* stream, bool use_strea
     // peer access between the first device and every other one: slabs are stored straight into the first
     // device's memory, the mesh is pulled from it
     for (size_t i = 1; i < ids.size(); ++i) {
+        if (ids[i] == ids[0]) {  // the same GPU: its memory is simply its own
+            ctx->dev[i].peer_to_first = true;
+            continue;
+        }
         int to0 = 0, from0 = 0;
         cudaDeviceCanAccessPeer(&to0, ids[i], ids[0]);
         cudaDeviceCanAccessPeer(&from0, ids[0], ids[i]);

@@ -120,10 +120,15 @@ def test_zero_cell_count_returns_empty(m2s):
     assert out.shape == (0,)
 
 
+def _two_devices(torch):
+    # two GPUs when the box has them; else the same GPU twice (m2s_create accepts a repeated ordinal: two "devices"
+    # of the context with their own streams and slabs), so that the multi-device paths run on a one-GPU box too
+    return [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+
+
 def test_multi_device_context_matches_single(m2s):
     torch = pytest.importorskip("torch")
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    devs = _two_devices(torch)
     verts, tris = synth.bumpy_torus(32, 20)
     mn, mx = synth.padded_grid_box(verts)
     grid = m2s.Grid.from_bounding_box(mn, mx, [37, 20, 24])
@@ -133,7 +138,7 @@ def test_multi_device_context_matches_single(m2s):
     qa = m2s.default_context().sdf(verts, tris, q, 3, 0)
     n = 37 * 20 * 24
     for build_mode in (m2s.BUILD_REPLICATED, m2s.BUILD_BROADCAST):
-        with m2s.Context([0, 1]) as c2:
+        with m2s.Context(devs) as c2:
             assert c2.device_count == 2
             c2.set_option(m2s.OPT_BUILD_MODE, build_mode)
             # pageable destination: staged (small grid), then forced through the pinned ring
@@ -238,15 +243,14 @@ def test_multi_device_slab_balance_keeps_the_bits(m2s):
     # a multi-device context moves its slab cuts to equal shares of the previous call's measured kernel times
     # (M2S_OPT_BALANCE, default on): the cuts change from call to call on a lopsided grid, the result never does
     torch = pytest.importorskip("torch")
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    devs = _two_devices(torch)
     verts, tris = synth.bumpy_torus(96, 64)
     mn, mx = synth.padded_grid_box(verts)
     mx = mx.copy()
     mx[0] += 3.0  # the mesh sits in the low-x third of the box: equal-width slabs are far from equal cost
     grid = m2s.Grid.from_bounding_box(mn, mx, [160, 48, 40])
     one = m2s.default_context().grid_sdf(verts, tris, grid, RAYCAST)
-    with m2s.Context([0, 1]) as c2:
+    with m2s.Context(devs) as c2:
         times = []
         for _ in range(4):
             two = c2.grid_sdf(verts, tris, grid, RAYCAST)
@@ -254,7 +258,8 @@ def test_multi_device_slab_balance_keeps_the_bits(m2s):
             times.append((c2.timings(0)["dist_ms"], c2.timings(1)["dist_ms"]))
         # the imbalance of the first (equal-width) call shrinks once the cuts follow the measured times
         ratio = [max(a, b) / max(min(a, b), 1e-6) for a, b in times]
-        assert ratio[-1] < ratio[0] or ratio[0] < 1.15, (times, ratio)
+        if devs[0] != devs[1]:  # two kernels sharing one GPU do not have separable times
+            assert ratio[-1] < ratio[0] or ratio[0] < 1.15, (times, ratio)
         c2.set_option(m2s.OPT_BALANCE, 0)
         assert np.array_equal(one.view(np.uint32), c2.grid_sdf(verts, tris, grid, RAYCAST).view(np.uint32))
         c2.set_option(m2s.OPT_BALANCE, 1)

@@ -1026,11 +1026,24 @@ cudaError_t launch_ray_bins(Device& d, MeshDev& m) {
     const size_t cells = (size_t)3 * R * R;
     const uint64_t cap64 = (uint64_t)RAYBIN_ITEMS_PER_TRI * 3u * nt + 1024u;
     const uint32_t capacity = (uint32_t)std::min<uint64_t>(cap64, 0xfffffff0ull);
-    CK(m.bin_offsets.ensure((cells + 1) * 4));
-    CK(m.bin_cursor.ensure((cells + 1) * 4));
-    CK(m.bin_items.ensure((size_t)capacity * 4));
-    CK(m.bin_big.ensure((size_t)3 * RAYBIN_MAX_BIG * 4));
-    CK(m.bin_meta.ensure(32));
+    {
+        // the bins are an accelerator, not a requirement: a mesh too large for their item array (144 bytes per triangle)
+        // keeps the packet walk of the box tree
+        cudaError_t e = m.bin_offsets.ensure((cells + 1) * 4);
+        if (e == cudaSuccess) e = m.bin_cursor.ensure((cells + 1) * 4);
+        if (e == cudaSuccess) e = m.bin_items.ensure((size_t)capacity * 4);
+        if (e == cudaSuccess) e = m.bin_big.ensure((size_t)3 * RAYBIN_MAX_BIG * 4);
+        if (e == cudaSuccess) e = m.bin_meta.ensure(32);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            DevBuf* bufs[] = {&m.bin_offsets, &m.bin_cursor, &m.bin_items, &m.bin_big, &m.bin_meta};
+            for (DevBuf* b : bufs) b->release();
+            m.bvh.bins = RayBins{};
+            m.bins_built = true;  // decided: no bins for this mesh
+            return cudaSuccess;
+        }
+        CK(e);
+    }
     CK(cudaMemsetAsync(m.bin_cursor.p, 0, (cells + 1) * 4, s));
     CK(cudaMemsetAsync(m.bin_meta.p, 0, 32, s));
     const float4* rec = m.rec_sorted.as<float4>();

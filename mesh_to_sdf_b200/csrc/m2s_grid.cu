@@ -14,8 +14,8 @@ namespace m2s {
 namespace {
 
 // ---------------------------------------------------------------------------------------------------
-// Run kernel. One warp = 32 lanes x a RUN of V = 2 consecutive voxels along z (tile 2 x 4 x 8 cells) walks the LBVH
-// ONCE as a packet: the stack lives in shared memory, node loads are warp-uniform (one L1 wavefront instead of up
+// Run kernel. One warp = 32 lanes x a RUN of V = 2 or 4 consecutive voxels along z (warp tile 2 x 4 x 4V cells, or
+// 4 x 4 x 2V with LAYOUT 1; grid_run_length picks per grid / mesh shape) walks the LBVH ONCE as a packet: the stack lives in shared memory, node loads are warp-uniform (one L1 wavefront instead of up
 // to 32), control flow is uniform, and every voxel still prunes with its own radius, so each result is the same
 // exact minimum. A child is entered if any voxel needs it; the child most lanes are nearer to goes first; a stack
 // entry is dropped when its warp-min bound exceeds the warp-max radius.
@@ -32,7 +32,8 @@ namespace {
 // the parent, in a warp-shared queue in shared memory that is drained 32 at a time, any lane working for any voxel
 // of the tile - the owner's position arrives by shuffle (its z recomputed with the owner's own Grid::get_cell_center
 // arithmetic), the minimum returns through a 64-bit shared-memory atomicMin on (d2 bits, slot) - so the expensive
-// un-fused reference arithmetic runs with ~all lanes busy.
+// un-fused reference arithmetic runs with ~all lanes busy. The per-voxel results (d2, slot) live only in that shared
+// memory; registers keep what every node visit needs, the pruning bound of the lane's own voxels.
 //
 // Seeds: every search starts from ONE known-near triangle so that its radius is tight from the first node on: each
 // tile publishes the nearest-triangle slots of its x-far voxels (tile_slot, __stcg) and a tile starts from the

@@ -8,8 +8,8 @@ configs, one process per GPU.
 
 N = 1 (default): workload C3 (the configuration BASELINE.json's metric is quoted on: ~100k triangles, 256^3 grid,
   Raycast); the other single-GPU configurations (C2, C4, C5 on one GPU) ride along in `extra_configs`.
-N > 1: workload C5 (1M triangles, 512^3 grid, Raycast), STRONG scaling: the x-slabs of ONE grid are computed by the
-  N ranks and assembled into ONE flat result — device-resident on rank 0 (every rank's distance kernel stores its
+N > 1: workload C5 (1M triangles, 512^3 grid, Raycast; C3 rides along in `extra_configs`), STRONG scaling: the
+  x-slabs of ONE grid are computed by the N ranks and assembled into ONE flat result — device-resident on rank 0 (every rank's distance kernel stores its
   slab straight into rank 0's buffer over NVLink: cudaIpc mapping, no gather step) for `value`, one host buffer
   shared by the ranks for `e2e`. The timed region ends when the whole grid is there.
 
@@ -845,6 +845,9 @@ def run_ours(args):
         if name not in GRID_WORKLOADS:
             raise SystemExit("multi-GPU runs take a grid workload (C2, C3, C5)")
         line = bench_grid_multi(env, m2s, name, args.steps, warmup, balance=not args.equal_slabs)
+        if not args.workload and not args.no_extra:
+            # the metric's own grid (256^3, C3) over the same ranks, strong scaling into one assembled grid as well
+            line["extra_configs"] = [bench_grid_multi(env, m2s, "C3", args.steps, warmup, balance=not args.equal_slabs)]
     else:
         name = args.workload or "C3"
         cpu = not args.no_cpu_baseline

@@ -510,14 +510,16 @@ void advise_huge_pages(void* p, size_t bytes) {
 
 // ---- slab cuts over the devices of a context ---------------------------------------------------------------------
 // cuts[i] .. cuts[i + 1] = the x range of device i
-std::vector<uint64_t> slab_cuts(m2s_ctx* ctx, int nd, uint64_t xa, uint64_t xb, const GridArgs& ga, uint64_t nt) {
+std::vector<uint64_t> slab_cuts(m2s_ctx* ctx, int nd, uint64_t xa, uint64_t xb, const GridArgs& ga, uint64_t nt,
+                                int kind) {
     SlabBalance& b = ctx->balance;
-    const bool same = b.valid && b.nd == nd && b.xa == xa && b.xb == xb && b.ny == ga.g.ny && b.nz == ga.g.nz && b.nt == nt;
+    const bool same = b.valid && b.nd == nd && b.xa == xa && b.xb == xb && b.ny == ga.g.ny && b.nz == ga.g.nz &&
+                      b.nt == nt && b.kind == kind;
     if (!(ctx->balance_slabs && same)) {
         b.cuts.resize((size_t)nd + 1);
         for (int i = 0; i <= nd; ++i) b.cuts[(size_t)i] = xa + (xb - xa) * (uint64_t)i / (uint64_t)nd;
     }
-    b.xa = xa; b.xb = xb; b.ny = ga.g.ny; b.nz = ga.g.nz; b.nt = nt; b.nd = nd;
+    b.xa = xa; b.xb = xb; b.ny = ga.g.ny; b.nz = ga.g.nz; b.nt = nt; b.nd = nd; b.kind = kind;
     b.valid = false;
     b.pending = nd > 1 && ctx->balance_slabs;
     return b.cuts;
@@ -544,6 +546,9 @@ void update_slab_balance(m2s_ctx* ctx) {
         b.valid = true;
         return;
     }
+    // a cut moves by a quarter of the mean slab per call at most: a kernel held up for a call by a saturated host link
+    // or a busy device cannot throw the split far off
+    const double max_move = 0.25 * (double)span / nd;
     std::vector<uint64_t> cuts((size_t)nd + 1);
     cuts[0] = b.xa;
     double acc = 0.0;
@@ -554,6 +559,7 @@ void update_slab_balance(m2s_ctx* ctx) {
         const double x0 = (double)b.cuts[(size_t)r], x1 = (double)b.cuts[(size_t)r + 1];
         double x = x0 + (x1 - x0) * (want - acc) / std::max(t[(size_t)r], 1e-12);
         x = 0.5 * (x + (double)b.cuts[(size_t)k]);  // damped: one odd measurement moves a cut half-way at most
+        x = std::min(std::max(x, (double)b.cuts[(size_t)k] - max_move), (double)b.cuts[(size_t)k] + max_move);
         uint64_t xi = b.xa + (uint64_t)std::llround(std::max(0.0, x - (double)b.xa) / (double)align) * align;
         const uint64_t lo = cuts[(size_t)k - 1] + align, hi = b.xb - align * (uint64_t)(nd - k);
         cuts[(size_t)k] = std::min(std::max(xi, lo), hi);
@@ -601,7 +607,7 @@ m2s_status grid_host(m2s_ctx* ctx, m2s_mesh* handle, const float* verts_xyz, uin
         bool registered;
     };
     std::vector<Slab> slabs(nd);
-    const std::vector<uint64_t> cuts = slab_cuts(ctx, nd, xa, xb, ga, nt);
+    const std::vector<uint64_t> cuts = slab_cuts(ctx, nd, xa, xb, ga, nt, 1);
     for (int i = 0; i < nd; ++i) {
         Device& d = ctx->dev[i];
         Slab& sl = slabs[i];
@@ -799,7 +805,7 @@ m2s_status grid_device(m2s_ctx* ctx, m2s_mesh* handle, const float* d_verts, uin
         m2s_status s = stage_meshes(ctx, nd, handle, in_dev, nv, nt, raycast, meshes);
         if (s != M2S_OK) return s;
     }
-    const std::vector<uint64_t> cuts = slab_cuts(ctx, nd, xa, xb, ga, nt);
+    const std::vector<uint64_t> cuts = slab_cuts(ctx, nd, xa, xb, ga, nt, 0);
     Device& d0 = ctx->dev[0];
     if (nd > 1) {
         // the destination may still be in use by earlier work on the first device's stream

@@ -258,6 +258,7 @@ struct m2s_mesh {
 struct SlabBalance {
     uint64_t xa = 0, xb = 0, ny = 0, nz = 0, nt = 0;
     int nd = 0;
+    int kind = 0;                // 0: device destination, 1: host destination (their kernel times differ: PCIe stores)
     std::vector<uint64_t> cuts;  // nd + 1 entries, cuts[0] = xa, cuts[nd] = xb
     bool valid = false;          // cuts hold a measured split for the key above
     bool pending = false;        // a call with these cuts is in flight / finished and its timings were not used yet

@@ -58,6 +58,9 @@ constexpr int BX = (int)GRID_BRICK_X, BY = 8;  // a block of 4 warps covers a 4 
 #define RUN_SEED_BLOCKS 5  // resident blocks per SM assumed when choosing how far back the seeds come from
 #endif
 constexpr int RUN_WARPS = 4;
+#ifndef RUN_FLUSH_AT
+#define RUN_FLUSH_AT 32  // queued (triangle, voxel) items that trigger the exact stage
+#endif
 
 enum : int { RUN_SIGN_NONE = 0, RUN_SIGN_RAYCAST = 1, RUN_SIGN_NORMAL = 2 };
 
@@ -68,7 +71,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
                    BuildStatus* __restrict__ st, uint32_t* tile_slot, const uint32_t seed_planes,
                    const Progress progress) {
     constexpr int NV = 32 * V;         // voxels per tile
-    constexpr int QCAP = 32 + 2 * NV;  // < 32 items left over + at most 2 leaves x NV voxels appended by one node
+    constexpr int QCAP = RUN_FLUSH_AT + 2 * NV;  // < RUN_FLUSH_AT items left over + at most 2 leaves x NV voxels appended by one node
     constexpr uint32_t BZR = 4u * V;   // brick extent in z
     constexpr bool NORMAL = SIGN == RUN_SIGN_NORMAL;
     __shared__ uint2 s_stack[RUN_WARPS][PKT_STACK];
@@ -270,7 +273,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     };
     uint32_t cur = 0u;  // the root: always an internal node; leaves are consumed at their parent
     for (;;) {
-        if (qn >= 32) flush(false);  // here, where the loop-carried state merges anyway
+        if (qn >= RUN_FLUSH_AT) flush(false);  // here, where the loop-carried state merges anyway
         PKT_COUNT(n_nodes);
         float2 dd[V];  // squared lower bounds of voxel i: (left child, right child)
         uint32_t lref, rref;

@@ -189,6 +189,10 @@ class Topology:
 
     def get_triangles(self, n_vertices: int) -> np.ndarray:
         """``Topology::get_triangles`` (``lib.rs:175-193``) → uint32 [nt, 3]."""
+        if self.kind == 0 and self.indices is not None and self.indices.dtype == np.uint32:
+            # a u32 triangle list IS its own expansion (tuples() drops a trailing partial triple): no copy
+            n3 = self.indices.size // 3
+            return self.indices[:3 * n3].reshape(n3, 3)
         L = lib()
         if self.indices is None:
             ptr, nbytes, n = None, 4, 0

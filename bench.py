@@ -568,10 +568,12 @@ def bench_post_passes(env, ctx, m2s, grid, d_sdf, cells, reps=10):
 
     ms = timed(lambda: ctx.grid_order_device(d_sdf.data_ptr(), cells, d_order.data_ptr(), d_mm.data_ptr()))
     b = 8 * cells + 8  # the grid read once, the order written once, (min, max)
+    sort_b = 60 * cells  # what the four radix passes move (csrc/m2s_sort.cuh): 4 + 12 | 16 | 16 | 12 bytes per cell
     out["grid_order"] = {"ms": ms, "Mcells_per_s": cells / ms / 1e3, "algorithmic_bytes": int(b),
                          "roofline_frac_hbm": b / (ms * 1e-3) / 1e9 / peak,
-                         "what": "m2s_grid_order_device: total-order keys -> cub::DeviceRadixSort::SortPairs (library) -> "
-                                 "min / max; the radix passes over (key, index) pairs are the sort's own traffic"}
+                         "sort_pass_bytes": int(sort_b), "sort_pass_frac_hbm": sort_b / (ms * 1e-3) / 1e9 / peak,
+                         "what": "m2s_grid_order_device: the library's own onesweep radix sort (4 x 8 bits, keys from the "
+                                 "distances on the fly, cell indices as payloads) + min / max; no library kernel"}
     n_pts = 4_000_000
     lo = torch.tensor(np.asarray(grid.first_cell), device=env.dev)
     hi = torch.tensor(np.asarray(grid.get_last_cell(), np.float32), device=env.dev)

@@ -944,7 +944,7 @@ void release_device(Device& d) {
     cudaSetDevice(d.ordinal);
     if (d.stream || !d.own_stream) cudaStreamSynchronize(d.stream);
     DevBuf* bufs[] = {&d.verts, &d.tris, &d.rec_orig, &d.tobb, &d.tri_lo, &d.tri_hi, &d.keys_in, &d.keys_out,
-                      &d.vals_in, &d.vals_out, &d.cub_tmp, &d.leaf_parent, &d.node_parent, &d.node_flag, &d.slot_list, &d.slot_count,
+                      &d.vals_in, &d.vals_out, &d.sort_tmp, &d.leaf_parent, &d.node_parent, &d.node_flag, &d.slot_list, &d.slot_count,
                       &d.call_status, &d.rows[0], &d.rows[1], &d.rows[2], &d.big_list, &d.big_count, &d.stats,
                       &d.tile_slot, &d.progress, &d.queries, &d.q_sorted, &d.q_perm, &d.q_keys_in, &d.q_keys_out,
                       &d.q_vals_in, &d.out, &d.post_keys, &d.post_idx, &d.post_mm, &d.post_in, &d.post_pts,

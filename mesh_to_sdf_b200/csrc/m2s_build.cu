@@ -8,11 +8,10 @@
 #include <algorithm>
 
 #include <cuda/atomic>
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include "m2s_geom.cuh"
 #include "m2s_internal.h"
+#include "m2s_sort.cuh"
 
 namespace m2s {
 
@@ -217,21 +216,19 @@ __device__ __forceinline__ uint64_t morton63(float x, float y, float z, const Bu
 // K2: Morton key of the centre of the padded box.
 __global__ void __launch_bounds__(256)
 k_tri_morton(const float4* __restrict__ tri_lo, const float4* __restrict__ tri_hi, uint32_t nt,
-             const BuildStatus* __restrict__ st, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+             const BuildStatus* __restrict__ st, uint64_t* __restrict__ keys) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const float4 l = tri_lo[t], h = tri_hi[t];
     keys[t] = morton63(0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z), st);
-    vals[t] = t;
 }
 
 __global__ void __launch_bounds__(256)
 k_point_morton(const float* __restrict__ q, uint32_t nq, const BuildStatus* __restrict__ st,
-               uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+               uint64_t* __restrict__ keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     keys[i] = morton63(q[3 * i], q[3 * i + 1], q[3 * i + 2], st);
-    vals[i] = i;
 }
 
 // query bounds (so that query Morton codes use a box that contains the queries) + finite check
@@ -943,33 +940,36 @@ cudaError_t launch_build(Device& d, MeshDev& m, const float* d_verts, uint64_t n
                                                   d.tri_hi.as<float4>(), st);
     if (after_records) CK(cudaEventRecord(after_records, s));
     k_tri_morton<<<blocks_for(nt, bs), bs, 0, s>>>(d.tri_lo.as<float4>(), d.tri_hi.as<float4>(), (uint32_t)nt, st,
-                                                   d.keys_in.as<uint64_t>(), d.vals_in.as<uint32_t>());
+                                                   d.keys_in.as<uint64_t>());
     d.launches += 2;
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.keys_in.as<uint64_t>(), d.keys_out.as<uint64_t>(),
-                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, MORTON_BITS, s));
-    CK(d.cub_tmp.ensure(tmp_bytes));
-    CK(cub::DeviceRadixSort::SortPairs(d.cub_tmp.p, tmp_bytes, d.keys_in.as<uint64_t>(), d.keys_out.as<uint64_t>(),
-                                       d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>(), (int)nt, 0, MORTON_BITS, s));
-    d.launches += 8;  // CUB onesweep: histogram + scan + 6 digit passes
+    // Morton order of the triangles: pass 0 reads keys_in and takes the positions as payloads (m2s_sort.cuh)
+    uint64_t* const kbuf[2] = {d.keys_out.as<uint64_t>(), d.keys_in.as<uint64_t>()};
+    uint32_t* const vbuf[2] = {d.vals_in.as<uint32_t>(), d.vals_out.as<uint32_t>()};
+    constexpr int SORTED = (MORTON_BITS / 8 - 1) & 1;  // buffer of the last pass
+    static_assert(MORTON_BITS % 8 == 0, "whole radix passes");
+    CK(d.sort_tmp.ensure(radix_sort_scratch_bytes(nt)));
+    CK(radix_sort_pairs(s, sort_detail::PtrSrc<uint64_t>{d.keys_in.as<uint64_t>()}, kbuf, vbuf, nt, MORTON_BITS,
+                        d.sort_tmp.p, true, &d.launches));
+    const uint64_t* keys_sorted = kbuf[SORTED];
+    const uint32_t* order = vbuf[SORTED];
     k_tri_permute<<<blocks_for(nt, bs), bs, 0, s>>>(d.rec_orig.as<float4>(), d.tri_lo.as<float4>(),
-                                                    d.vals_out.as<uint32_t>(), (uint32_t)nt, st,
+                                                    order, (uint32_t)nt, st,
                                                     m.rec_sorted.as<float4>(), d.tobb.as<float4>(),
                                                     m.tri_id_sorted.as<uint32_t>());
     d.launches++;
     if (nleaf > 1) {
         CK(cudaMemsetAsync(d.node_flag.p, 0, (size_t)nleaf * 4, s));
-        k_hierarchy<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(d.keys_out.as<uint64_t>(), (int)nleaf,
+        k_hierarchy<<<blocks_for(nleaf - 1, bs), bs, 0, s>>>(keys_sorted, (int)nleaf,
                                                              m.boxes.as<float4>(), d.leaf_parent.as<uint32_t>(),
                                                              d.node_parent.as<uint32_t>(), m.node_range.as<uint2>());
         // 54 KB of dynamic shared memory: opt-in per device (the attribute belongs to the current device's context)
         CK(cudaFuncSetAttribute(k_refit_windows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 REFIT_LEVELS * REFIT_WINDOW * 6 * 4));
         k_refit_windows<<<blocks_for(nleaf, REFIT_WINDOW), REFIT_WINDOW, REFIT_LEVELS * REFIT_WINDOW * 6 * 4, s>>>(
-            d.tri_lo.as<float4>(), d.tri_hi.as<float4>(), d.vals_out.as<uint32_t>(), (int)nleaf, m.boxes.as<float4>(),
+            d.tri_lo.as<float4>(), d.tri_hi.as<float4>(), order, (int)nleaf, m.boxes.as<float4>(),
             m.node_range.as<uint2>());
         k_refit_climb<<<blocks_for((uint64_t)2 * nleaf - 1, bs), bs, 0, s>>>(
-            d.tri_lo.as<float4>(), d.tri_hi.as<float4>(), d.vals_out.as<uint32_t>(), (int)nleaf, m.boxes.as<float4>(),
+            d.tri_lo.as<float4>(), d.tri_hi.as<float4>(), order, (int)nleaf, m.boxes.as<float4>(),
             d.leaf_parent.as<uint32_t>(), d.node_parent.as<uint32_t>(), m.node_range.as<uint2>(),
             d.node_flag.as<uint32_t>());
         d.launches++;
@@ -1054,14 +1054,12 @@ cudaError_t launch_ray_bins(Device& d, MeshDev& m) {
     k_raybins<0><<<blocks_for(nt, 256), 256, 0, s>>>(rec, nt, st, R, cursor, nullptr, nullptr, m.bin_big.as<uint32_t>(),
                                                      meta, capacity);
     k_raybins_verdict<<<1, 32, 0, s>>>(meta, capacity);
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cursor, offsets, (int)(cells + 1), s));
-    CK(d.cub_tmp.ensure(tmp_bytes));
-    CK(cub::DeviceScan::ExclusiveSum(d.cub_tmp.p, tmp_bytes, cursor, offsets, (int)(cells + 1), s));
+    CK(d.sort_tmp.ensure(exclusive_scan_scratch_bytes(cells + 1)));
+    CK(exclusive_scan_u32(s, cursor, offsets, cells + 1, d.sort_tmp.p));
     CK(cudaMemsetAsync(m.bin_cursor.p, 0, (cells + 1) * 4, s));
     k_raybins<1><<<blocks_for(nt, 256), 256, 0, s>>>(rec, nt, st, R, cursor, offsets, m.bin_items.as<uint32_t>(),
                                                      m.bin_big.as<uint32_t>(), meta, capacity);
-    d.launches += 5;  // two bin passes, the verdict, the scan's two kernels
+    d.launches += 4;  // two bin passes, the verdict, the scan
     m.bvh.bins = RayBins{R, offsets, m.bin_items.as<uint32_t>(), m.bin_big.as<uint32_t>(), meta, st};
     m.bins_built = true;
     return cudaGetLastError();
@@ -1079,18 +1077,16 @@ cudaError_t sort_queries(Device& d, const float* d_queries, uint64_t nq) {
     CK(d.q_vals_in.ensure(nq * 4));
     CK(d.q_perm.ensure(nq * 4));
     k_point_bounds<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, (uint32_t)nq, st);
-    k_point_morton<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, (uint32_t)nq, st, d.q_keys_in.as<uint64_t>(),
-                                                     d.q_vals_in.as<uint32_t>());
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.q_keys_in.as<uint64_t>(), d.q_keys_out.as<uint64_t>(),
-                                       d.q_vals_in.as<uint32_t>(), d.q_perm.as<uint32_t>(), (int)nq, 0, MORTON_BITS, s));
-    CK(d.cub_tmp.ensure(tmp_bytes));
-    CK(cub::DeviceRadixSort::SortPairs(d.cub_tmp.p, tmp_bytes, d.q_keys_in.as<uint64_t>(),
-                                       d.q_keys_out.as<uint64_t>(), d.q_vals_in.as<uint32_t>(),
-                                       d.q_perm.as<uint32_t>(), (int)nq, 0, MORTON_BITS, s));
+    k_point_morton<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, (uint32_t)nq, st, d.q_keys_in.as<uint64_t>());
+    uint64_t* const kbuf[2] = {d.q_keys_out.as<uint64_t>(), d.q_keys_in.as<uint64_t>()};
+    uint32_t* const vbuf[2] = {d.q_vals_in.as<uint32_t>(), d.q_perm.as<uint32_t>()};
+    static_assert(((MORTON_BITS / 8 - 1) & 1) == 1, "the last pass must write q_perm");
+    CK(d.sort_tmp.ensure(radix_sort_scratch_bytes(nq)));
+    CK(radix_sort_pairs(s, sort_detail::PtrSrc<uint64_t>{d.q_keys_in.as<uint64_t>()}, kbuf, vbuf, nq, MORTON_BITS,
+                        d.sort_tmp.p, false, &d.launches));
     k_point_gather<<<blocks_for(nq, bs), bs, 0, s>>>(d_queries, d.q_perm.as<uint32_t>(), (uint32_t)nq,
                                                      d.q_sorted.as<float4>());
-    d.launches += 11;
+    d.launches += 3;
     return cudaGetLastError();
 }
 

@@ -169,7 +169,7 @@ struct Device {
 
     DevBuf verts, tris;           // staging for the host entry points
     // build scratch (dead after launch_build)
-    DevBuf rec_orig, tobb, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, cub_tmp;
+    DevBuf rec_orig, tobb, tri_lo, tri_hi, keys_in, keys_out, vals_in, vals_out, sort_tmp;
     DevBuf leaf_parent, node_parent, node_flag;
     DevBuf slot_list, slot_count; // child slots whose box is fitted by a whole warp (k_search_nodes_big)
     MeshDev scratch;              // the mesh of the one-shot entry points

@@ -10,15 +10,14 @@
 // Both are HBM-bound streaming passes (4 B read + 4..8 B written per cell / 12 B + 32 B gathered per sample).
 #include <algorithm>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "m2s_geom.cuh"
 #include "m2s_internal.h"
+#include "m2s_sort.cuh"
 
 namespace m2s {
 namespace {
 
-// f32::total_cmp as an unsigned key: -NaN < -inf < ... < -0 < +0 < ... < +inf < NaN
+// f32::total_cmp as an unsigned key (the sort computes the same key on the fly: sort_detail::F32TotalOrderSrc)
 __device__ __forceinline__ uint32_t total_order_key(float v) {
     const uint32_t b = __float_as_uint(v);
     return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
@@ -30,20 +29,13 @@ __device__ __forceinline__ uint32_t total_order_key(float v) {
 __device__ __forceinline__ uint32_t partial_order_key(float v) { return total_order_key(v == 0.0f ? 0.0f : v); }
 
 __global__ void __launch_bounds__(256)
-k_order_keys(const float* __restrict__ sdf, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
-             unsigned long long* __restrict__ mm) {
+k_order_limits(const float* __restrict__ sdf, uint32_t n, unsigned long long* __restrict__ mm) {
     unsigned long long lo = ~0ull, hi = 0ull;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float v = __ldg(sdf + i);
-        if (keys) {
-            keys[i] = total_order_key(v);
-            idx[i] = i;
-        }
-        const unsigned long long pk = ((unsigned long long)partial_order_key(v) << 32) | i;
+        const unsigned long long pk = ((unsigned long long)partial_order_key(__ldg(sdf + i)) << 32) | i;
         lo = pk < lo ? pk : lo;
         hi = pk > hi ? pk : hi;
     }
-    if (!mm) return;
     for (int o = 16; o; o >>= 1) {
         const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
         lo = l2 < lo ? l2 : lo;
@@ -157,32 +149,25 @@ cudaError_t launch_grid_order(Device& d, const float* d_sdf, uint64_t n, uint32_
     cudaStream_t s = d.stream;
     if (n == 0) return cudaSuccess;
     const uint32_t n32 = (uint32_t)n;
-    CK(d.post_mm.ensure(16));
-    unsigned long long* mm = d.post_mm.as<unsigned long long>();
     if (d_minmax) {
+        CK(d.post_mm.ensure(16));
+        unsigned long long* mm = d.post_mm.as<unsigned long long>();
         CK(cudaMemsetAsync(mm, 0xff, 8, s));
         CK(cudaMemsetAsync(mm + 1, 0x00, 8, s));
+        const unsigned nb = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)d.sm_count * 8);
+        k_order_limits<<<nb, 256, 0, s>>>(d_sdf, n32, mm);
+        k_order_minmax<<<1, 1, 0, s>>>(d_sdf, mm, d_minmax);
+        d.launches += 2;
     }
-    uint32_t *keys = nullptr, *idx = nullptr;
     if (d_order) {
+        // four 8-bit passes over the total-order keys, computed from the distances on the fly in pass 0; the payloads
+        // (cell indices) of the last pass land in the caller's array and its keys are not written (m2s_sort.cuh)
         CK(d.post_keys.ensure(n * 4 * 2));
         CK(d.post_idx.ensure(n * 4));
-        keys = d.post_keys.as<uint32_t>();
-        idx = d.post_idx.as<uint32_t>();
-    }
-    const unsigned nb = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)d.sm_count * 8);
-    k_order_keys<<<nb, 256, 0, s>>>(d_sdf, n32, keys, idx, d_minmax ? mm : nullptr);
-    d.launches++;
-    if (d_order) {
-        size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys + n, idx, d_order, (int)n32, 0, 32, s));
-        CK(d.cub_tmp.ensure(tmp));
-        CK(cub::DeviceRadixSort::SortPairs(d.cub_tmp.p, tmp, keys, keys + n, idx, d_order, (int)n32, 0, 32, s));  // stable
-        d.launches += 5;
-    }
-    if (d_minmax) {
-        k_order_minmax<<<1, 1, 0, s>>>(d_sdf, mm, d_minmax);
-        d.launches++;
+        CK(d.sort_tmp.ensure(radix_sort_scratch_bytes(n)));
+        uint32_t* const kbuf[2] = {d.post_keys.as<uint32_t>(), d.post_keys.as<uint32_t>() + n};
+        uint32_t* const vbuf[2] = {d.post_idx.as<uint32_t>(), d_order};
+        CK(radix_sort_pairs(s, sort_detail::F32TotalOrderSrc{d_sdf}, kbuf, vbuf, n, 32, d.sort_tmp.p, false, &d.launches));
     }
     return cudaGetLastError();
 }

@@ -46,6 +46,18 @@ def test_library_does_not_link_the_oracle_or_python(m2s):
     assert "oracle" not in out and "python" not in out and "torch" not in out
 
 
+def test_library_contains_no_library_kernels(m2s):
+    """Every kernel of the product is hand-written: the radix sort and the scan are csrc/m2s_sort.cuh, no cub /
+    thrust instantiation is linked in, and no source of the product includes them."""
+    out = subprocess.run(["nm", "-C", m2s.LIB_PATH], capture_output=True, text=True).stdout
+    assert "k_sort_onesweep" in out and "k_exclusive_scan_u32" in out
+    assert "cub::" not in out and "thrust::" not in out
+    csrc = os.path.join(ROOT, "mesh_to_sdf_b200", "csrc")
+    for f in os.listdir(csrc):
+        src = open(os.path.join(csrc, f), errors="ignore").read()
+        assert not re.search(r"#include\s*<(cub|thrust)/", src), f
+
+
 def test_header_compiles_as_c():
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
                        capture_output=True, text=True)

@@ -61,17 +61,29 @@ def test_sample_oracle_properties():
 
 # ---- CUDA kernels against the oracle (GPU) -----------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 31, 1000, 262_144 + 17])
+@pytest.mark.parametrize("n", [1, 31, 1000, 4096, 4097, 12_289, 262_144 + 17, 2_000_003])
 def test_gpu_grid_order_matches_oracle(m2s, n):
+    # sizes around the 4096-pair tiles of the radix sort (csrc/m2s_sort.cuh): one tile, a full tile, a tile with a
+    # single pair, many tiles with look-back
     rng = np.random.default_rng(n)
     a = rng.standard_normal(n).astype(np.float32)
     a[rng.integers(0, n, n // 3 + 1)] = np.float32(0.5)  # many ties -> stability matters
     if n > 8:
         a[3], a[5] = 0.0, -0.0
+    if n > 64:  # every class f32::total_cmp orders: NaNs of both signs, infinities, denormals
+        a[7:13] = np.array([0x7fc00000, 0xffc00000, 0x7f800000, 0xff800000, 0x00000001, 0x80000001], np.uint32).view(np.float32)
+        a[40:60] *= np.float32(1e-30)  # spread over many exponents
     with m2s.Context() as c:
         order, (lo, hi) = c.grid_order(a)
     assert np.array_equal(order, post.grid_order(a))
-    wlo, whi = post.minmax(a)
+    if not np.isnan(a).any():  # itertools::minmax over PartialOrd has no defined answer with NaNs
+        wlo, whi = post.minmax(a)
+        assert lo.tobytes() == wlo.tobytes() and hi.tobytes() == whi.tobytes()
+    b = np.where(np.isnan(a), np.float32(0.25), a)  # the same array without NaNs: iso limits as well
+    with m2s.Context() as c:
+        order, (lo, hi) = c.grid_order(b)
+    assert np.array_equal(order, post.grid_order(b))
+    wlo, whi = post.minmax(b)
     assert lo.tobytes() == wlo.tobytes() and hi.tobytes() == whi.tobytes()
 
 

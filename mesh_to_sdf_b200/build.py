@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libm2s.so")
 SOURCES = ["m2s_build.cu", "m2s_grid.cu", "m2s_points.cu", "m2s_post.cu", "m2s_api.cu"]
-HEADERS = ["m2s_geom.cuh", "m2s_search.cuh", "m2s_internal.h", os.path.join("..", "..", "include", "m2s.h")]
+HEADERS = ["m2s_geom.cuh", "m2s_search.cuh", "m2s_sort.cuh", "m2s_internal.h", os.path.join("..", "..", "include", "m2s.h")]
 
 NVCC_COMPILE = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -146,7 +146,7 @@ m2s_status check_grid(m2s_ctx* ctx, const float first[3], const float size[3], c
 }
 
 m2s_status check_queries(m2s_ctx* ctx, uint64_t nq) {
-    // the Morton sort of the queries counts its items in an int (cub::DeviceRadixSort)
+    // queries are indexed with 32 bits on the device (sort payloads, packet bases)
     if (nq >= (1ull << 31)) return fail(ctx, M2S_EINVAL, "more than 2^31-1 query points");
     return M2S_OK;
 }

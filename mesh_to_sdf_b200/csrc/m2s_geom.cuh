@@ -65,47 +65,28 @@ __device__ __forceinline__ f3 closest_point_triangle(f3 p, f3 a, f3 b, f3 c) {
     const float d5 = v_dot(ab, cp);
     const float d6 = v_dot(ac, cp);
     if (d6 >= 0.0f && d5 <= d6) return c;
-    // The three edge regions and the face region each end in ONE IEEE division (geo.rs:113, :120, :129, :133) and
-    // they diverge inside a warp: every region hands (numerator, denominator) to a single division site where the
-    // lanes of all four have reconverged, then finishes with its own expression. Same operations, same order per
-    // region - bit-identical to the cascade of early returns.
     const float vc = fsub(fmul(d1, d4), fmul(d3, d2));
-    float num, den, vb = 0.0f;
-    int region;  // 0: edge ab, 1: edge ac, 2: edge bc, 3: face
     if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
-        num = d1;
-        den = fsub(d1, d3);
-        region = 0;
-    } else {
-        vb = fsub(fmul(d5, d2), fmul(d1, d6));
-        if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
-            num = d2;
-            den = fsub(d2, d6);
-            region = 1;
-        } else {
-            const float va = fsub(fmul(d3, d6), fmul(d5, d4));
-            const float d43 = fsub(d4, d3);
-            const float d56 = fsub(d5, d6);
-            if (va <= 0.0f && d43 >= 0.0f && d56 >= 0.0f) {
-                num = d43;
-                den = fadd(d43, d56);
-                region = 2;
-            } else {
-                num = 1.0f;
-                den = fadd(fadd(va, vb), vc);
-                region = 3;
-            }
-        }
+        const float v = fdiv(d1, fsub(d1, d3));
+        return v_add(a, v_fmul(ab, v));
     }
-    const float q = fdiv(num, den);
-    if (region == 3) {
-        const float v = fmul(vb, q);
-        const float w = fmul(vc, q);
-        return v_add(v_add(a, v_fmul(ab, v)), v_fmul(ac, w));
+    const float vb = fsub(fmul(d5, d2), fmul(d1, d6));
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        const float v = fdiv(d2, fsub(d2, d6));
+        return v_add(a, v_fmul(ac, v));
     }
-    const f3 base = region == 2 ? b : a;
-    const f3 edge = region == 0 ? ab : (region == 1 ? ac : v_sub(c, b));
-    return v_add(base, v_fmul(edge, q));
+    const float va = fsub(fmul(d3, d6), fmul(d5, d4));
+    const float d43 = fsub(d4, d3);
+    const float d56 = fsub(d5, d6);
+    if (va <= 0.0f && d43 >= 0.0f && d56 >= 0.0f) {
+        const float v = fdiv(d43, fadd(d43, d56));
+        const f3 bc = v_sub(c, b);
+        return v_add(b, v_fmul(bc, v));
+    }
+    const float denom = fdiv(1.0f, fadd(fadd(va, vb), vc));
+    const float v = fmul(vb, denom);
+    const float w = fmul(vc, denom);
+    return v_add(v_add(a, v_fmul(ab, v)), v_fmul(ac, w));
 }
 
 // src/geo.rs:70-138 including the degenerate guards :73-88.

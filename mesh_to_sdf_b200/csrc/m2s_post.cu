@@ -47,6 +47,30 @@ k_order_limits(const float* __restrict__ sdf, uint32_t n, unsigned long long* __
     }
 }
 
+// The same limits, taken on the sort's own read of the distances (its histogram kernel): the partial-order key differs
+// from the total-order key the sort sees only for -0.0, whose key 0x7fffffff becomes that of +0.0.
+struct LimitsObserver {
+    unsigned long long* mm;
+    unsigned long long lo = ~0ull, hi = 0ull;
+    __device__ __forceinline__ void see(uint32_t i, uint64_t total_key) {
+        const uint32_t k = (uint32_t)total_key == 0x7fffffffu ? 0x80000000u : (uint32_t)total_key;
+        const unsigned long long pk = ((unsigned long long)k << 32) | i;
+        lo = pk < lo ? pk : lo;
+        hi = pk > hi ? pk : hi;
+    }
+    __device__ __forceinline__ void finish() {
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+            lo = l2 < lo ? l2 : lo;
+            hi = h2 > hi ? h2 : hi;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(mm + 0, lo);
+            atomicMax(mm + 1, hi);
+        }
+    }
+};
+
 __global__ void k_order_minmax(const float* __restrict__ sdf, const unsigned long long* __restrict__ mm,
                                float* __restrict__ out) {
     out[0] = sdf[(uint32_t)mm[0]];
@@ -149,25 +173,33 @@ cudaError_t launch_grid_order(Device& d, const float* d_sdf, uint64_t n, uint32_
     cudaStream_t s = d.stream;
     if (n == 0) return cudaSuccess;
     const uint32_t n32 = (uint32_t)n;
+    unsigned long long* mm = nullptr;
     if (d_minmax) {
         CK(d.post_mm.ensure(16));
-        unsigned long long* mm = d.post_mm.as<unsigned long long>();
+        mm = d.post_mm.as<unsigned long long>();
         CK(cudaMemsetAsync(mm, 0xff, 8, s));
         CK(cudaMemsetAsync(mm + 1, 0x00, 8, s));
-        const unsigned nb = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)d.sm_count * 8);
-        k_order_limits<<<nb, 256, 0, s>>>(d_sdf, n32, mm);
-        k_order_minmax<<<1, 1, 0, s>>>(d_sdf, mm, d_minmax);
-        d.launches += 2;
     }
     if (d_order) {
         // four 8-bit passes over the total-order keys, computed from the distances on the fly in pass 0; the payloads
-        // (cell indices) of the last pass land in the caller's array and its keys are not written (m2s_sort.cuh)
+        // (cell indices) of the last pass land in the caller's array and its keys are not written (m2s_sort.cuh).
+        // The iso limits ride along on the histogram kernel's read of the distances.
         CK(d.post_keys.ensure(n * 4 * 2));
         CK(d.post_idx.ensure(n * 4));
         CK(d.sort_tmp.ensure(radix_sort_scratch_bytes(n)));
         uint32_t* const kbuf[2] = {d.post_keys.as<uint32_t>(), d.post_keys.as<uint32_t>() + n};
         uint32_t* const vbuf[2] = {d.post_idx.as<uint32_t>(), d_order};
-        CK(radix_sort_pairs(s, sort_detail::F32TotalOrderSrc{d_sdf}, kbuf, vbuf, n, 32, d.sort_tmp.p, false, &d.launches));
+        const sort_detail::F32TotalOrderSrc src{d_sdf};
+        if (d_minmax) CK(radix_sort_pairs(s, src, kbuf, vbuf, n, 32, d.sort_tmp.p, false, &d.launches, LimitsObserver{mm}));
+        else CK(radix_sort_pairs(s, src, kbuf, vbuf, n, 32, d.sort_tmp.p, false, &d.launches));
+    } else if (d_minmax) {
+        const unsigned nb = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)d.sm_count * 8);
+        k_order_limits<<<nb, 256, 0, s>>>(d_sdf, n32, mm);
+        d.launches++;
+    }
+    if (d_minmax) {
+        k_order_minmax<<<1, 1, 0, s>>>(d_sdf, mm, d_minmax);
+        d.launches++;
     }
     return cudaGetLastError();
 }

@@ -54,6 +54,12 @@ struct F32TotalOrderSrc {
     }
 };
 
+// The histogram kernel reads every key once; an observer rides along on that read (the iso limits of a grid).
+struct NoObserver {
+    __device__ __forceinline__ void see(uint32_t, uint64_t) {}
+    __device__ __forceinline__ void finish() {}
+};
+
 template <typename K>
 __device__ __forceinline__ uint32_t digit_of(K k, int shift) { return (uint32_t)(k >> shift) & (RADIX - 1); }
 
@@ -97,9 +103,9 @@ __device__ __forceinline__ void st_word(unsigned long long* p, unsigned long lon
 
 // Digit histograms of every pass in one read of the keys: shared-memory atomics, except that a warp whose 32 keys
 // share a digit (the rule for the upper digits of distances / Morton codes) adds 32 once.
-template <typename K, typename Src>
+template <typename K, typename Src, typename Obs>
 __global__ void __launch_bounds__(THREADS)
-k_sort_histograms(Src src, uint32_t n, int passes, uint32_t* __restrict__ hist /* [passes][RADIX] */) {
+k_sort_histograms(Src src, uint32_t n, int passes, uint32_t* __restrict__ hist /* [passes][RADIX] */, Obs obs) {
     __shared__ uint32_t sh[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS) sh[i] = 0;
     __syncthreads();
@@ -115,6 +121,7 @@ k_sort_histograms(Src src, uint32_t n, int passes, uint32_t* __restrict__ hist /
             const uint64_t i = base + 32 * u + lane;
             valid[u] = i < n;
             k[u] = valid[u] ? src((uint32_t)i) : K(0);
+            if (valid[u]) obs.see((uint32_t)i, (uint64_t)k[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -133,6 +140,7 @@ k_sort_histograms(Src src, uint32_t n, int passes, uint32_t* __restrict__ hist /
     __syncthreads();
     for (int i = threadIdx.x; i < passes * RADIX; i += THREADS)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    obs.finish();
 }
 
 // counts -> exclusive prefixes, one block per pass
@@ -404,9 +412,9 @@ inline size_t radix_sort_scratch_bytes(uint64_t n) {
 // the element positions 0..n-1 as payloads; pass i writes kbuf[i & 1] / vbuf[i & 1], so the result is in buffer
 // (passes - 1) & 1. The last pass writes keys only if keys_of_result. n < 2^32; launches (optional) is bumped by
 // the number of kernels enqueued.
-template <typename K, typename Src>
+template <typename K, typename Src, typename Obs = sort_detail::NoObserver>
 cudaError_t radix_sort_pairs(cudaStream_t s, Src src, K* const kbuf[2], uint32_t* const vbuf[2], uint64_t n, int key_bits,
-                             void* scratch, bool keys_of_result, uint64_t* launches = nullptr) {
+                             void* scratch, bool keys_of_result, uint64_t* launches = nullptr, Obs obs = Obs{}) {
     using namespace sort_detail;
     const int passes = radix_sort_passes(key_bits);
     if (n == 0 || passes == 0 || passes > MAX_PASSES) return n == 0 ? cudaSuccess : cudaErrorInvalidValue;
@@ -417,7 +425,7 @@ cudaError_t radix_sort_pairs(cudaStream_t s, Src src, K* const kbuf[2], uint32_t
     cudaError_t e = cudaMemsetAsync(scratch, 0, radix_sort_scratch_bytes(n), s);
     if (e != cudaSuccess) return e;
     const unsigned hist_blocks = (unsigned)(tiles < 148u * 8u ? tiles : 148u * 8u);  // a tile = 4 steps of a block
-    k_sort_histograms<K, Src><<<hist_blocks, THREADS, 0, s>>>(src, (uint32_t)n, passes, hist);
+    k_sort_histograms<K, Src, Obs><<<hist_blocks, THREADS, 0, s>>>(src, (uint32_t)n, passes, hist, obs);
     k_sort_digit_offsets<<<passes, RADIX, 0, s>>>(hist);
     constexpr size_t smem = onesweep_smem_bytes<K>();
     if (smem > 48 * 1024) {  // opt-in above 48 KB; the attribute belongs to the current device's context

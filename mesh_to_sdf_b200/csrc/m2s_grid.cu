@@ -57,15 +57,24 @@ constexpr int BX = (int)GRID_BRICK_X, BY = 8;  // a block of 4 warps covers a 4 
 #ifndef RUN_SEED_BLOCKS
 #define RUN_SEED_BLOCKS 5  // resident blocks per SM assumed when choosing how far back the seeds come from
 #endif
-constexpr int RUN_WARPS = 4;
+constexpr int RUN_WARPS = 4;  // warp tiles per brick
+#ifndef RUN_BLOCK_WARPS
+#define RUN_BLOCK_WARPS 1  // warps per thread block: a brick is computed by RUN_WARPS / RUN_BLOCK_WARPS consecutive blocks
+#endif
+constexpr int RUN_SPLIT = RUN_WARPS / RUN_BLOCK_WARPS;
 #ifndef RUN_FLUSH_AT
 #define RUN_FLUSH_AT 32  // queued (triangle, voxel) items that trigger the exact stage
 #endif
 
 enum : int { RUN_SIGN_NONE = 0, RUN_SIGN_RAYCAST = 1, RUN_SIGN_NORMAL = 2 };
+#ifdef M2S_STATS_ITEMS
+#define PKT_COUNT_LEAF(x)
+#else
+#define PKT_COUNT_LEAF(x) PKT_COUNT(x)
+#endif
 
 template <int SIGN, int V, int LAYOUT>
-__global__ void __launch_bounds__(32 * RUN_WARPS, RUN_MIN_BLOCKS)
+__global__ void __launch_bounds__(32 * RUN_BLOCK_WARPS, RUN_MIN_BLOCKS * RUN_SPLIT)
 k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
                    const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
                    BuildStatus* __restrict__ st, uint32_t* tile_slot, const uint32_t seed_planes,
@@ -74,21 +83,23 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     constexpr int QCAP = RUN_FLUSH_AT + 2 * NV;  // < RUN_FLUSH_AT items left over + at most 2 leaves x NV voxels appended by one node
     constexpr uint32_t BZR = 4u * V;   // brick extent in z
     constexpr bool NORMAL = SIGN == RUN_SIGN_NORMAL;
-    __shared__ uint2 s_stack[RUN_WARPS][PKT_STACK];
-    __shared__ uint2 s_queue[RUN_WARPS][QCAP];             // exact items: (triangle slot | degen, owner voxel = i * 32 + lane)
-    __shared__ unsigned long long s_best[RUN_WARPS][NV];   // per owner voxel: (d2 bits << 32) | [negative bit] | slot
-    __shared__ uint32_t s_pos[RUN_WARPS][NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
+    __shared__ uint2 s_stack[RUN_BLOCK_WARPS][PKT_STACK];
+    __shared__ uint2 s_queue[RUN_BLOCK_WARPS][QCAP];             // exact items: (triangle slot | degen, owner voxel = i * 32 + lane)
+    __shared__ unsigned long long s_best[RUN_BLOCK_WARPS][NV];   // per owner voxel: (d2 bits << 32) | [negative bit] | slot
+    __shared__ uint32_t s_pos[RUN_BLOCK_WARPS][NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
     const unsigned full = 0xffffffffu;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t lwarp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    // brick and warp tile of this warp: RUN_SPLIT consecutive blocks share a brick
+    const uint32_t brick = blockIdx.x / RUN_SPLIT, warp = (blockIdx.x % RUN_SPLIT) * RUN_BLOCK_WARPS + lwarp;
     const unsigned lt_mask = (1u << lane) - 1u;
-    uint2* const stack = s_stack[warp];
-    uint2* const queue = s_queue[warp];
-    unsigned long long* const best = s_best[warp];
-    uint32_t* const pos = s_pos[warp];
+    uint2* const stack = s_stack[lwarp];
+    uint2* const queue = s_queue[lwarp];
+    unsigned long long* const best = s_best[lwarp];
+    uint32_t* const pos = s_pos[lwarp];
 
     // bricks numbered z fastest, x slowest: consecutive blocks share tree nodes in L1 / L2
     const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZR - 1) / BZR;
-    uint32_t bid = blockIdx.x;
+    uint32_t bid = brick;
     const uint32_t bz = bid % nbz;
     bid /= nbz;
     const uint32_t by = bid % nby, bx = bid / nby;
@@ -115,7 +126,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         if (threadIdx.x == 0) {
             __threadfence();
             const uint32_t done = atomicAdd(progress.count + bx, 1u) + 1u;
-            if (done == nby * nbz) {
+            if (done == nby * nbz * RUN_SPLIT) {
                 __threadfence_system();
                 progress.flag[bx] = progress.epoch;
             }
@@ -155,11 +166,11 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     // the x-far voxels of a brick: LAYOUT 0 lanes 16..31 of the warps with wx = 1, LAYOUT 1 lanes 24..31 of every warp
     const uint32_t src_warp = LAYOUT == 0 ? (warp | 2u) : warp, src_idx = LAYOUT == 0 ? (lane & 15u) : (lane & 7u);
     const bool publishes = LAYOUT == 0 ? (lane >= 16u && (warp & 2u)) : ((lane >> 3) == 3u);
-    if (tile_slot && blockIdx.x >= back) {
-        nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - back) * RUN_WARPS + src_warp) * 16u + src_idx);
+    if (tile_slot && brick >= back) {
+        nseed = __ldcg(tile_slot + ((size_t)(brick - back) * RUN_WARPS + src_warp) * 16u + src_idx);
         // a straggler: the brick twice as far back has certainly finished (still a good radius)
-        if (nseed == 0xffffffffu && blockIdx.x >= 2u * back)
-            nseed = __ldcg(tile_slot + ((size_t)(blockIdx.x - 2u * back) * RUN_WARPS + src_warp) * 16u + src_idx);
+        if (nseed == 0xffffffffu && brick >= 2u * back)
+            nseed = __ldcg(tile_slot + ((size_t)(brick - 2u * back) * RUN_WARPS + src_warp) * 16u + src_idx);
     }
 #ifdef M2S_STATS_BUILD
     if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 3, 1ull);
@@ -218,6 +229,9 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     auto flush = [&](bool everything) {
         const int nb = everything ? (qn + 31) >> 5 : qn >> 5;
         if (nb == 0) return;
+#ifdef M2S_STATS_ITEMS  // development: the "leaves" counter counts exact (triangle, voxel) evaluations instead
+        n_leaves += (uint32_t)min(nb * 32, qn);
+#endif
         __syncwarp();
         for (int b = 0; b < nb; ++b) {
             const int idx = b * 32 + (int)lane;
@@ -292,14 +306,14 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             if (lref & LEAF_BIT) {
                 if (bl) {
                     enqueue(wl, (lref & LEAF_INDEX_MASK) | ((lref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                    PKT_COUNT(n_leaves);
+                    PKT_COUNT_LEAF(n_leaves);
                 }
                 bl = 0u;
             }
             if (rref & LEAF_BIT) {
                 if (br) {
                     enqueue(wr, (rref & LEAF_INDEX_MASK) | ((rref & LEAF_DEGEN_BIT) ? TRI_DEGEN_BIT : 0u));
-                    PKT_COUNT(n_leaves);
+                    PKT_COUNT_LEAF(n_leaves);
                 }
                 br = 0u;
             }
@@ -359,7 +373,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     if (tile_slot && publishes) {
         // the middle voxel of the run (the first one where the run is cut by the grid's end)
         if (valid[0])
-            __stcg(tile_slot + ((size_t)blockIdx.x * RUN_WARPS + warp) * 16u + src_idx,
+            __stcg(tile_slot + ((size_t)brick * RUN_WARPS + warp) * 16u + src_idx,
                    (valid[V / 2] ? slot[V / 2] : slot[0]) & ~(NORMAL ? RUN_NEG_BIT : 0u));
     }
 
@@ -653,7 +667,7 @@ static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams
     constexpr uint32_t BZR = 4u * V;
     const uint64_t nrun = (uint64_t)cdiv(g.x1 - g.x0, BX) * cdiv(g.ny, BY) * cdiv(g.nz, BZR);
     if (nrun == 0) return cudaSuccess;
-    if (nrun > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    if (nrun * RUN_SPLIT > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     const unsigned nbr = (unsigned)nrun;
     const float mag = grid_magnitude(g);
     BuildStatus* st = d.call_status.as<BuildStatus>();
@@ -674,13 +688,13 @@ static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams
     bvh.stats = d.want_stats ? d.stats.as<unsigned long long>() : nullptr;
 #endif
     if (rb)
-        k_grid_nearest_run<RUN_SIGN_RAYCAST, V, LAYOUT><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_RAYCAST, V, LAYOUT><<<nbr * RUN_SPLIT, 32 * RUN_BLOCK_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                               tile_slot, planes, pr);
     else if (mode == MODE_NORMAL)
-        k_grid_nearest_run<RUN_SIGN_NORMAL, V, LAYOUT><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_NORMAL, V, LAYOUT><<<nbr * RUN_SPLIT, 32 * RUN_BLOCK_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                              tile_slot, planes, pr);
     else
-        k_grid_nearest_run<RUN_SIGN_NONE, V, LAYOUT><<<nbr, 32 * RUN_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+        k_grid_nearest_run<RUN_SIGN_NONE, V, LAYOUT><<<nbr * RUN_SPLIT, 32 * RUN_BLOCK_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
                                                                            tile_slot, planes, pr);
     d.launches++;
     return cudaGetLastError();

@@ -204,17 +204,20 @@ __device__ __forceinline__ uint32_t ray_parities(const Bvh& bvh, const f3 o, con
 #ifndef PRUN_MIN_BLOCKS
 #define PRUN_MIN_BLOCKS 5
 #endif
+#ifndef PRUN_BLOCK_WARPS
+#define PRUN_BLOCK_WARPS 1  // packets per thread block: a block keeps its resources until its slowest warp is done
+#endif
 
 template <int MODE, int SIGN>
-__global__ void __launch_bounds__(128, PRUN_MIN_BLOCKS)
+__global__ void __launch_bounds__(32 * PRUN_BLOCK_WARPS, PRUN_MIN_BLOCKS * 4 / PRUN_BLOCK_WARPS)
 k_points_run(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, float* __restrict__ out,
              BuildStatus* __restrict__ st) {
     constexpr int QCAP = 32 + 2 * 32;
     constexpr bool NORMAL = MODE == MODE_NORMAL, ARGMIN = MODE == MODE_ARGMIN;
-    __shared__ uint2 s_stack[4][PKT_STACK];
-    __shared__ uint2 s_queue[4][QCAP];            // (triangle slot | degen, owner lane)
-    __shared__ unsigned long long s_best[4][32];  // per owner: (d2 bits << 32) | payload (see pack below)
-    __shared__ uint32_t s_pos[4][NORMAL ? 32 : 1];
+    __shared__ uint2 s_stack[PRUN_BLOCK_WARPS][PKT_STACK];
+    __shared__ uint2 s_queue[PRUN_BLOCK_WARPS][QCAP];            // (triangle slot | degen, owner lane)
+    __shared__ unsigned long long s_best[PRUN_BLOCK_WARPS][32];  // per owner: (d2 bits << 32) | payload (see pack below)
+    __shared__ uint32_t s_pos[PRUN_BLOCK_WARPS][NORMAL ? 32 : 1];
     const unsigned full = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -223,7 +226,7 @@ k_points_run(const Bvh bvh, const float4* __restrict__ q_sorted, uint32_t nq, fl
     unsigned long long* const best = s_best[warp];
     uint32_t* const pos = s_pos[warp];
 
-    const uint32_t base = (blockIdx.x * 4u + warp) * 32u;
+    const uint32_t base = (blockIdx.x * (uint32_t)PRUN_BLOCK_WARPS + warp) * 32u;
     if (base >= nq) return;  // warp-uniform
     const uint32_t idx = base + lane;
     const bool valid = idx < nq;
@@ -427,17 +430,17 @@ cudaError_t launch_points(Device& d, MeshDev& m, uint64_t nq, int mode, int sign
     // after sort_queries: the call's scene bounds now include the queries, which only the device knows
     CK(launch_nodes_interleave(d, m, 0.0f, true));
     if (sign_rule != 0 && !d.no_ray_bins) CK(launch_ray_bins(d, m));
-    const unsigned nbr = (unsigned)((nq + 127) / 128);
+    const unsigned nbr = (unsigned)((nq + 32 * PRUN_BLOCK_WARPS - 1) / (32 * PRUN_BLOCK_WARPS));
     Bvh bvh = m.bvh;
     if (d.no_ray_bins) bvh.bins = RayBins{};
 #ifdef M2S_STATS_BUILD
     bvh.stats = d.want_stats ? d.stats.as<unsigned long long>() : nullptr;
 #endif
-    if (mode == MODE_NORMAL) k_points_run<MODE_NORMAL, 0><<<nbr, 128, 0, s>>>(bvh, q, n, d_out, st);
-    else if (mode == MODE_ARGMIN) k_points_run<MODE_ARGMIN, 0><<<nbr, 128, 0, s>>>(bvh, q, n, d_out, st);
-    else if (sign_rule == 1) k_points_run<MODE_UNSIGNED, 1><<<nbr, 128, 0, s>>>(bvh, q, n, d_out, st);
-    else if (sign_rule == 3) k_points_run<MODE_UNSIGNED, 3><<<nbr, 128, 0, s>>>(bvh, q, n, d_out, st);
-    else k_points_run<MODE_UNSIGNED, 0><<<nbr, 128, 0, s>>>(bvh, q, n, d_out, st);
+    if (mode == MODE_NORMAL) k_points_run<MODE_NORMAL, 0><<<nbr, 32 * PRUN_BLOCK_WARPS, 0, s>>>(bvh, q, n, d_out, st);
+    else if (mode == MODE_ARGMIN) k_points_run<MODE_ARGMIN, 0><<<nbr, 32 * PRUN_BLOCK_WARPS, 0, s>>>(bvh, q, n, d_out, st);
+    else if (sign_rule == 1) k_points_run<MODE_UNSIGNED, 1><<<nbr, 32 * PRUN_BLOCK_WARPS, 0, s>>>(bvh, q, n, d_out, st);
+    else if (sign_rule == 3) k_points_run<MODE_UNSIGNED, 3><<<nbr, 32 * PRUN_BLOCK_WARPS, 0, s>>>(bvh, q, n, d_out, st);
+    else k_points_run<MODE_UNSIGNED, 0><<<nbr, 32 * PRUN_BLOCK_WARPS, 0, s>>>(bvh, q, n, d_out, st);
     d.launches++;
     return cudaGetLastError();
 }

@@ -52,7 +52,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 constexpr int BX = (int)GRID_BRICK_X, BY = 8;  // a block of 4 warps covers a 4 x 8 x 4V brick
 #ifndef RUN_MIN_BLOCKS
-#define RUN_MIN_BLOCKS 5
+#define RUN_MIN_BLOCKS 7
 #endif
 #ifndef RUN_SEED_BLOCKS
 #define RUN_SEED_BLOCKS 5  // resident blocks per SM assumed when choosing how far back the seeds come from

@@ -7,6 +7,7 @@
 // The leaf arithmetic (m2s_geom.cuh) is bit-identical to src/geo.rs; the tree only prunes, with a conservative
 // slack, so |d| equals the brute-force minimum of generic/default.rs bit for bit.
 #include <algorithm>
+#include <type_traits>
 
 #include "m2s_search.cuh"
 
@@ -58,10 +59,19 @@ constexpr int BX = (int)GRID_BRICK_X, BY = 8;  // a block of 4 warps covers a 4 
 #define RUN_SEED_BLOCKS 5  // resident blocks per SM assumed when choosing how far back the seeds come from
 #endif
 constexpr int RUN_WARPS = 4;  // warp tiles per brick
-#ifndef RUN_BLOCK_WARPS
-#define RUN_BLOCK_WARPS 1  // warps per thread block: a brick is computed by RUN_WARPS / RUN_BLOCK_WARPS consecutive blocks
+// One warp per thread block (a block of four warps held its registers and shared memory until its slowest warp was
+// done: -3 .. -4 % kernel time, -7 .. -11 % for the scattered-query kernel). On grids large enough to keep the device
+// busy with blocks twice as long (lane layout 0), a block computes TILES = 2 warp tiles one after the other along x -
+// the two x-halves of its half brick - and the second one starts from the first one's results: seeds from 1 - 2 cells
+// away, handed over in registers (C3: -4 % kernel time; the global seeds of a 256^3 grid come from 8 - 16 cells away,
+// because that is how thick the band of bricks in flight is).
+#ifndef RUN_TILES_X
+#define RUN_TILES_X 2
 #endif
-constexpr int RUN_SPLIT = RUN_WARPS / RUN_BLOCK_WARPS;
+#ifndef RUN_TILES_MIN_WAVES
+#define RUN_TILES_MIN_WAVES 8  // two tiles per block only from this many waves of resident blocks on
+#endif
+static_assert(RUN_TILES_X == 1 || RUN_TILES_X == 2, "a half brick has two x-halves");
 #ifndef RUN_FLUSH_AT
 #define RUN_FLUSH_AT 32  // queued (triangle, voxel) items that trigger the exact stage
 #endif
@@ -73,8 +83,8 @@ enum : int { RUN_SIGN_NONE = 0, RUN_SIGN_RAYCAST = 1, RUN_SIGN_NORMAL = 2 };
 #define PKT_COUNT_LEAF(x) PKT_COUNT(x)
 #endif
 
-template <int SIGN, int V, int LAYOUT>
-__global__ void __launch_bounds__(32 * RUN_BLOCK_WARPS, RUN_MIN_BLOCKS * RUN_SPLIT)
+template <int SIGN, int V, int LAYOUT, int TILES>
+__global__ void __launch_bounds__(32, RUN_MIN_BLOCKS * 4)
 k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, const uint32_t* __restrict__ px,
                    const uint32_t* __restrict__ py, const uint32_t* __restrict__ pz, float* __restrict__ out,
                    BuildStatus* __restrict__ st, uint32_t* tile_slot, const uint32_t seed_planes,
@@ -83,19 +93,17 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     constexpr int QCAP = RUN_FLUSH_AT + 2 * NV;  // < RUN_FLUSH_AT items left over + at most 2 leaves x NV voxels appended by one node
     constexpr uint32_t BZR = 4u * V;   // brick extent in z
     constexpr bool NORMAL = SIGN == RUN_SIGN_NORMAL;
-    __shared__ uint2 s_stack[RUN_BLOCK_WARPS][PKT_STACK];
-    __shared__ uint2 s_queue[RUN_BLOCK_WARPS][QCAP];             // exact items: (triangle slot | degen, owner voxel = i * 32 + lane)
-    __shared__ unsigned long long s_best[RUN_BLOCK_WARPS][NV];   // per owner voxel: (d2 bits << 32) | [negative bit] | slot
-    __shared__ uint32_t s_pos[RUN_BLOCK_WARPS][NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
+    static_assert(TILES == 1 || (TILES == 2 && LAYOUT == 0), "tiles of a block: one, or the two x-halves (layout 0)");
+    constexpr uint32_t BLOCKS_PER_BRICK = RUN_WARPS / TILES;
+    __shared__ uint2 stack[PKT_STACK];
+    __shared__ uint2 queue[QCAP];             // exact items: (triangle slot | degen, owner voxel = i * 32 + lane)
+    __shared__ unsigned long long best[NV];   // per owner voxel: (d2 bits << 32) | [negative bit] | slot
+    __shared__ uint32_t pos[NORMAL ? NV : 1];  // NORMAL: d2 bits of the nearest positive triangle
     const unsigned full = 0xffffffffu;
-    const uint32_t lwarp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    // brick and warp tile of this warp: RUN_SPLIT consecutive blocks share a brick
-    const uint32_t brick = blockIdx.x / RUN_SPLIT, warp = (blockIdx.x % RUN_SPLIT) * RUN_BLOCK_WARPS + lwarp;
+    const uint32_t lane = threadIdx.x;
+    // BLOCKS_PER_BRICK consecutive blocks share a brick
+    const uint32_t brick = blockIdx.x / BLOCKS_PER_BRICK, sub = blockIdx.x % BLOCKS_PER_BRICK;
     const unsigned lt_mask = (1u << lane) - 1u;
-    uint2* const stack = s_stack[lwarp];
-    uint2* const queue = s_queue[lwarp];
-    unsigned long long* const best = s_best[lwarp];
-    uint32_t* const pos = s_pos[lwarp];
 
     // bricks numbered z fastest, x slowest: consecutive blocks share tree nodes in L1 / L2
     const uint32_t nby = (g.ny + BY - 1) / BY, nbz = (g.nz + BZR - 1) / BZR;
@@ -103,6 +111,31 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     const uint32_t bz = bid % nbz;
     bid /= nbz;
     const uint32_t by = bid % nby, bx = bid / nby;
+    // every BLOCK reports the completion of its stores; the last block of a brick plane publishes the plane's flag
+    // in mapped host memory (the host copies finished planes while the kernel runs, m2s_api.cu): one thread releases
+    // the block's stores at device scope - cumulative over what the barrier made visible to it - and bumps the plane's
+    // counter; the block that completes the plane fences at system scope before it publishes the flag.
+    auto signal_done = [&]() {
+        if (progress.count == nullptr) return;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const uint32_t done = atomicAdd(progress.count + bx, 1u) + 1u;
+            if (done == nby * nbz * BLOCKS_PER_BRICK) {
+                __threadfence_system();
+                progress.flag[bx] = progress.epoch;
+            }
+        }
+    };
+    const float mag = fmaxf(scene_magnitude(st), grid_mag);
+    const float eps = 4.0e-6f * mag;
+    const float inv_s = pair_inv_scale(mag), inv_s2 = inv_s * inv_s;
+    int overflow = 0;
+    bool nan = false;
+    uint32_t carry = 0xffffffffu;  // nearest-triangle slot handed over by the previous tile of this block
+#pragma unroll 1
+    for (int tile = 0; tile < TILES; ++tile) {
+    const uint32_t warp = TILES == 2 ? (uint32_t)tile * 2u + sub : (TILES == 4 ? (uint32_t)tile : sub);  // (wx, wy) / (wy, wz)
     // first voxel of this lane's run (x relative to the slab start); a block of 4 warps covers a 4 x 8 x 4V brick
     //   LAYOUT 0: warp tile 2 x 4 x 4V - warps (wx, wy), lanes (lx:2, ly:4, run:4): compact where cells are thin in z
     //   LAYOUT 1: warp tile 4 x 4 x 2V - warps (wy, wz), lanes (lx:4, ly:4, run:2): compact where cells are cubic
@@ -115,26 +148,9 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
 #pragma unroll
     for (int i = 0; i < V; ++i) valid[i] = valid_xy && z0 + i < g.nz;
 
-    // every BLOCK reports the completion of its stores; the last block of a brick plane publishes the plane's flag
-    // in mapped host memory (the host copies finished planes while the kernel runs, m2s_api.cu). All four warps meet
-    // at a barrier (a block keeps its resources until its last warp exits anyway), then one thread releases the
-    // block's stores at device scope - cumulative over what the barrier made visible to it - and bumps the plane's
-    // counter; the block that completes the plane fences at system scope before it publishes the flag.
-    auto signal_done = [&]() {
-        if (progress.count == nullptr) return;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const uint32_t done = atomicAdd(progress.count + bx, 1u) + 1u;
-            if (done == nby * nbz * RUN_SPLIT) {
-                __threadfence_system();
-                progress.flag[bx] = progress.epoch;
-            }
-        }
-    };
     if (!__any_sync(full, valid[0])) {  // warp-uniform (voxel 0 is the first of the run to be valid)
-        signal_done();
-        return;
+        carry = 0xffffffffu;
+        continue;
     }
 
     const f3 p0 = {cell_center(g.fx, g.sx, x), cell_center(g.fy, g.sy, y), cell_center(g.fz, g.sz, z0)};
@@ -142,9 +158,6 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
 #pragma unroll
     for (int i = 1; i < V; ++i) step[i] = cell_center(g.fz, g.sz, z0 + i) - p0.z;
 
-    const float mag = fmaxf(scene_magnitude(st), grid_mag);
-    const float eps = 4.0e-6f * mag;
-    const float inv_s = pair_inv_scale(mag), inv_s2 = inv_s * inv_s;
     // (dist + slack)^2, rounded up a little: the squared search radius in scene units
     auto radius2_of = [&](float d2) {
         const float dist = sqrt_approx(d2);
@@ -157,7 +170,6 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     // Per-voxel results live in shared memory (best / pos): any lane improves any voxel of the tile with atomicMin.
     // Registers only keep what every node visit needs: the pruning bound of the lane's own voxels.
     float bnd[V];
-    bool nan = false;
 
     // Seed: the nearest triangle of the voxel with the same (y, z run) on the x-far face of the brick
     // `seed_planes` steps back in x, published by the warp that computed it.
@@ -166,7 +178,9 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     // the x-far voxels of a brick: LAYOUT 0 lanes 16..31 of the warps with wx = 1, LAYOUT 1 lanes 24..31 of every warp
     const uint32_t src_warp = LAYOUT == 0 ? (warp | 2u) : warp, src_idx = LAYOUT == 0 ? (lane & 15u) : (lane & 7u);
     const bool publishes = LAYOUT == 0 ? (lane >= 16u && (warp & 2u)) : ((lane >> 3) == 3u);
-    if (tile_slot && brick >= back) {
+    if (tile > 0) {
+        nseed = carry;  // the tile this block has just finished: its x-far voxel with the same (y, z run)
+    } else if (tile_slot && brick >= back) {
         nseed = __ldcg(tile_slot + ((size_t)(brick - back) * RUN_WARPS + src_warp) * 16u + src_idx);
         // a straggler: the brick twice as far back has certainly finished (still a good radius)
         if (nseed == 0xffffffffu && brick >= 2u * back)
@@ -213,7 +227,6 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     float max_b = warp_max_b();
 
     int qn = 0, sp = 0;  // warp-uniform
-    int overflow = 0;
     [[maybe_unused]] uint32_t n_nodes = 0, n_leaves = 0;
 
     // every lane calls it; w[i]: this lane's voxel i needs triangle `item`
@@ -376,6 +389,13 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
             __stcg(tile_slot + ((size_t)brick * RUN_WARPS + warp) * 16u + src_idx,
                    (valid[V / 2] ? slot[V / 2] : slot[0]) & ~(NORMAL ? RUN_NEG_BIT : 0u));
     }
+    if (TILES > 1) {
+        // ... and hand them to the next tile of this block: lane L continues from lane 16 + (L & 15), the voxel of
+        // the x-far half with the same (y, z run), 1 or 2 cells away
+        const uint32_t mine =
+            valid[0] ? ((valid[V / 2] ? slot[V / 2] : slot[0]) & ~(NORMAL ? RUN_NEG_BIT : 0u)) : 0xffffffffu;
+        carry = __shfl_sync(full, mine, 16 + (int)(lane & 15u));
+    }
 
     // sqrt is monotone: min sqrt = sqrt min
     float res[V];
@@ -416,8 +436,6 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         for (int i = 0; i < V; ++i)
             if (valid[i]) o[i] = res[i];
     }
-    signal_done();
-    if (overflow) atomicExch(&st->stack_overflow, 1);
 #ifdef M2S_STATS_BUILD
     if (bvh.stats && lane == 0) {
         atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
@@ -425,6 +443,10 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         atomicAdd(bvh.stats + 2, 1ull);
     }
 #endif
+    __syncwarp();  // the shared arrays are reused by the next tile
+    }  // tiles of this block
+    signal_done();
+    if (overflow) atomicExch(&st->stack_overflow, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -667,7 +689,7 @@ static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams
     constexpr uint32_t BZR = 4u * V;
     const uint64_t nrun = (uint64_t)cdiv(g.x1 - g.x0, BX) * cdiv(g.ny, BY) * cdiv(g.nz, BZR);
     if (nrun == 0) return cudaSuccess;
-    if (nrun * RUN_SPLIT > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    if (nrun * RUN_WARPS > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     const unsigned nbr = (unsigned)nrun;
     const float mag = grid_magnitude(g);
     BuildStatus* st = d.call_status.as<BuildStatus>();
@@ -687,15 +709,25 @@ static cudaError_t launch_grid_nearest_v(Device& d, MeshDev& m, const GridParams
 #ifdef M2S_STATS_BUILD
     bvh.stats = d.want_stats ? d.stats.as<unsigned long long>() : nullptr;
 #endif
-    if (rb)
-        k_grid_nearest_run<RUN_SIGN_RAYCAST, V, LAYOUT><<<nbr * RUN_SPLIT, 32 * RUN_BLOCK_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
-                                                                              tile_slot, planes, pr);
-    else if (mode == MODE_NORMAL)
-        k_grid_nearest_run<RUN_SIGN_NORMAL, V, LAYOUT><<<nbr * RUN_SPLIT, 32 * RUN_BLOCK_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
-                                                                             tile_slot, planes, pr);
+    auto launch = [&](auto tiles) {
+        constexpr int T = decltype(tiles)::value;
+        const unsigned blocks = nbr * (RUN_WARPS / T);
+        if (rb)
+            k_grid_nearest_run<RUN_SIGN_RAYCAST, V, LAYOUT, T><<<blocks, 32, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+                                                                                  tile_slot, planes, pr);
+        else if (mode == MODE_NORMAL)
+            k_grid_nearest_run<RUN_SIGN_NORMAL, V, LAYOUT, T><<<blocks, 32, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+                                                                                 tile_slot, planes, pr);
+        else
+            k_grid_nearest_run<RUN_SIGN_NONE, V, LAYOUT, T><<<blocks, 32, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
+                                                                               tile_slot, planes, pr);
+    };
+    // blocks of two tiles only where there are enough of them: on a small grid the longer blocks lengthen the tail
+    const uint64_t resident_blocks = (uint64_t)d.sm_count * RUN_MIN_BLOCKS * 4;
+    if (LAYOUT == 0 && RUN_TILES_X == 2 && nrun * 2 >= (uint64_t)RUN_TILES_MIN_WAVES * resident_blocks)
+        launch(std::integral_constant<int, LAYOUT == 0 ? 2 : 1>{});
     else
-        k_grid_nearest_run<RUN_SIGN_NONE, V, LAYOUT><<<nbr * RUN_SPLIT, 32 * RUN_BLOCK_WARPS, 0, s>>>(bvh, g, mag, b0, b1, b2, d_out, st,
-                                                                           tile_slot, planes, pr);
+        launch(std::integral_constant<int, 1>{});
     d.launches++;
     return cudaGetLastError();
 }

@@ -430,11 +430,11 @@ def timed_host_steps(env, call, steps, warmup=2):
     return s
 
 
-def run_kernel_name(sign, grid, n_tris, x_planes=None):
-    """Name of the distance kernel's instantiation for this launch: the library picks the run length V (voxels per
-    lane) per grid / mesh shape — csrc/m2s_grid.cu grid_run_length, restated here for the label only."""
-    nx = grid.cell_count[0] if x_planes is None else x_planes
-    cells = float(nx) * grid.cell_count[1] * grid.cell_count[2]
+def run_kernel_name(sign, grid, n_tris):
+    """Name of the distance kernel's instantiation: the library picks the run length V (voxels per lane) from the
+    shape of the WHOLE grid and the mesh, also for a slab of it — csrc/m2s_grid.cu grid_run_length, restated here
+    for the label only."""
+    cells = float(grid.cell_count[0]) * grid.cell_count[1] * grid.cell_count[2]
     sx, sy, sz = (abs(float(v)) for v in grid.cell_size)
     thin_z = 16.0 * sz <= 1.5 * max(2.0 * sx, 4.0 * sy)
     fine = cells >= 64.0 * n_tris
@@ -835,7 +835,7 @@ def bench_grid_multi(env, m2s, name, steps, warmup, balance=True):
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": grid_config(name, verts, tris, grid, sign, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(all_launches),
-        "roofline": roofline_block(run_kernel_name(sign, grid, len(tris), x1 - x0) + " (slowest rank's slab)", kern_ms, b_alg,
+        "roofline": roofline_block(run_kernel_name(sign, grid, len(tris)) + " (slowest rank's slab)", kern_ms, b_alg,
                                    f"k_grid_nearest_dram_bytes_per_launch_{name}", ISSUE_NOTE),
         "phases_ms": phases, "per_rank_phases_ms": rank_table, "single_gpu_same_workload": single,
         "slab_cuts": {"method": "equal shares of the measured per-slab kernel time over up to 8 untimed steps, frozen before "

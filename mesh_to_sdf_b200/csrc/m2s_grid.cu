@@ -51,7 +51,7 @@ namespace {
 // nearest with its own sign. Everything inside the near-tie window of the radius stays alive. Values can differ
 // from a triangle-order fold by the width of that window (compare_distances is not transitive); signs agree.
 // ---------------------------------------------------------------------------------------------------
-constexpr int BX = (int)GRID_BRICK_X, BY = 8;  // a block of 4 warps covers a 4 x 8 x 4V brick
+constexpr int BX = (int)GRID_BRICK_X, BY = 8;  // a brick = 4 warp tiles = 4 x 8 x 4V cells
 #ifndef RUN_MIN_BLOCKS
 #define RUN_MIN_BLOCKS 7
 #endif
@@ -136,7 +136,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
 #pragma unroll 1
     for (int tile = 0; tile < TILES; ++tile) {
     const uint32_t warp = TILES == 2 ? (uint32_t)tile * 2u + sub : (TILES == 4 ? (uint32_t)tile : sub);  // (wx, wy) / (wy, wz)
-    // first voxel of this lane's run (x relative to the slab start); a block of 4 warps covers a 4 x 8 x 4V brick
+    // first voxel of this lane's run (x relative to the slab start); the 4 warp tiles of a brick cover 4 x 8 x 4V cells
     //   LAYOUT 0: warp tile 2 x 4 x 4V - warps (wx, wy), lanes (lx:2, ly:4, run:4): compact where cells are thin in z
     //   LAYOUT 1: warp tile 4 x 4 x 2V - warps (wy, wz), lanes (lx:4, ly:4, run:2): compact where cells are cubic
     const uint32_t xr = bx * BX + (LAYOUT == 0 ? ((warp >> 1) & 1u) * 2u + (lane >> 4) : (lane >> 3));

@@ -21,6 +21,11 @@ grid = m2s.Grid.from_bounding_box(mn, mx, [n, n, n])
 d_out = torch.empty(n ** 3, dtype=torch.float32, device="cuda")
 stats = bool(os.environ.get("M2S_STATS"))
 with m2s.Context([0]) as ctx, ctx.mesh(verts, tris) as mesh:
+    if len(sys.argv) > 1 and sys.argv[1] == "ncu":  # two launches of one brick plane for a profiler capture
+        for _ in range(2):
+            mesh.grid_sdf_device(grid, 0, 192, 196, d_out.data_ptr() + 4 * 192 * n * n)
+            ctx.synchronize()
+        sys.exit(0)
     for v in (4, 2):
         ctx.set_option(m2s.OPT_RUN_LENGTH, v)
         whole = None

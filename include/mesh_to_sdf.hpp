@@ -5,8 +5,9 @@
 // surface is in rust/mesh_to_sdf.
 //
 //   Rust                                   C++ (namespace mesh_to_sdf)
-//   generate_sdf(&v, Topology, &q, accel)  generate_sdf(v, topology, q, accel)         -> std::vector<float>
-//   generate_grid_sdf(&v, Topology, &g, s) generate_grid_sdf(v, topology, grid, sign)  -> std::vector<float>
+//   generate_sdf(&v, Topology, &q, accel)  generate_sdf(v, topology, q, accel)         -> Distances (a std::vector<float>
+//                                                                                        that is not zero-filled first)
+//   generate_grid_sdf(&v, Topology, &g, s) generate_grid_sdf(v, topology, grid, sign)  -> Distances
 //   panic!                                 throws mesh_to_sdf::Panic
 //   trait Point                            any type with .x .y .z floats or operator[] (see point_traits)
 // Extensions that have no counterpart in the crate (they remove copies the GPU path would otherwise pay):
@@ -19,6 +20,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
+#include <new>
+#include <type_traits>
+#include <utility>
 #include <mutex>
 #include <optional>
 #include <stdexcept>
@@ -205,6 +210,30 @@ inline void check(m2s_ctx* c, m2s_status rc) {
     if (rc == M2S_EEMPTY) throw Panic(rc, "called `Option::unwrap()` on a `None` value (" + msg + ")");  // rtree.rs:117
     throw Panic(rc, "mesh_to_sdf backend error: " + msg);
 }
+// std::vector<float>(n) zero-fills its n floats on the calling thread: for a 256^3 grid that is 64 MiB of first-touch
+// page faults - several times the GPU's whole call - spent on values libm2s overwrites one and all. The results of this
+// facade are therefore vectors whose allocator default-initialises (no fill), which is what the reference's
+// `vec![0.0; n]` costs too (alloc_zeroed hands out untouched pages): the pages are first touched by the library's copy
+// threads, in parallel and while the GPU still computes.
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    default_init_allocator() = default;
+    template <class U>
+    default_init_allocator(const default_init_allocator<U>&) noexcept {}
+    template <class U>
+    struct rebind {
+        using other = default_init_allocator<U>;
+    };
+    template <class U>
+    void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+        ::new (static_cast<void*>(p)) U;
+    }
+    template <class U, class... A>
+    void construct(U* p, A&&... a) {
+        ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+
 template <class V>
 std::vector<float> pack(const std::vector<V>& v) {
     std::vector<float> out;
@@ -218,14 +247,18 @@ std::vector<float> pack(const std::vector<V>& v) {
 }
 }  // namespace detail
 
+// What generate_sdf / generate_grid_sdf return: a std::vector of f32 in every respect but one - resizing it does not
+// zero-fill (see detail::default_init_allocator).
+using Distances = std::vector<float, detail::default_init_allocator<float>>;
+
 // generate_sdf(vertices, indices, query_points, acceleration_method) -> Vec<f32>       (lib.rs:291-311)
 template <class V, class I>
-std::vector<float> generate_sdf(const std::vector<V>& vertices, Topology<I> indices, const std::vector<V>& query_points,
+Distances generate_sdf(const std::vector<V>& vertices, Topology<I> indices, const std::vector<V>& query_points,
                                 AccelerationMethod method = {}) {
     const std::vector<uint32_t> tris = indices.get_triangles(vertices.size());
     if (tris.empty() && method.kind == AccelerationMethod::RtreeBvh) return {};  // rtree_bvh.rs:104-106
     const std::vector<float> v = detail::pack(vertices), q = detail::pack(query_points);
-    std::vector<float> out(query_points.size());
+    Distances out(query_points.size());
     m2s_ctx* c = detail::context();
     std::lock_guard<std::mutex> lock(detail::call_mutex());
     detail::check(c, m2s_generate_sdf(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, q.data(),
@@ -235,8 +268,8 @@ std::vector<float> generate_sdf(const std::vector<V>& vertices, Topology<I> indi
 
 // generate_grid_sdf(vertices, indices, grid, sign_method) -> Vec<f32>                   (generate/grid.rs:265-378)
 template <class V, class I>
-std::vector<float> generate_grid_sdf(const std::vector<V>& vertices, Topology<I> indices, const Grid<V>& grid,
-                                     SignMethod sign_method = SignMethod::Raycast) {
+Distances generate_grid_sdf(const std::vector<V>& vertices, Topology<I> indices, const Grid<V>& grid,
+                            SignMethod sign_method = SignMethod::Raycast) {
     using T = point_traits<V>;
     const std::vector<uint32_t> tris = indices.get_triangles(vertices.size());
     const std::vector<float> v = detail::pack(vertices);
@@ -246,7 +279,7 @@ std::vector<float> generate_grid_sdf(const std::vector<V>& vertices, Topology<I>
     const uint64_t count[3] = {n[0], n[1], n[2]};
     // a pageable Vec like the reference's (generate/grid.rs:376): libm2s fills it from its pinned ring with host
     // threads while the kernel is still running (m2s_timings.host_path == M2S_PATH_PIPELINED for >= 4 MiB)
-    std::vector<float> out(grid.get_total_cell_count());
+    Distances out(grid.get_total_cell_count());
     m2s_ctx* c = detail::context();
     std::lock_guard<std::mutex> lock(detail::call_mutex());
     detail::check(c, m2s_generate_grid_sdf(c, v.data(), vertices.size(), tris.data(), tris.size() / 3, first, size, count,
@@ -335,21 +368,21 @@ class Mesh {
     Mesh(const Mesh&) = delete;
     Mesh& operator=(const Mesh&) = delete;
     ~Mesh() { m2s_mesh_destroy(h_); }
-    std::vector<float> generate_grid_sdf(const Grid<V>& grid, SignMethod sign_method = SignMethod::Raycast) const {
+    Distances generate_grid_sdf(const Grid<V>& grid, SignMethod sign_method = SignMethod::Raycast) const {
         using T = point_traits<V>;
         const V f = grid.get_first_cell(), s = grid.get_cell_size();
         const float first[3] = {T::x(f), T::y(f), T::z(f)}, size[3] = {T::x(s), T::y(s), T::z(s)};
         const auto n = grid.get_cell_count();
         const uint64_t count[3] = {n[0], n[1], n[2]};
-        std::vector<float> out(grid.get_total_cell_count());
+        Distances out(grid.get_total_cell_count());
         m2s_ctx* c = detail::context();
         std::lock_guard<std::mutex> lock(detail::call_mutex());
         detail::check(c, m2s_mesh_grid_sdf(c, h_, first, size, count, (int)sign_method, 0, n[0], out.data()));
         return out;
     }
-    std::vector<float> generate_sdf(const std::vector<V>& query_points, AccelerationMethod method = {}) const {
+    Distances generate_sdf(const std::vector<V>& query_points, AccelerationMethod method = {}) const {
         const std::vector<float> q = detail::pack(query_points);
-        std::vector<float> out(query_points.size());
+        Distances out(query_points.size());
         m2s_ctx* c = detail::context();
         std::lock_guard<std::mutex> lock(detail::call_mutex());
         const m2s_status rc = m2s_mesh_sdf(c, h_, q.data(), query_points.size(), (int)method.kind, (int)method.sign, out.data());
@@ -366,7 +399,8 @@ struct GridOrder {
     std::vector<uint32_t> ordered_indices;  // (0..n).sorted_by(|i, j| data[i].total_cmp(&data[j]))
     float min, max;                         // data.iter().copied().minmax()
 };
-inline GridOrder grid_order(const std::vector<float>& sdf) {
+template <class A>
+GridOrder grid_order(const std::vector<float, A>& sdf) {
     GridOrder r{std::vector<uint32_t>(sdf.size()), 0.0f, 0.0f};
     float mm[2] = {0.0f, 0.0f};
     m2s_ctx* c = detail::context();
@@ -381,9 +415,9 @@ enum class SampleMode { Snap = 0, Trilinear = 1, Tetrahedral = 2 };  // raymarch
 
 // sdf_grid(position, iso) at every point: 100.0 outside [first_cell, last_cell], else the snapped / interpolated
 // grid value minus iso — the "distance from any point with interpolation" of the TODO at src/grid.rs:172.
-template <class V>
-std::vector<float> sample_grid_sdf(const std::vector<float>& sdf, const Grid<V>& grid, const std::vector<V>& points,
-                                   SampleMode mode = SampleMode::Trilinear, float iso = 0.0f) {
+template <class V, class A>
+Distances sample_grid_sdf(const std::vector<float, A>& sdf, const Grid<V>& grid, const std::vector<V>& points,
+                          SampleMode mode = SampleMode::Trilinear, float iso = 0.0f) {
     using T = point_traits<V>;
     if (sdf.size() != grid.get_total_cell_count()) throw Panic(M2S_EINVAL, "sdf length does not match the grid");
     const V f = grid.get_first_cell(), s = grid.get_cell_size();
@@ -391,7 +425,7 @@ std::vector<float> sample_grid_sdf(const std::vector<float>& sdf, const Grid<V>&
     const auto n = grid.get_cell_count();
     const uint64_t count[3] = {n[0], n[1], n[2]};
     const std::vector<float> p = detail::pack(points);
-    std::vector<float> out(points.size());
+    Distances out(points.size());
     m2s_ctx* c = detail::context();
     std::lock_guard<std::mutex> lock(detail::call_mutex());
     detail::check(c, m2s_sample_grid_sdf(c, sdf.data(), first, size, count, p.data(), points.size(), (int)mode, iso,

@@ -124,6 +124,11 @@ static void test_host_paths_and_handles() {
     const auto topo = Topology<uint32_t>::triangle_list(indices);
     const auto sdf = generate_grid_sdf(vertices, topo, grid, SignMethod::Raycast);
     CHECK(last_timings().host_path == M2S_PATH_PIPELINED);  // the drop-in Vec<f32> path
+    // the result is a std::vector<float> that was never zero-filled by the calling thread (its pages are first touched
+    // by the library's copy threads); it converts to a plain vector by range
+    static_assert(std::is_same<std::remove_const_t<decltype(sdf)>, Distances>::value, "facade result type");
+    const std::vector<float> plain(sdf.begin(), sdf.end());
+    CHECK(plain.size() == grid.get_total_cell_count() && plain.back() == sdf.back());
     PinnedVec pinned;
     generate_grid_sdf_into(vertices, topo, grid, SignMethod::Raycast, pinned);
     CHECK(last_timings().host_path == M2S_PATH_ZEROCOPY && pinned.size() == sdf.size());

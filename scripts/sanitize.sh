@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over the shipped kernels: memcheck, racecheck, synccheck, initcheck on a 64^3
-# Raycast + Normal grid, a pipelined pageable copy, and a 50k-query C4-shaped call. Summaries -> gpurun_out/sanitize_*.log
+# Raycast + Normal grid, a pipelined pageable copy, a 50k-query C4-shaped call and the render order of the grid (radix sort). Summaries -> gpurun_out/sanitize_*.log
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -24,6 +24,8 @@ with m2s.Context() as c:
     with c.mesh(verts, tris) as mesh:
         mesh.grid_sdf(grid, 0)
         mesh.sdf(q[:5000], 3)
+    order, (lo, hi) = c.grid_order(a)  # the radix sort over 64 tiles (look-back), iso limits on its histogram read
+    assert np.all(np.diff(a[order]) >= 0) and lo == a.min() and hi == a.max()
 print("case ok", float(np.abs(a).sum()), float(np.abs(b).sum()))
 PY
 for tool in memcheck racecheck synccheck initcheck; do

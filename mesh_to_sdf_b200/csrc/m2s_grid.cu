@@ -186,7 +186,7 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
         if (nseed == 0xffffffffu && brick >= 2u * back)
             nseed = __ldcg(tile_slot + ((size_t)(brick - 2u * back) * RUN_WARPS + src_warp) * 16u + src_idx);
     }
-#ifdef M2S_STATS_BUILD
+#if defined(M2S_STATS_BUILD) && !defined(M2S_STATS_HEAVY)
     if (tile_slot && bvh.stats && lane == 0 && nseed == 0xffffffffu) atomicAdd(bvh.stats + 3, 1ull);
 #endif
     if (__any_sync(full, nseed >= bvh.nt)) {
@@ -438,8 +438,16 @@ k_grid_nearest_run(const Bvh bvh, const GridParams g, const float grid_mag, cons
     }
 #ifdef M2S_STATS_BUILD
     if (bvh.stats && lane == 0) {
+#ifdef M2S_STATS_HEAVY  // development: how heavy is the tail? node visits in / number of tiles above M2S_STATS_HEAVY visits, max
+        if (n_nodes > M2S_STATS_HEAVY) {
+            atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
+            atomicAdd(bvh.stats + 1, 1ull);
+        }
+        atomicMax(bvh.stats + 3, (unsigned long long)n_nodes);
+#else
         atomicAdd(bvh.stats + 0, (unsigned long long)n_nodes);
         atomicAdd(bvh.stats + 1, (unsigned long long)n_leaves);
+#endif
         atomicAdd(bvh.stats + 2, 1ull);
     }
 #endif

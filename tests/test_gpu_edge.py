@@ -179,6 +179,26 @@ def test_multi_device_context_matches_single(m2s):
                 assert np.array_equal(mesh.sdf(q, 3).view(np.uint32), qa.view(np.uint32))
 
 
+def test_duplicate_and_coincident_triangles_keep_the_distances(m2s, oracle):
+    # every triangle three times over (9 216 triangles: several tiles of the Morton radix sort, three equal keys each)
+    # plus 6 000 copies of ONE triangle (thousands of equal keys in a row: the sort's all-lanes-equal path, and a
+    # Karras tree that splits them by index only): unsigned distances are those of the plain mesh, bit for bit
+    verts, tris = synth.bumpy_torus(48, 32)
+    mn, mx = synth.padded_grid_box(verts)
+    grid = m2s.Grid.from_bounding_box(mn, mx, [20, 18, 22])
+    many = np.concatenate([tris, tris, tris, np.repeat(tris[1234:1235], 6000, axis=0)])
+    ctx = m2s.default_context()
+    plain = ctx.grid_sdf(verts, tris, grid, NORMAL)
+    dup = ctx.grid_sdf(verts, many, grid, NORMAL)
+    assert np.array_equal(np.abs(dup).view(np.uint32), np.abs(plain).view(np.uint32))
+    q = synth.splitmix64_points(3000, mn, mx)
+    a = ctx.sdf(verts, tris, q, 0, NORMAL)   # AccelerationMethod::None
+    b = ctx.sdf(verts, many, q, 3, NORMAL)   # RtreeBvh (queries Morton-sorted by the same radix sort)
+    assert np.array_equal(np.abs(a).view(np.uint32), np.abs(b).view(np.uint32))
+    want = oracle.grid_cells_exact(verts, tris, grid.first_cell, grid.cell_size, grid.cell_count, NORMAL)
+    assert np.max(np.abs(np.abs(plain) - np.abs(want))) <= 4e-6
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_triangle_soup(m2s, oracle, seed):
     # not a surface at all: intersecting, duplicated, coplanar, sliver and zero-area triangles, shared and

@@ -835,8 +835,9 @@ def bench_grid_multi(env, m2s, name, steps, warmup, balance=True):
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": grid_config(name, verts, tris, grid, sign, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(all_launches),
+        # traffic: no ncu capture of a slab launch exists (the committed one is the whole grid in one launch) -> null
         "roofline": roofline_block(run_kernel_name(sign, grid, len(tris)) + " (slowest rank's slab)", kern_ms, b_alg,
-                                   f"k_grid_nearest_dram_bytes_per_launch_{name}", ISSUE_NOTE),
+                                   None, ISSUE_NOTE),
         "phases_ms": phases, "per_rank_phases_ms": rank_table, "single_gpu_same_workload": single,
         "slab_cuts": {"method": "equal shares of the measured per-slab kernel time over up to 8 untimed steps, frozen before "
                                 "the warm-up" if balance else "equal widths",

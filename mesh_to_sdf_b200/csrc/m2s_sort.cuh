@@ -28,7 +28,13 @@ namespace sort_detail {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int ITEMS = 16;                 // pairs per thread
+#ifndef M2S_SORT_ITEMS
+#define M2S_SORT_ITEMS 16
+#endif
+#ifndef M2S_SORT_MIN_BLOCKS32
+#define M2S_SORT_MIN_BLOCKS32 4
+#endif
+constexpr int ITEMS = M2S_SORT_ITEMS;     // pairs per thread (even)
 constexpr int TILE = THREADS * ITEMS;     // 4096 pairs per block
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
@@ -164,7 +170,7 @@ static __global__ void __launch_bounds__(RADIX) k_sort_digit_offsets(uint32_t* _
 // One pass over one digit. src yields the keys of this pass (an array or, in pass 0, anything computed per element);
 // vals_in == nullptr means "the payload is the element's position".
 template <typename K, typename Src>
-__global__ void __launch_bounds__(THREADS, sizeof(K) == 4 ? 4 : 3)
+__global__ void __launch_bounds__(THREADS, sizeof(K) == 4 ? M2S_SORT_MIN_BLOCKS32 : M2S_SORT_MIN_BLOCKS32 - 1)
 k_sort_onesweep(Src src, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 uint32_t n, int shift, int pass, const uint32_t* __restrict__ digit_base /* [RADIX] exclusive */,
                 uint32_t* __restrict__ tile_counter, unsigned long long* __restrict__ lookback) {
